@@ -1,0 +1,265 @@
+// core.cu — library plumbing, row norms / normalisation, candidate-list merge.
+#include "frb_common.cuh"
+
+#include <mutex>
+#include <utility>
+#include <vector>
+
+namespace frb {
+
+// ---- launch profiling (frb_profile_enable / frb_profile_read) ------------------------------------
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof[FRB_K_COUNT];
+
+ProfileScope::ProfileScope(int kernel_id, cudaStream_t st) : kernel(kernel_id), stream(st), start(nullptr), stop(nullptr), on(false)
+{
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof_on) return;
+    if (cudaEventCreate(&start) != cudaSuccess || cudaEventCreate(&stop) != cudaSuccess) return;
+    on = true;
+    cudaEventRecord(start, stream);
+}
+
+ProfileScope::~ProfileScope()
+{
+    if (!on) return;
+    cudaEventRecord(stop, stream);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof[kernel].push_back({start, stop});
+}
+
+static thread_local char g_err[512] = "";
+
+char *last_error_buf() { return g_err; }
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count()
+{
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (dev != cached_dev) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
+        cached = p.multiProcessorCount;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One warp per row: sum of squares with 128-bit loads + shuffle reduction.
+// sqrt of the fp32 sum of squares, accumulated pairwise in fp32 (numpy's nrm2 is also fp32).
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float row_sumsq(const float *__restrict__ row, int dim, int lane)
+{
+    float acc = 0.f;
+    if ((dim & 3) == 0 && ((uintptr_t)row & 15) == 0) {
+        const float4 *r4 = reinterpret_cast<const float4 *>(row);
+        for (int i = lane; i < dim / 4; i += 32) {
+            float4 v = __ldg(r4 + i);
+            acc = fmaf(v.x, v.x, acc);
+            acc = fmaf(v.y, v.y, acc);
+            acc = fmaf(v.z, v.z, acc);
+            acc = fmaf(v.w, v.w, acc);
+        }
+    } else {
+        for (int i = lane; i < dim; i += 32) {
+            float v = __ldg(row + i);
+            acc = fmaf(v, v, acc);
+        }
+    }
+    return warp_sum(acc);
+}
+
+__global__ void __launch_bounds__(256) row_norms_kernel(const float *__restrict__ x, int64_t rows, int dim,
+                                                        float *__restrict__ out)
+{
+    int lane = threadIdx.x & 31;
+    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        float ss = row_sumsq(x + r * dim, dim, lane);
+        if (lane == 0) out[r] = sqrtf(ss);
+    }
+}
+
+template <typename OutT>
+__device__ __forceinline__ OutT cast_out(float v);
+template <>
+__device__ __forceinline__ float cast_out<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 cast_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) normalize_rows_kernel(const float *__restrict__ x, int64_t rows, int dim,
+                                                             int mode, OutT *__restrict__ out)
+{
+    int lane = threadIdx.x & 31;
+    int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        const float *row = x + r * dim;
+        float denom = 1.f;
+        if (mode != FRB_QNORM_NONE) {
+            float n = sqrtf(row_sumsq(row, dim, lane));
+            denom = (mode == FRB_QNORM_CLAMP) ? fmaxf(n, 1e-12f) : (n + 1e-8f);
+        }
+        OutT *o = out + r * dim;
+        for (int i = lane; i < dim; i += 32) {
+            float v = __ldg(row + i);
+            o[i] = cast_out<OutT>(mode == FRB_QNORM_NONE ? v : __fdiv_rn(v, denom));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One thread per query merges n_lists sorted candidate lists of length k (k <= FRB_MAX_K).
+template <bool LARGEST>
+__global__ void __launch_bounds__(128) topk_merge_kernel(const float *__restrict__ cs, const int64_t *__restrict__ ci,
+                                                         int n_lists, int64_t n_query, int k,
+                                                         float *__restrict__ os, int64_t *__restrict__ oi)
+{
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_query) return;
+    float s[FRB_MAX_K];
+    int64_t id[FRB_MAX_K];
+    list_init<LARGEST>(s, id, k);
+    for (int l = 0; l < n_lists; l++) {
+        const float *ls = cs + ((int64_t)l * n_query + q) * k;
+        const int64_t *li = ci + ((int64_t)l * n_query + q) * k;
+        for (int j = 0; j < k; j++) {
+            float v = ls[j];
+            int64_t idx = li[j];
+            if (idx < 0) continue;
+            if (!better<LARGEST>(v, idx, s[k - 1], id[k - 1])) continue;
+            int p = k - 1;
+            while (p > 0 && better<LARGEST>(v, idx, s[p - 1], id[p - 1])) {
+                s[p] = s[p - 1];
+                id[p] = id[p - 1];
+                --p;
+            }
+            s[p] = v;
+            id[p] = idx;
+        }
+    }
+    for (int j = 0; j < k; j++) {
+        os[q * k + j] = s[j];
+        oi[q * k + j] = id[j];
+    }
+}
+
+}  // namespace frb
+
+using namespace frb;
+
+extern "C" {
+
+int frb_version(void) { return 100; }
+
+int frb_profile_enable(int on)
+{
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = on != 0;
+    return FRB_OK;
+}
+
+int frb_profile_read(int kernel, float *total_ms, int *launches)
+{
+    FRB_CHECK_ARG(kernel >= 0 && kernel < FRB_K_COUNT, "frb_profile_read: kernel=%d", kernel);
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        ev.swap(g_prof[kernel]);
+    }
+    float total = 0.f;
+    for (auto &e : ev) {
+        float ms = 0.f;
+        FRB_CUDA_OK(cudaEventSynchronize(e.second));
+        FRB_CUDA_OK(cudaEventElapsedTime(&ms, e.first, e.second));
+        total += ms;
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+    if (total_ms) *total_ms = total;
+    if (launches) *launches = (int)ev.size();
+    return FRB_OK;
+}
+
+const char *frb_last_error(void) { return last_error_buf(); }
+
+int frb_device_info(int *sm, int *major, int *minor)
+{
+    int dev = 0;
+    FRB_CUDA_OK(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    FRB_CUDA_OK(cudaGetDeviceProperties(&p, dev));
+    if (sm) *sm = p.multiProcessorCount;
+    if (major) *major = p.major;
+    if (minor) *minor = p.minor;
+    return FRB_OK;
+}
+
+int frb_row_norms_f32(const float *x, int64_t rows, int dim, float *out, void *stream)
+{
+    FRB_CHECK_ARG(rows >= 0 && dim > 0, "frb_row_norms_f32: rows=%lld dim=%d", (long long)rows, dim);
+    if (rows == 0) return FRB_OK;
+    FRB_CHECK_ARG(x && out, "frb_row_norms_f32: null pointer");
+    int64_t blocks = (rows + 7) / 8;
+    int grid = (int)(blocks < (int64_t)sm_count() * 8 ? blocks : (int64_t)sm_count() * 8);
+    if (grid < 1) grid = 1;
+    row_norms_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, dim, out);
+    FRB_LAUNCH_OK("row_norms_kernel");
+    return FRB_OK;
+}
+
+int frb_normalize_rows(const float *x, int64_t rows, int dim, int mode, void *out, int out_dtype, void *stream)
+{
+    FRB_CHECK_ARG(rows >= 0 && dim > 0, "frb_normalize_rows: rows=%lld dim=%d", (long long)rows, dim);
+    FRB_CHECK_ARG(mode >= FRB_QNORM_NONE && mode <= FRB_QNORM_EPS, "frb_normalize_rows: mode=%d", mode);
+    FRB_CHECK_ARG(out_dtype == FRB_F32 || out_dtype == FRB_BF16, "frb_normalize_rows: out_dtype=%d", out_dtype);
+    if (rows == 0) return FRB_OK;
+    FRB_CHECK_ARG(x && out, "frb_normalize_rows: null pointer");
+    int64_t blocks = (rows + 7) / 8;
+    int grid = (int)(blocks < (int64_t)sm_count() * 8 ? blocks : (int64_t)sm_count() * 8);
+    if (grid < 1) grid = 1;
+    if (out_dtype == FRB_F32)
+        normalize_rows_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, dim, mode, (float *)out);
+    else
+        normalize_rows_kernel<__nv_bfloat16>
+            <<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, dim, mode, (__nv_bfloat16 *)out);
+    FRB_LAUNCH_OK("normalize_rows_kernel");
+    return FRB_OK;
+}
+
+int frb_topk_merge(const float *cs, const int64_t *ci, int n_lists, int64_t n_query, int k, int largest,
+                   float *os, int64_t *oi, void *stream)
+{
+    FRB_CHECK_ARG(n_lists >= 1 && n_query >= 0 && k >= 1 && k <= FRB_MAX_K,
+                  "frb_topk_merge: n_lists=%d n_query=%lld k=%d", n_lists, (long long)n_query, k);
+    if (n_query == 0) return FRB_OK;
+    FRB_CHECK_ARG(cs && ci && os && oi, "frb_topk_merge: null pointer");
+    int grid = (int)((n_query + 127) / 128);
+    if (largest)
+        topk_merge_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(cs, ci, n_lists, n_query, k, os, oi);
+    else
+        topk_merge_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(cs, ci, n_lists, n_query, k, os, oi);
+    FRB_LAUNCH_OK("topk_merge_kernel");
+    return FRB_OK;
+}
+
+}  // extern "C"

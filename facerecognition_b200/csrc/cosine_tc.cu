@@ -1,0 +1,441 @@
+// cosine_tc.cu — K1 (bf16): similarity GEMM on tcgen05 tensor cores with a fused per-query top-k.
+//
+// Replaces, for bf16 galleries, the np.dot(E, P.T) + argsort of the reference's batched evaluation
+// (notebooks/evaluate_arcface_kaggle.ipynb:618,713), faiss.IndexFlatIP.search
+// (inference/recognition_engine.py:304) and the per-identity loops (recognition_engine.py:277-289,
+// web_app.py:545-554).  The Q x N score matrix lives only in TMEM: it never reaches shared or global
+// memory.
+//
+// Shape.  D[128 queries x 256 gallery rows] += A[128 x 16] * B[256 x 16]^T, bf16 in, fp32 accumulate,
+// one tcgen05.mma per 16 of K, issued by one thread.  Queries sit on the M axis so that TMEM lane ==
+// query: an epilogue thread owns one query and streams that query's scores out of TMEM with
+// tcgen05.ld, keeping its best-k list privately (no cross-thread traffic for the selection).
+//
+// Work unit = (128-query tile qt, group of G consecutive 256-row gallery tiles); unit id u = group * n_qt
+// + qt, CTA p takes u = p, p + grid, ...  Units running at the same time therefore share their gallery
+// group, which is read from HBM once and from L2 by the other query tiles.
+//
+// Warp roles (256 threads):  warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane),
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM lanes 32*(w%4)..+31).
+// Shared memory: A = the unit's 128 x dim query tile (dim/64 k-blocks of 16 KB, resident for the unit),
+// B = ring of 32 KB stages (256 rows x 64 of K), both 128-byte swizzled K-major as written by TMA.
+// TMEM: 2 accumulator stages x 256 columns, so the epilogue of tile t overlaps the MMAs of tile t+1.
+#include "frb_common.cuh"
+
+#include <cuda.h>  // CUtensorMap + enums (types only; the encode entry point is fetched at run time)
+
+namespace frb {
+
+constexpr int kTcBlockM = 128;   // queries per tile (TMEM lanes)
+constexpr int kTcBlockN = 256;   // gallery rows per tile (TMEM columns per accumulator stage)
+constexpr int kTcBlockK = 64;    // bf16 elements per 128-byte swizzle row
+constexpr int kTcUmmaK = 16;
+constexpr int kTcThreads = 256;
+constexpr int kTcMaxKBlocks = 8;  // dim <= 512
+constexpr uint32_t kTcABytesPerKb = kTcBlockM * kTcBlockK * 2;  // 16 KB
+constexpr uint32_t kTcBBytesPerStage = kTcBlockN * kTcBlockK * 2;  // 32 KB
+constexpr int kTcMaxStages = 8;
+constexpr size_t kTcSmemLimit = 227 * 1024;
+
+struct TcBarriers {
+    uint64_t full[kTcMaxStages];
+    uint64_t empty[kTcMaxStages];
+    uint64_t a_full, a_empty;
+    uint64_t tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive columns of fp32 accumulators -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float *v)
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
+// start>>4 | LBO(16 B units)=1 <<16 | SBO = 1024 B (8 rows x 128 B) >>4 <<32 | version 1 <<46 | layout 2 <<61
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr)
+{
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// kind::f16 instruction descriptor: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), both K-major, N>>3 at 17, M>>4 at 24
+constexpr uint32_t kTcIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcBlockN >> 3) << 17) | ((uint32_t)(kTcBlockM >> 4) << 24);
+
+struct TcParams {
+    int64_t n_query, n_gallery;
+    int k_blocks;          // dim / 64
+    int stages;            // B ring depth
+    int64_t n_qtiles, n_tiles, tiles_per_group, n_groups;
+    int k;
+    int64_t idx_base;
+    float *cand_scores;    // [n_groups, n_query, k]
+    int64_t *cand_idx;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g, const TcParams p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B atoms need 1024-byte alignment
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *smem_a = smem;
+    unsigned char *smem_b = smem + (size_t)p.k_blocks * kTcABytesPerKb;
+    TcBarriers *bars = reinterpret_cast<TcBarriers *>(smem_b + (size_t)p.stages * kTcBBytesPerStage);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_units = p.n_qtiles * p.n_groups;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_g) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; s++) {
+            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->empty[s], 1);
+        }
+        mbar_init(&bars->a_full, 1);
+        mbar_init(&bars->a_empty, 1);
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&bars->tmem_full[s], 1);
+            mbar_init(&bars->tmem_empty[s], 4);  // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, a_phase = 0;
+            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const int64_t qt = u % p.n_qtiles, grp = u / p.n_qtiles;
+                const int64_t t0 = grp * p.tiles_per_group;
+                const int64_t t1 = (t0 + p.tiles_per_group < p.n_tiles) ? t0 + p.tiles_per_group : p.n_tiles;
+                mbar_wait(&bars->a_empty, a_phase ^ 1);  // previous unit's MMAs have finished reading A
+                mbar_expect_tx(&bars->a_full, (uint32_t)p.k_blocks * kTcABytesPerKb);
+                for (int kb = 0; kb < p.k_blocks; kb++)
+                    tma_load_2d(smem_a + (size_t)kb * kTcABytesPerKb, &tmap_q, &bars->a_full, kb * kTcBlockK, (int)(qt * kTcBlockM));
+                a_phase ^= 1;
+                for (int64_t t = t0; t < t1; t++) {
+                    for (int kb = 0; kb < p.k_blocks; kb++) {
+                        mbar_wait(&bars->empty[stage], phase ^ 1);
+                        mbar_expect_tx(&bars->full[stage], kTcBBytesPerStage);
+                        tma_load_2d(smem_b + (size_t)stage * kTcBBytesPerStage, &tmap_g, &bars->full[stage], kb * kTcBlockK,
+                                    (int)(t * kTcBlockN));
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, a_phase = 0, acc_phase = 0;
+            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const int64_t grp = u / p.n_qtiles;
+                const int64_t t0 = grp * p.tiles_per_group;
+                const int64_t t1 = (t0 + p.tiles_per_group < p.n_tiles) ? t0 + p.tiles_per_group : p.n_tiles;
+                mbar_wait(&bars->a_full, a_phase);
+                a_phase ^= 1;
+                tcgen05_fence_after();
+                for (int64_t t = t0; t < t1; t++) {
+                    mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);  // epilogue drained this accumulator
+                    tcgen05_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)acc * kTcBlockN;
+                    for (int kb = 0; kb < p.k_blocks; kb++) {
+                        mbar_wait(&bars->full[stage], phase);
+                        tcgen05_fence_after();
+                        const uint64_t da = make_sw128_desc(smem_u32(smem_a + (size_t)kb * kTcABytesPerKb));
+                        const uint64_t db = make_sw128_desc(smem_u32(smem_b + (size_t)stage * kTcBBytesPerStage));
+#pragma unroll
+                        for (int k4 = 0; k4 < kTcBlockK / kTcUmmaK; k4++) {
+                            // advance 16 elements (32 B) along K inside the 128-byte swizzle row: +2 in 16-byte units
+                            umma_bf16(tmem_d, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), kTcIdesc, (kb | k4) != 0 ? 1u : 0u);
+                        }
+                        tcgen05_commit(&bars->empty[stage]);  // stage reusable once these MMAs retire
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                    tcgen05_commit(&bars->tmem_full[acc]);  // accumulator ready for the epilogue
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+                tcgen05_commit(&bars->a_empty);  // A may be overwritten by the next unit
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: TMEM -> registers -> per-query best-k =====================
+        const int ew = warp & 3;                       // TMEM lane quadrant this warp may read
+        const int row = ew * 32 + lane;                // query row inside the tile == TMEM lane
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        float best_s[FRB_MAX_K];
+        int64_t best_i[FRB_MAX_K];
+        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int64_t qt = u % p.n_qtiles, grp = u / p.n_qtiles;
+            const int64_t t0 = grp * p.tiles_per_group;
+            const int64_t t1 = (t0 + p.tiles_per_group < p.n_tiles) ? t0 + p.tiles_per_group : p.n_tiles;
+            list_init<true>(best_s, best_i, p.k);
+            float kth = -INFINITY;
+            for (int64_t t = t0; t < t1; t++) {
+                mbar_wait(&bars->tmem_full[acc], acc_phase);
+                tcgen05_fence_after();
+                const int64_t n0 = t * kTcBlockN;
+                const int valid = (int)((p.n_gallery - n0) < kTcBlockN ? (p.n_gallery - n0) : kTcBlockN);
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kTcBlockN;
+#pragma unroll 1
+                for (int c0 = 0; c0 < kTcBlockN; c0 += 32) {
+                    float v[32];
+                    tmem_ld_32x32(taddr + (uint32_t)c0, v);
+                    if (c0 + 32 <= valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if (v[j] > kth) kth = list_insert_stream<true>(best_s, best_i, p.k, v[j], p.idx_base + n0 + c0 + j);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if (c0 + j < valid && v[j] > kth)
+                                kth = list_insert_stream<true>(best_s, best_i, p.k, v[j], p.idx_base + n0 + c0 + j);
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            const int64_t q = qt * kTcBlockM + row;
+            if (q < p.n_query) {
+                const int64_t o = (grp * p.n_query + q) * p.k;
+                for (int j = 0; j < p.k; j++) {
+                    p.cand_scores[o + j] = best_s[j];
+                    p.cand_idx[o + j] = best_i[j];
+                }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+// row-major bf16 [rows, dim] -> boxes of (64 of K) x box_rows rows, 128-byte swizzled, zero fill out of bounds
+static int make_bf16_map(CUtensorMap *map, const void *base, int64_t rows, int dim, int box_rows)
+{
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+        return FRB_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)dim, (cuuint64_t)(rows > 0 ? rows : 1)};
+    cuuint64_t strides[1] = {(cuuint64_t)dim * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kTcBlockK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld dim=%d)", (int)r, (long long)rows, dim);
+        return FRB_ERR_CUDA;
+    }
+    return FRB_OK;
+}
+
+struct TcPlan {
+    int64_t n_qtiles, n_tiles, tiles_per_group, n_groups;
+    size_t qbf16_bytes, idx_bytes, score_bytes;
+};
+
+static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
+{
+    TcPlan pl;
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    pl.n_qtiles = (nq + kTcBlockM - 1) / kTcBlockM;
+    pl.n_tiles = (ng + kTcBlockN - 1) / kTcBlockN;
+    if (pl.n_tiles < 1) pl.n_tiles = 1;
+    // ~16 units per CTA for balance; a unit's gallery group is shared (through L2) by all query tiles
+    int64_t want_groups = ((int64_t)sms * 16 + pl.n_qtiles - 1) / pl.n_qtiles;
+    if (want_groups > pl.n_tiles) want_groups = pl.n_tiles;
+    if (want_groups > 1024) want_groups = 1024;
+    if (want_groups < 1) want_groups = 1;
+    pl.tiles_per_group = (pl.n_tiles + want_groups - 1) / want_groups;
+    pl.n_groups = (pl.n_tiles + pl.tiles_per_group - 1) / pl.tiles_per_group;
+    size_t n = (size_t)pl.n_groups * (size_t)nq * (size_t)k;
+    pl.qbf16_bytes = align_up((size_t)pl.n_qtiles * kTcBlockM * (size_t)dim * 2, 1024);
+    pl.idx_bytes = align_up(n * sizeof(int64_t), 256);
+    pl.score_bytes = align_up(n * sizeof(float), 256);
+    return pl;
+}
+
+size_t cosine_tc_workspace_bytes(int64_t n_query, int64_t n_gallery, int dim, int k)
+{
+    TcPlan pl = tc_plan(n_query, n_gallery, dim, k);
+    return pl.qbf16_bytes + pl.idx_bytes + pl.score_bytes;
+}
+
+int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16, int64_t ng, int dim, int qnorm_mode, int k,
+                     int64_t idx_base, float *out_scores, int64_t *out_idx, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    (void)ws_bytes;
+    if (dim % kTcBlockK != 0 || dim / kTcBlockK > kTcMaxKBlocks) {
+        set_error("bf16 tensor-core path: dim=%d must be a multiple of 64 and <= 512", dim);
+        return FRB_ERR_UNSUPPORTED;
+    }
+    int dev = 0, major = 0;
+    FRB_CUDA_OK(cudaGetDevice(&dev));
+    FRB_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) {
+        set_error("bf16 tensor-core path needs an sm_100-class GPU (tcgen05); device is sm_%d", major * 10);
+        return FRB_ERR_UNSUPPORTED;
+    }
+    TcPlan pl = tc_plan(nq, ng, dim, k);
+    char *w = (char *)ws;
+    __nv_bfloat16 *qb = (__nv_bfloat16 *)w;
+    int64_t *ci = (int64_t *)(w + pl.qbf16_bytes);
+    float *cs = (float *)(w + pl.qbf16_bytes + pl.idx_bytes);
+
+    // prologue: L2-normalise in fp32, round to bf16 (rows beyond n_query are never read: TMA zero-fills)
+    int rc = frb_normalize_rows(queries, nq, dim, qnorm_mode, qb, FRB_BF16, st);
+    if (rc != FRB_OK) return rc;
+
+    CUtensorMap tq, tg;
+    rc = make_bf16_map(&tq, qb, nq, dim, kTcBlockM);
+    if (rc != FRB_OK) return rc;
+    rc = make_bf16_map(&tg, ng > 0 ? gallery_bf16 : (const void *)qb, ng, dim, kTcBlockN);
+    if (rc != FRB_OK) return rc;
+
+    TcParams p;
+    p.n_query = nq;
+    p.n_gallery = ng;
+    p.k_blocks = dim / kTcBlockK;
+    const size_t a_bytes = (size_t)p.k_blocks * kTcABytesPerKb;
+    int stages = (int)((kTcSmemLimit - 1024 - sizeof(TcBarriers) - a_bytes) / kTcBBytesPerStage);
+    if (stages > kTcMaxStages) stages = kTcMaxStages;
+    if (stages < 2) {
+        set_error("bf16 tensor-core path: not enough shared memory for 2 gallery stages");
+        return FRB_ERR_UNSUPPORTED;
+    }
+    p.stages = stages;
+    p.n_qtiles = pl.n_qtiles;
+    p.n_tiles = pl.n_tiles;
+    p.tiles_per_group = pl.tiles_per_group;
+    p.n_groups = pl.n_groups;
+    p.k = k;
+    p.idx_base = idx_base;
+    p.cand_scores = cs;
+    p.cand_idx = ci;
+    const size_t smem = 1024 + a_bytes + (size_t)stages * kTcBBytesPerStage + sizeof(TcBarriers);
+    FRB_CUDA_OK(cudaFuncSetAttribute(cosine_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = sm_count();
+    int64_t n_units = pl.n_qtiles * pl.n_groups;
+    int grid = (int)(n_units < sms ? n_units : sms);
+    if (ng == 0) {
+        // nothing to scan: emit empty lists through the merge of zero-row groups
+        p.n_tiles = 0;
+    }
+    {
+        ProfileScope prof(FRB_K_COSINE_TC, st);
+        cosine_tc_kernel<<<grid, kTcThreads, smem, st>>>(tq, tg, p);
+    }
+    FRB_LAUNCH_OK("cosine_tc_kernel");
+    return frb_topk_merge(cs, ci, (int)pl.n_groups, nq, k, /*largest=*/1, out_scores, out_idx, st);
+}
+
+}  // namespace frb

@@ -1,0 +1,155 @@
+"""Tensor-level wrappers over the libfrb200 C ABI.
+
+PyTorch is used here for device memory, streams and nothing else: every function takes CUDA
+tensors, passes raw device pointers + the current stream to the C entry point named in its
+docstring, and returns CUDA tensors.  No arithmetic is done in torch.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native as N
+
+_I64 = ctypes.c_int64
+
+
+def _require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise ValueError("facerecognition_b200 kernels take CUDA tensors (there is no CPU path)")
+        if not t.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ValueError(f"tensors on different devices: {dev} vs {t.device}")
+    return dev
+
+
+def _p(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else ctypes.c_void_p(0)
+
+
+def _stream(dev: torch.device):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def row_norms(x: torch.Tensor) -> torch.Tensor:
+    """frb_row_norms_f32: fp32 [R, D] -> fp32 [R] L2 norms."""
+    dev = _require_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2
+    out = torch.empty(x.shape[0], dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        N.call("frb_row_norms_f32", _p(x), _I64(x.shape[0]), x.shape[1], _p(out), _stream(dev))
+    return out
+
+
+def normalize_rows(x: torch.Tensor, mode: int = N.FRB_QNORM_EPS, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """frb_normalize_rows: fp32 [R, D] -> fp32|bf16 [R, D], x/max(|x|,1e-12) (CLAMP) or x/(|x|+1e-8) (EPS)."""
+    dev = _require_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2
+    assert out_dtype in (torch.float32, torch.bfloat16)
+    out = torch.empty(x.shape, dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        N.call("frb_normalize_rows", _p(x), _I64(x.shape[0]), x.shape[1], mode, _p(out),
+               N.FRB_F32 if out_dtype == torch.float32 else N.FRB_BF16, _stream(dev))
+    return out
+
+
+def cosine_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, *, score_mode: int = N.FRB_SCORE_IP,
+                qnorm_mode: int = N.FRB_QNORM_NONE, q_norms: Optional[torch.Tensor] = None,
+                g_norms: Optional[torch.Tensor] = None, idx_base: int = 0,
+                out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """frb_cosine_topk: fp32 queries [Q, D] x fp32|bf16 gallery [N, D] -> (scores fp32 [Q, k], idx int64 [Q, k])."""
+    dev = _require_cuda(queries, gallery, q_norms, g_norms)
+    assert queries.dtype == torch.float32 and queries.dim() == 2 and gallery.dim() == 2
+    assert gallery.dtype in (torch.float32, torch.bfloat16)
+    assert gallery.shape[0] == 0 or gallery.shape[1] == queries.shape[1]
+    q, d, n = queries.shape[0], queries.shape[1], gallery.shape[0]
+    gdt = N.FRB_F32 if gallery.dtype == torch.float32 else N.FRB_BF16
+    if out is None:
+        scores = torch.empty((q, k), dtype=torch.float32, device=dev)
+        idx = torch.empty((q, k), dtype=torch.int64, device=dev)
+    else:
+        scores, idx = out
+    with torch.cuda.device(dev):
+        ws_bytes = N.lib.frb_cosine_topk_workspace_bytes(q, n, d, gdt, k)
+        ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=dev)
+        N.call("frb_cosine_topk", _p(queries), _I64(q), _p(gallery), gdt, _I64(n), d, _p(q_norms), _p(g_norms),
+               score_mode, qnorm_mode, k, _I64(idx_base), _p(scores), _p(idx), _p(ws), ctypes.c_size_t(ws.numel()),
+               _stream(dev))
+    return scores, idx
+
+
+def topk_merge(cand_scores: torch.Tensor, cand_idx: torch.Tensor, largest: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """frb_topk_merge: [R, Q, k] candidate lists -> best [Q, k] (ties -> lowest idx; idx < 0 is padding)."""
+    dev = _require_cuda(cand_scores, cand_idx)
+    assert cand_scores.dtype == torch.float32 and cand_idx.dtype == torch.int64
+    assert cand_scores.dim() == 3 and cand_scores.shape == cand_idx.shape
+    r, q, k = cand_scores.shape
+    scores = torch.empty((q, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((q, k), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        N.call("frb_topk_merge", _p(cand_scores), _p(cand_idx), r, _I64(q), k, 1 if largest else 0, _p(scores), _p(idx),
+               _stream(dev))
+    return scores, idx
+
+
+def lbp_codes(images: torch.Tensor, radius: int = 1, neighbors: int = 8) -> torch.Tensor:
+    """frb_lbp_codes_u8: u8 [B, H, W] -> u8 [B, H-2, W-2] LBP codes (OpenCV elbp_ semantics)."""
+    dev = _require_cuda(images)
+    assert images.dtype == torch.uint8 and images.dim() == 3
+    b, h, w = images.shape
+    out = torch.empty((b, max(h - 2, 0), max(w - 2, 0)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.call("frb_lbp_codes_u8", _p(images), _I64(b), h, w, radius, neighbors, _p(out), _stream(dev))
+    return out
+
+
+def lbp_hist(images: torch.Tensor, radius: int = 1, neighbors: int = 8, grid_x: int = 8, grid_y: int = 8
+             ) -> Tuple[torch.Tensor, int]:
+    """frb_lbp_hist_u8: u8 [B, H, W] -> (u16 [B, grid_x*grid_y*256] cell histograms, pixels per cell)."""
+    dev = _require_cuda(images)
+    assert images.dtype == torch.uint8 and images.dim() == 3
+    b, h, w = images.shape
+    out = torch.empty((b, grid_x * grid_y * 256), dtype=torch.uint16, device=dev)
+    cell_px = ctypes.c_int(0)
+    with torch.cuda.device(dev):
+        N.call("frb_lbp_hist_u8", _p(images), _I64(b), h, w, radius, neighbors, grid_x, grid_y, _p(out),
+               ctypes.byref(cell_px), _stream(dev))
+    return out, cell_px.value
+
+
+def chisq_topk(q_hist: torch.Tensor, q_cell_px: int, gallery: torch.Tensor, g_cell_px: int, k: int = 1,
+               idx_base: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """frb_chisq_topk: u16 [Q, L] vs u16 [N, L] -> (dist fp32 [Q, k] ascending, idx int64 [Q, k])."""
+    dev = _require_cuda(q_hist, gallery)
+    assert q_hist.dtype == torch.uint16 and gallery.dtype == torch.uint16 and q_hist.dim() == 2 and gallery.dim() == 2
+    q, hist_len, n = q_hist.shape[0], q_hist.shape[1], gallery.shape[0]
+    assert n == 0 or gallery.shape[1] == hist_len
+    dist = torch.empty((q, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((q, k), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        ws_bytes = N.lib.frb_chisq_topk_workspace_bytes(q, n, hist_len, k)
+        ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=dev)
+        N.call("frb_chisq_topk", _p(q_hist), _I64(q), q_cell_px, _p(gallery), _I64(n), hist_len, g_cell_px, k,
+               _I64(idx_base), _p(dist), _p(idx), _p(ws), ctypes.c_size_t(ws.numel()), _stream(dev))
+    return dist, idx
+
+
+def chisq_dist(q_hist: torch.Tensor, q_cell_px: int, gallery: torch.Tensor, g_cell_px: int) -> torch.Tensor:
+    """frb_chisq_dist: all distances, fp32 [Q, N]."""
+    dev = _require_cuda(q_hist, gallery)
+    assert q_hist.dtype == torch.uint16 and gallery.dtype == torch.uint16
+    q, hist_len, n = q_hist.shape[0], q_hist.shape[1], gallery.shape[0]
+    out = torch.empty((q, n), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        N.call("frb_chisq_dist", _p(q_hist), _I64(q), q_cell_px, _p(gallery), _I64(n), hist_len, g_cell_px, _p(out),
+               _stream(dev))
+    return out

@@ -1,0 +1,385 @@
+"""B200 drop-in for the reference's cosine identification stage.
+
+Mirrors inference/recognition_engine.py of sin0235/FaceRecognition: same class name, constructor
+arguments, method names, return shapes, sentinel returns and threshold rule; the per-identity Python
+loops are replaced by one fused similarity + top-k kernel call (libfrb200 frb_cosine_topk).
+
+  cosine_similarity(a, b)                         inference/recognition_engine.py:41-63
+  RecognitionEngine.recognize_with_db(emb)        :267-289   (dict DB, reference cosine rule, top-5)
+  RecognitionEngine.recognize_with_faiss(emb, k)  :291-326   (flat inner-product index)
+  RecognitionEngine.recognize / recognize_batch   :328-389
+  RecognitionEngine.add_to_db / save_db / ...     :391-435
+  match_facenet(db, embedding, threshold)         web_app.py:537-562 (inline FaceNet matcher)
+
+Out of scope: detection, alignment and the embedding network.  `recognize()` therefore
+takes its embeddings from an injected `embedder` callable (image -> float32[512] or None); with no
+embedder it returns the same status='error' dict the reference returns when no checkpoint is loaded.
+
+Batched entry points (new): recognize_embeddings(E), FlatIPIndex.search(E, k) — Q queries, one launch.
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import formats, ops
+
+
+def _match_device(device: Optional[str]) -> torch.device:
+    if device is not None and str(device).startswith("cuda"):
+        return torch.device(device)
+    return torch.device("cuda")
+
+
+def _to_dev(a: np.ndarray, dev: torch.device) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+
+
+def cosine_similarity(a: np.ndarray, b: np.ndarray) -> float:
+    """inference/recognition_engine.py:41-63, evaluated by the CUDA kernel (Q = N = 1):
+    0.0 if either norm is 0; raw dot if both norms are within 1e-3 of 1; else dot/(na*nb)."""
+    dev = torch.device("cuda")
+    qa = _to_dev(np.asarray(a).astype(np.float32).reshape(1, -1), dev)
+    gb = _to_dev(np.asarray(b).astype(np.float32).reshape(1, -1), dev)
+    if qa.shape[1] % 8:
+        pad = 8 - qa.shape[1] % 8
+        qa = torch.nn.functional.pad(qa, (0, pad)).contiguous()
+        gb = torch.nn.functional.pad(gb, (0, pad)).contiguous()
+    s, _ = ops.cosine_topk(qa, gb, 1, score_mode=N.FRB_SCORE_REF_COSINE, q_norms=ops.row_norms(qa),
+                           g_norms=ops.row_norms(gb))
+    return float(s[0, 0].item())
+
+
+class _GalleryDict(dict):
+    """dict that counts mutations so the device copy can be refreshed lazily; the reference's callers
+    read and write engine.db directly (web_app.py:545, recognition_engine.py:419)."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.version = 0
+
+    def _bump(self):
+        self.version += 1
+
+    def __setitem__(self, k, v):
+        super().__setitem__(k, v); self._bump()
+
+    def __delitem__(self, k):
+        super().__delitem__(k); self._bump()
+
+    def update(self, *a, **kw):
+        super().update(*a, **kw); self._bump()
+
+    def pop(self, *a):
+        r = super().pop(*a); self._bump(); return r
+
+    def popitem(self):
+        r = super().popitem(); self._bump(); return r
+
+    def clear(self):
+        super().clear(); self._bump()
+
+    def setdefault(self, k, d=None):
+        r = super().setdefault(k, d); self._bump(); return r
+
+
+class DeviceGallery:
+    """Row-major fp32 [N, D] copy of a {name: vector} dict on the GPU, with per-row norms.
+    Row i <-> i-th dict key (insertion order), which is what makes ties resolve as the reference's
+    stable sort does."""
+
+    def __init__(self, db: Dict[str, np.ndarray], device: torch.device):
+        self.names: List[str] = list(db.keys())
+        if self.names:
+            mat = np.stack([np.asarray(db[n]).astype(np.float32).flatten() for n in self.names], 0)
+        else:
+            mat = np.zeros((0, 8), np.float32)
+        self.dim = mat.shape[1]
+        self.rows = _to_dev(mat, device)
+        self.norms = ops.row_norms(self.rows) if len(self.names) else torch.zeros(0, device=device)
+        self._unit_rows = None
+
+    def unit_rows(self) -> torch.Tensor:
+        """rows / (||row|| + 1e-8) — web_app.py:549 normalises every db row this way."""
+        if self._unit_rows is None:
+            self._unit_rows = ops.normalize_rows(self.rows, N.FRB_QNORM_EPS)
+        return self._unit_rows
+
+
+class FlatIPIndex:
+    """GPU stand-in for faiss.IndexFlatIP as the reference uses it (inference/extract_embeddings.py:628-635,
+    inference/recognition_engine.py:304): .d, .ntotal, .add(x), .search(x, k) -> (scores, ids)."""
+
+    def __init__(self, d: int, device: Optional[str] = None, dtype: torch.dtype = torch.float32):
+        self.d = int(d)
+        self.device = _match_device(device)
+        self.dtype = dtype
+        self.rows = torch.zeros((0, self.d), dtype=dtype, device=self.device)
+
+    @property
+    def ntotal(self) -> int:
+        return int(self.rows.shape[0])
+
+    def add(self, x: np.ndarray) -> None:
+        x = _to_dev(np.asarray(x).reshape(-1, self.d), self.device)
+        if self.dtype == torch.bfloat16:
+            x = ops.normalize_rows(x, N.FRB_QNORM_NONE, torch.bfloat16)
+        self.rows = torch.cat([self.rows, x], 0).contiguous()
+
+    def search_device(self, x: torch.Tensor, k: int, qnorm_mode: int = N.FRB_QNORM_NONE):
+        return ops.cosine_topk(x, self.rows, k, score_mode=N.FRB_SCORE_IP, qnorm_mode=qnorm_mode)
+
+    def search(self, x: np.ndarray, k: int):
+        s, i = self.search_device(_to_dev(np.asarray(x).reshape(-1, self.d), self.device), k)
+        return s.cpu().numpy(), i.cpu().numpy()
+
+    @classmethod
+    def from_file(cls, path: str, device: Optional[str] = None) -> "FlatIPIndex":
+        rows = formats.read_faiss_flat_ip(path)
+        idx = cls(rows.shape[1], device)
+        idx.add(rows)
+        return idx
+
+    def write(self, path: str) -> None:
+        formats.write_faiss_flat_ip(path, self.rows.float().cpu().numpy())
+
+
+def build_faiss_index(embeddings: np.ndarray, output_path: str = None, use_gpu: bool = True,
+                      device: Optional[str] = None) -> FlatIPIndex:
+    """inference/extract_embeddings.py:595-645: rows / (||row|| + 1e-8), IndexFlatIP(dim).add, optional write."""
+    dev = _match_device(device)
+    e = _to_dev(np.asarray(embeddings).astype("float32"), dev)
+    index = FlatIPIndex(e.shape[1], str(dev))
+    index.rows = ops.normalize_rows(e, N.FRB_QNORM_EPS)
+    if output_path:
+        index.write(output_path)
+    return index
+
+
+class RecognitionEngine:
+    """Same surface as the reference's RecognitionEngine (inference/recognition_engine.py:66-435)."""
+
+    def __init__(
+        self,
+        model_path: str = "models/checkpoints/arcface/arcface_best.pth",
+        db_path: str = None,
+        faiss_index_path: str = None,
+        prototypes_path: str = None,
+        label_mapping_path: str = None,
+        device: str = None,
+        threshold: float = 0.5,
+        use_face_detection: bool = True,
+        embedder: Optional[Callable[[object], Optional[np.ndarray]]] = None,
+    ):
+        self.device = device or "cuda"
+        self.match_device = _match_device(device)
+        self.threshold = threshold
+        self.use_face_detection = use_face_detection
+        self.model_path = model_path
+        self.model = None           # the embedding network is out of scope; see `embedder`
+        self.embedder = embedder
+        self._db: Optional[_GalleryDict] = None
+        self._gallery: Optional[DeviceGallery] = None
+        self._gallery_version = -1
+        self.faiss_index: Optional[FlatIPIndex] = None
+        self.prototypes = None
+        self.label_to_id = None
+        self.id_to_label = None
+
+        if db_path and os.path.exists(db_path):
+            self.db = formats.load_embedding_db(db_path)
+            print(f"Loaded database: {len(self.db)} identities")
+        if faiss_index_path and os.path.exists(faiss_index_path):
+            self._load_faiss(faiss_index_path, prototypes_path, label_mapping_path)
+
+    # self.db stays a plain-looking dict for callers; assignments are wrapped so edits are noticed
+    @property
+    def db(self):
+        return self._db
+
+    @db.setter
+    def db(self, value):
+        if value is None:
+            self._db = None
+        elif isinstance(value, _GalleryDict):
+            self._db = value
+        else:
+            self._db = _GalleryDict(value)
+        self._gallery = None
+        self._gallery_version = -1
+
+    def _load_faiss(self, index_path: str, prototypes_path: str = None, mapping_path: str = None):
+        try:
+            self.faiss_index = FlatIPIndex.from_file(index_path, str(self.match_device))
+            print(f"Loaded FAISS index: {self.faiss_index.ntotal} vectors")
+        except Exception as e:  # same convention as the reference: report and carry on without an index
+            print(f"Loi load FAISS: {e}")
+            return
+        if prototypes_path and os.path.exists(prototypes_path):
+            self.prototypes = np.load(prototypes_path)
+            print(f"Loaded prototypes: {self.prototypes.shape}")
+        if mapping_path and os.path.exists(mapping_path):
+            self.label_to_id, self.id_to_label = formats.load_label_mapping(mapping_path)
+            print(f"Loaded label mapping: {len(self.label_to_id)} classes")
+
+    def set_threshold(self, threshold: float):
+        self.threshold = threshold
+
+    # ---- gallery on the device ---------------------------------------------------------------
+    def gallery(self) -> DeviceGallery:
+        if self._gallery is None or self._gallery_version != self._db.version:
+            self._gallery = DeviceGallery(self._db, self.match_device)
+            self._gallery_version = self._db.version
+        return self._gallery
+
+    # ---- matching -----------------------------------------------------------------------------
+    def _db_topk(self, emb: np.ndarray, k: int):
+        """(scores [Q, k], rows [Q, k]) on the host for Q query embeddings under the reference's cosine rule."""
+        g = self.gallery()
+        q = _to_dev(np.asarray(emb).astype(np.float32).reshape(-1, g.dim), self.match_device)
+        s, i = ops.cosine_topk(q, g.rows, k, score_mode=N.FRB_SCORE_REF_COSINE, q_norms=ops.row_norms(q), g_norms=g.norms)
+        return s.cpu().numpy(), i.cpu().numpy(), g.names
+
+    def _format_db_result(self, scores, rows, names):
+        top = [(names[j], float(s)) for s, j in zip(scores, rows) if j >= 0]
+        best_name, best_score = top[0]  # IndexError on an empty dict, as in the reference (:284)
+        if best_score < self.threshold:
+            return "Unknown", best_score, top
+        return best_name, best_score, top
+
+    def recognize_with_db(self, embedding: np.ndarray) -> Tuple[str, float, List[Tuple[str, float]]]:
+        """(best_name, best_score, top-5) — inference/recognition_engine.py:267-289."""
+        if self.db is None:
+            return "No database", 0.0, []
+        s, i, names = self._db_topk(embedding, 5)
+        return self._format_db_result(s[0], i[0], names)
+
+    def recognize_embeddings(self, embeddings: np.ndarray) -> List[Tuple[str, float, List[Tuple[str, float]]]]:
+        """Batched recognize_with_db: Q embeddings [Q, D] -> Q result tuples from ONE kernel launch."""
+        if self.db is None:
+            return [("No database", 0.0, [])] * len(embeddings)
+        s, i, names = self._db_topk(embeddings, 5)
+        return [self._format_db_result(s[r], i[r], names) for r in range(s.shape[0])]
+
+    def recognize_with_faiss(self, embedding: np.ndarray, k: int = 5) -> Tuple[str, float, List[Tuple[str, float]]]:
+        """inference/recognition_engine.py:291-326: e/(||e||+1e-8), IndexFlatIP.search, strict '<' threshold."""
+        if self.faiss_index is None:
+            return "No FAISS index", 0.0, []
+        q = _to_dev(np.asarray(embedding).astype(np.float32).reshape(1, -1), self.match_device)
+        scores, indices = self.faiss_index.search_device(q, k, qnorm_mode=N.FRB_QNORM_EPS)
+        scores, indices = scores.cpu().numpy().flatten(), indices.cpu().numpy().flatten()
+        results = []
+        for idx, score in zip(indices, scores):
+            if idx == -1:
+                continue
+            if self.id_to_label:
+                name = self.id_to_label.get(idx, f"ID_{idx}")
+            else:
+                name = f"ID_{idx}"
+            results.append((name, float(score)))
+        if len(results) == 0:
+            return "Unknown", 0.0, []
+        best_name, best_score = results[0]
+        if best_score < self.threshold:
+            return "Unknown", best_score, results
+        return best_name, best_score, results
+
+    # ---- image-level entry points ---------------------------------------------------------------
+    def extract_embedding(self, img_input) -> Optional[np.ndarray]:
+        """Detection/alignment/embedding are upstream of the hot path; delegate to the injected embedder."""
+        if self.embedder is None:
+            print("Model chua duoc load")
+            return None
+        return self.embedder(img_input)
+
+    def recognize(self, img_input, use_faiss: bool = None, k: int = 5) -> Dict:
+        """inference/recognition_engine.py:328-381 — same result dict and error statuses."""
+        result = {"identity": "Unknown", "confidence": 0.0, "top_k": [], "embedding": None, "status": "success"}
+        embedding = self.extract_embedding(img_input)
+        if embedding is None:
+            result["status"] = "error"
+            result["message"] = "Cannot extract embedding (no face or invalid image)"
+            return result
+        result["embedding"] = embedding
+        if use_faiss is None:
+            use_faiss = self.faiss_index is not None
+        if use_faiss and self.faiss_index is not None:
+            identity, confidence, top_k = self.recognize_with_faiss(embedding, k)
+        elif self.db is not None:
+            identity, confidence, top_k = self.recognize_with_db(embedding)
+        else:
+            result["status"] = "error"
+            result["message"] = "No database loaded"
+            return result
+        result["identity"], result["confidence"], result["top_k"] = identity, confidence, top_k
+        return result
+
+    def recognize_batch(self, img_inputs: Sequence, use_faiss: bool = None) -> List[Dict]:
+        """inference/recognition_engine.py:383-389."""
+        return [self.recognize(img, use_faiss) for img in img_inputs]
+
+    def add_to_db(self, name: str, img_inputs: Sequence) -> bool:
+        """inference/recognition_engine.py:391-422: mean of the embeddings, / (||mean|| + 1e-8)."""
+        embeddings = [e for e in (self.extract_embedding(img) for img in img_inputs) if e is not None]
+        if len(embeddings) == 0:
+            print(f"Khong the extract embedding cho {name}")
+            return False
+        mean_emb = np.mean(np.stack(embeddings), axis=0)
+        mean_emb = mean_emb / (np.linalg.norm(mean_emb) + 1e-8)
+        if self.db is None:
+            self.db = {}
+        self.db[name] = mean_emb
+        print(f"Added {name} to database (from {len(embeddings)} images)")
+        return True
+
+    def save_db(self, path: str):
+        if self.db:
+            formats.save_embedding_db(path, dict(self.db))
+            print(f"Saved database: {path}")
+
+    def get_db_identities(self) -> List[str]:
+        if self.db:
+            return list(self.db.keys())
+        return []
+
+
+def create_engine_from_embeddings_dir(model_path: str, embeddings_dir: str, threshold: float = 0.5,
+                                      device: str = None, embedder=None) -> RecognitionEngine:
+    """inference/recognition_engine.py:438-464."""
+    faiss_path = os.path.join(embeddings_dir, "arcface_index.faiss")
+    prototypes_path = os.path.join(embeddings_dir, "arcface_prototypes.npy")
+    mapping_path = os.path.join(embeddings_dir, "label_mapping.npy")
+    return RecognitionEngine(
+        model_path=model_path,
+        faiss_index_path=faiss_path if os.path.exists(faiss_path) else None,
+        prototypes_path=prototypes_path if os.path.exists(prototypes_path) else None,
+        label_mapping_path=mapping_path if os.path.exists(mapping_path) else None,
+        threshold=threshold, device=device, embedder=embedder)
+
+
+def match_facenet(db: Dict[str, np.ndarray], embedding: np.ndarray, threshold: float = 0.5,
+                  gallery: Optional[DeviceGallery] = None, device: Optional[str] = None):
+    """The inline FaceNet matcher of web_app.py:537-562 as a function: e/=(||e||+1e-8); per db row
+    d/=(||d||+1e-8), score=e.d, distance=||e-d||; sorted desc; strict '<' threshold; top-5 of
+    (name, score, distance).
+    Returns {"identity", "confidence", "distance", "top_k"}."""
+    dev = _match_device(device)
+    g = gallery or DeviceGallery(db, dev)
+    q = _to_dev(np.asarray(embedding).astype(np.float32).reshape(1, -1), dev)
+    qn = ops.normalize_rows(q, N.FRB_QNORM_EPS)
+    s, i = ops.cosine_topk(qn, g.unit_rows(), 5, score_mode=N.FRB_SCORE_IP)
+    s, i = s.cpu().numpy()[0], i.cpu().numpy()[0]
+    keep = [int(j) for j in i if j >= 0]
+    # the 5 winning rows come back to the host so the displayed L2 distance is the reference's own
+    # float32 expression ||e - d|| (web_app.py:552) rather than a cancellation-prone sqrt(2 - 2s)
+    e = qn.cpu().numpy()[0]
+    rows = g.unit_rows()[torch.tensor(keep, dtype=torch.int64, device=dev)].cpu().numpy() if keep else np.zeros((0, g.dim))
+    top_k = [(g.names[j], float(sc), float(np.linalg.norm(e - rows[r]))) for r, (sc, j) in enumerate(zip(s, keep))]
+    best_name, best_score, best_distance = top_k[0]
+    if best_score < threshold:
+        best_name = "Unknown"
+    return {"identity": best_name, "confidence": best_score, "distance": best_distance, "top_k": top_k}

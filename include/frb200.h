@@ -1,0 +1,165 @@
+/*
+ * frb200.h — C ABI of libfrb200.so, the B200 (sm_100a) identification-stage kernels.
+ *
+ * The reference (sin0235/FaceRecognition) is pure Python and has no FFI of its own
+ * (SURVEY.md §8b): its seam is a handful of Python methods.  Each entry point below
+ * names the reference call site whose arithmetic it replaces; the Python mirror of
+ * those methods (facerecognition_b200/) binds these symbols with ctypes
+ * (INTEGRATION.md shows the stub).  Paths are relative to the reference root.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no torch / C++ types.
+ *  - Every function returns an frb_status (0 = ok, <0 = error); nothing throws.
+ *    frb_last_error() returns a thread-local description of the last failure.
+ *  - "device" pointers are CUDA device pointers owned by the caller; `stream` is a
+ *    cudaStream_t passed as void* (NULL = legacy default stream).  All launches are
+ *    asynchronous on that stream; no function synchronises unless it says so.
+ *  - Workspaces are caller-owned device scratch; query the size first.
+ *  - Row indices are int64 and are offset by `idx_base`, so a rank that owns rows
+ *    [base, base+N) of a sharded gallery reports GLOBAL ids.
+ *  - Ties are always resolved to the LOWEST row index (the reference's stable sort /
+ *    OpenCV's strict '<' scan keep the first row).
+ *  - There is no CPU fallback: without a CUDA device of compute capability 10.x the
+ *    calls fail with FRB_ERR_CUDA / FRB_ERR_UNSUPPORTED.
+ */
+#ifndef FRB200_H
+#define FRB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum frb_status {
+    FRB_OK = 0,
+    FRB_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, k out of range ...) */
+    FRB_ERR_UNSUPPORTED = -2, /* valid request outside what the kernels implement            */
+    FRB_ERR_CUDA = -3,        /* CUDA runtime / driver error (see frb_last_error)             */
+    FRB_ERR_WORKSPACE = -4    /* workspace missing or too small                               */
+} frb_status;
+
+typedef enum frb_dtype { FRB_F32 = 0, FRB_BF16 = 1 } frb_dtype;
+
+/* How a query row x is scaled before the dot product. */
+typedef enum frb_qnorm {
+    FRB_QNORM_NONE = 0,   /* use as given                                                       */
+    FRB_QNORM_CLAMP = 1,  /* x / max(||x||, 1e-12)  — torch F.normalize, inference/extract_embeddings.py:381,434 */
+    FRB_QNORM_EPS = 2     /* x / (||x|| + 1e-8)     — inference/recognition_engine.py:302, web_app.py:540       */
+} frb_qnorm;
+
+/* How a (query, gallery-row) score is formed from the dot product. */
+typedef enum frb_score {
+    FRB_SCORE_IP = 0,         /* inner product of the (optionally normalised) query with the stored row:
+                                 faiss.IndexFlatIP.search, inference/recognition_engine.py:304;
+                                 np.dot(E, P.T), notebooks/evaluate_arcface_kaggle.ipynb:618             */
+    FRB_SCORE_REF_COSINE = 1  /* cosine_similarity(), inference/recognition_engine.py:41-63: 0 if either
+                                 norm is 0; raw dot if both norms are within 1e-3 of 1; else dot/(na*nb).
+                                 Needs q_norms and g_norms.                                            */
+} frb_score;
+
+#define FRB_MAX_K 64
+
+/* ---- library -------------------------------------------------------------------------- */
+int frb_version(void);
+const char *frb_last_error(void);
+/* sm_count / cc_major / cc_minor of the current CUDA device. */
+int frb_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---- measurement --------------------------------------------------------------------- */
+/* Kernel ids for the profiling counters below. */
+typedef enum frb_kernel {
+    FRB_K_COSINE_TC = 0,   /* cosine_tc_kernel   (bf16 tcgen05 similarity + top-k) */
+    FRB_K_COSINE_SIMT = 1, /* cosine_simt_kernel (fp32 FFMA similarity + top-k)    */
+    FRB_K_LBP_HIST = 2,    /* lbp_hist_kernel                                       */
+    FRB_K_CHISQ = 3,       /* chisq_kernel                                          */
+    FRB_K_COUNT = 4
+} frb_kernel;
+
+/* When enabled, every launch of the four hot kernels is bracketed by a CUDA event pair on the
+ * launching stream (what bench.py's roofline line is computed from).  Off by default. */
+int frb_profile_enable(int on);
+/* Waits for the recorded launches of `kernel` to finish, returns their summed device time and count,
+ * and clears the record. */
+int frb_profile_read(int kernel, float *total_ms, int *launches);
+
+/* ---- cosine path (K1) ------------------------------------------------------------------ */
+
+/* ||x_r||_2 per row, fp32.  Replaces the two np.linalg.norm calls of cosine_similarity
+ * (inference/recognition_engine.py:52-53), hoisted out of the per-pair loop. */
+int frb_row_norms_f32(const float *x_dev, int64_t rows, int dim, float *out_norms_dev, void *stream);
+
+/* Row-wise L2 normalisation with the reference's two conventions, writing fp32 or bf16.
+ * mode = FRB_QNORM_CLAMP | FRB_QNORM_EPS (NONE = plain cast).  Replaces
+ * extract_embeddings.py:622-623 (index rows), web_app.py:549 (db rows), :540 (query). */
+int frb_normalize_rows(const float *x_dev, int64_t rows, int dim, int mode, void *out_dev, int out_dtype,
+                       void *stream);
+
+/* Scratch bytes for frb_cosine_topk at this problem size. */
+size_t frb_cosine_topk_workspace_bytes(int64_t n_query, int64_t n_gallery, int dim, int gallery_dtype, int k);
+
+/* Fused similarity + top-k: for each of n_query fp32 queries [n_query, dim] find the k best
+ * rows of gallery [n_gallery, dim] (fp32 or bf16, row-major).  The n_query x n_gallery score
+ * matrix never reaches HBM.
+ *   gallery_dtype FRB_F32 : exact fp32 FFMA kernel (<=1e-5 of the reference's numpy scores).
+ *   gallery_dtype FRB_BF16: tcgen05 tensor-core kernel (queries normalised in fp32, rounded to
+ *                           bf16 in the prologue; fp32 accumulate in TMEM; <=1e-3).
+ *   q_norms_dev / g_norms_dev : fp32 row norms, required for FRB_SCORE_REF_COSINE, else NULL.
+ *   out_scores_dev [n_query, k] fp32 descending; out_idx_dev [n_query, k] int64 (idx_base + row);
+ *   slots beyond n_gallery hold (-inf, -1) like faiss.
+ * Replaces: RecognitionEngine.recognize_with_db loop+sort (inference/recognition_engine.py:277-289),
+ * recognize_with_faiss search (:304), web_app.py:545-554, the notebooks' np.dot+argsort. */
+int frb_cosine_topk(const float *queries_dev, int64_t n_query, const void *gallery_dev, int gallery_dtype,
+                    int64_t n_gallery, int dim, const float *q_norms_dev, const float *g_norms_dev,
+                    int score_mode, int qnorm_mode, int k, int64_t idx_base, float *out_scores_dev,
+                    int64_t *out_idx_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* Merge R candidate lists per query (e.g. one per GPU after the all-gather, or one per
+ * gallery chunk): cand_scores [R, n_query, k], cand_idx [R, n_query, k] -> best k.
+ * largest != 0: descending score (cosine); largest == 0: ascending distance (LBPH).
+ * Entries with idx < 0 are padding.  Ties -> lowest idx, so the result does not depend on R. */
+int frb_topk_merge(const float *cand_scores_dev, const int64_t *cand_idx_dev, int n_lists, int64_t n_query,
+                   int k, int largest, float *out_scores_dev, int64_t *out_idx_dev, void *stream);
+
+/* ---- LBPH path (K2, K3) ---------------------------------------------------------------- */
+
+/* LBP codes, OpenCV elbp_ semantics (radius 1, 8 neighbours, float32 bilinear diagonals,
+ * (t > c) || |t - c| < FLT_EPSILON): images u8 [count, rows, cols] -> codes u8
+ * [count, rows-2, cols-2].  Exposed for bit-exact parity checks of the code stage. */
+int frb_lbp_codes_u8(const uint8_t *images_dev, int64_t count, int rows, int cols, int radius, int neighbors,
+                     uint8_t *out_codes_dev, void *stream);
+
+/* LBP codes + spatial histogram in one pass (codes never reach HBM): images u8
+ * [count, rows, cols] -> integer cell histograms u16 [count, grid_x*grid_y*256], cell
+ * (i, j) at row i*grid_x + j, cell size floor((cols-2)/grid_x) x floor((rows-2)/grid_y).
+ * *out_cell_px (host, may be NULL) receives the pixel count per cell; OpenCV's float view
+ * is (float)count * (float)(1.0 / cell_px).
+ * Replaces the per-image body of cv2.face LBPH train()/predict() (models/lbphmodel/train_lbph.py:35,
+ * models/lbphmodel/inference_lbph.py:5): elbp + spatial_histogram. */
+int frb_lbp_hist_u8(const uint8_t *images_dev, int64_t count, int rows, int cols, int radius, int neighbors,
+                    int grid_x, int grid_y, uint16_t *out_hist_dev, int *out_cell_px, void *stream);
+
+size_t frb_chisq_topk_workspace_bytes(int64_t n_query, int64_t n_gallery, int hist_len, int k);
+
+/* Chi-square (HISTCMP_CHISQR_ALT) nearest neighbours: for each query histogram find the k
+ * gallery rows with the smallest d = 2 * sum_j (h_j - q_j)^2 / (h_j + q_j), h = count/cell_px.
+ *   q_hist_dev  u16 [n_query, hist_len], counts with q_cell_px pixels per cell
+ *   gallery_dev u16 [n_gallery, hist_len], counts with g_cell_px pixels per cell
+ *   out_dist_dev fp32 [n_query, k] ascending; out_idx_dev int64 [n_query, k] (idx_base + row),
+ *   (+inf, -1) beyond n_gallery.  First row wins ties (StandardCollector's strict '<').
+ * Replaces the compareHist scan of cv2.face LBPH predict() (web_app.py:587,
+ * models/lbphmodel/evaluate_lbph.py:32, models/lbphmodel/threshold_lbph.py:48). */
+int frb_chisq_topk(const uint16_t *q_hist_dev, int64_t n_query, int q_cell_px, const uint16_t *gallery_dev,
+                   int64_t n_gallery, int hist_len, int g_cell_px, int k, int64_t idx_base,
+                   float *out_dist_dev, int64_t *out_idx_dev, void *workspace_dev, size_t workspace_bytes,
+                   void *stream);
+
+/* All distances: out_dist_dev fp32 [n_query, n_gallery] (parity checks, threshold sweeps). */
+int frb_chisq_dist(const uint16_t *q_hist_dev, int64_t n_query, int q_cell_px, const uint16_t *gallery_dev,
+                   int64_t n_gallery, int hist_len, int g_cell_px, float *out_dist_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRB200_H */

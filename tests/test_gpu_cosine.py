@@ -1,0 +1,219 @@
+"""Cosine-path parity on the GPU through the C ABI: the reference's own outputs (golden fixtures),
+the oracle on seeded inputs, and size-independent properties at BASELINE's full sizes.
+Tolerances (north_star): 1e-5 for fp32 scores, 1e-3 for bf16; top-1 identical except stated near-ties."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cosine as OC
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-5
+TOL_BF16 = 1e-3
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def unit(x):
+    return (x / np.linalg.norm(x, axis=-1, keepdims=True)).astype(np.float32)
+
+
+def check_topk(scores, idx, ref_scores_full, k, tol):
+    """scores/idx [Q,k] vs the full reference score matrix: same values within tol; same ids except near-ties."""
+    order = np.lexsort((np.broadcast_to(np.arange(ref_scores_full.shape[1]), ref_scores_full.shape), -ref_scores_full), axis=1)[:, :k]
+    want = np.take_along_axis(ref_scores_full, order, 1)
+    np.testing.assert_allclose(scores, want, atol=tol, rtol=0)
+    mism = idx != order
+    for r, j in zip(*np.nonzero(mism)):
+        assert abs(ref_scores_full[r, idx[r, j]] - want[r, j]) <= 2 * tol, (r, j, idx[r, j], order[r, j])
+    return order
+
+
+def test_golden_reference_outputs_through_engine(cosine_golden):
+    """The real reference's recognize_with_db outputs, replayed through the drop-in RecognitionEngine."""
+    import facerecognition_b200 as F
+    g = cosine_golden
+    eng = F.RecognitionEngine(model_path=None, threshold=float(g["a_threshold"]), use_face_detection=False)
+    eng.db = {str(n): v for n, v in zip(g["a_names"], g["a_gallery"])}
+    S = g["a_scores"]
+    batched = eng.recognize_embeddings(g["a_queries"])
+    for i, e in enumerate(g["a_queries"]):
+        name, score, top = eng.recognize_with_db(e)
+        assert (name, score, top) == batched[i]
+        assert abs(score - g["a_best_scores"][i]) <= TOL_F32
+        np.testing.assert_allclose([t[1] for t in top], g["a_top_scores"][i], atol=TOL_F32, rtol=0)
+        ref_names = [str(x) for x in g["a_top_names"][i]]
+        got_names = [t[0] for t in top]
+        if got_names != ref_names:           # only allowed where the reference's own scores are near-tied
+            row = dict(zip([str(n) for n in g["a_names"]], S[i]))
+            assert all(abs(row[a] - row[b]) <= 2 * TOL_F32 for a, b in zip(got_names, ref_names))
+        assert name == str(g["a_best_names"][i]) or abs(g["a_best_scores"][i] - float(g["a_threshold"])) <= TOL_F32
+    assert [t[0] for t in eng.recognize_with_db(g["a_gallery"][3])[2][:2]] == ["id_00003", "id_00007"]  # stable tie order
+    # zero query: every score 0.0 -> first five identities in insertion order, "Unknown"
+    name, score, top = eng.recognize_with_db(g["a_queries"][2])
+    assert name == "Unknown" and score == 0.0 and [t[0] for t in top] == [f"id_{i:05d}" for i in range(5)]
+
+
+def test_engine_sentinels_small_db_and_mutation(cosine_golden, tmp_path):
+    import facerecognition_b200 as F
+    g = cosine_golden
+    eng = F.RecognitionEngine(model_path=None, threshold=0.65, use_face_detection=False)
+    assert eng.recognize_with_db(g["b_query"]) == (str(g["b_sentinel_name"]), float(g["b_sentinel_score"]), [])
+    assert eng.recognize_with_faiss(g["b_query"]) == ("No FAISS index", 0.0, [])
+    assert eng.recognize("x.jpg")["status"] == "error"                       # no embedder, like no checkpoint
+    eng.db = {f"p{i}": v for i, v in enumerate(g["b_gallery"])}
+    name, score, top = eng.recognize_with_db(g["b_query"])
+    assert name == str(g["b_best_name"]) and abs(score - float(g["b_best_score"])) <= TOL_F32 and len(top) == 3
+    assert [t[0] for t in top] == [str(x) for x in g["b_top_names"]]
+    # callers mutate engine.db in place (recognition_engine.py:419); the device copy must follow
+    eng.db["new"] = g["b_query"]
+    assert eng.recognize_with_db(g["b_query"])[0] == "new"
+    # embedder-driven recognize()/add_to_db()/save_db()
+    table = {"img_a": g["b_gallery"][0], "img_b": g["b_gallery"][2], "bad": None}
+    eng2 = F.RecognitionEngine(model_path=None, threshold=0.5, use_face_detection=False, embedder=table.get)
+    assert eng2.recognize("img_a") == {"identity": "Unknown", "confidence": 0.0, "top_k": [], "embedding": table["img_a"],
+                                       "status": "error", "message": "No database loaded"}
+    assert eng2.add_to_db("alice", ["img_a", "bad"]) and not eng2.add_to_db("nobody", ["bad"])
+    r = eng2.recognize("img_a")
+    assert r["identity"] == "alice" and abs(r["confidence"] - 1.0) < 1e-5 and r["status"] == "success"
+    assert [d["identity"] for d in eng2.recognize_batch(["img_a", "img_b", "bad"])][:2] == ["alice", "Unknown"]
+    p = str(tmp_path / "db.npy")
+    eng2.save_db(p)
+    eng3 = F.RecognitionEngine(model_path=None, db_path=p, use_face_detection=False)
+    assert eng3.get_db_identities() == ["alice"]
+    assert abs(F.cosine_similarity(g["b_gallery"][0] * 2, g["b_gallery"][1]) - OC.cosine_similarity(g["b_gallery"][0] * 2, g["b_gallery"][1])) < TOL_F32
+    assert F.cosine_similarity(np.zeros(512), g["b_gallery"][1]) == 0.0
+
+
+@pytest.mark.parametrize("Q,N,k", [(1, 1, 1), (3, 5, 5), (64, 128, 1), (65, 129, 5), (256, 10000, 1), (256, 10000, 5),
+                                   (7, 4099, 16), (130, 700, 64)])
+def test_fp32_kernel_vs_oracle(Q, N, k):
+    """frb_cosine_topk, fp32 gallery; (256, 10000) is BASELINE configs[1]."""
+    from facerecognition_b200 import ops, _native as NV
+    rng = np.random.default_rng(Q * 1000 + N)
+    gal = unit(rng.standard_normal((N, 512)))
+    q = unit(gal[rng.integers(0, N, Q)] + 0.03 * rng.standard_normal((Q, 512)).astype(np.float32))
+    q[::7] = rng.standard_normal((len(q[::7]), 512)).astype(np.float32) * 3          # un-normalised
+    if N > 10:
+        gal[N // 2] = gal[1]                                                         # exact duplicate
+        gal[3] *= 2.0
+        gal[4] = 0
+    for mode in ("ip", "ref", "eps"):
+        if mode == "ip":
+            s, i = ops.cosine_topk(dev(q), dev(gal), k)
+            ref = q.astype(np.float64) @ gal.T.astype(np.float64)
+        elif mode == "eps":
+            s, i = ops.cosine_topk(dev(q), dev(gal), k, qnorm_mode=NV.FRB_QNORM_EPS)
+            qn = q / (np.linalg.norm(q, axis=1, keepdims=True) + 1e-8)
+            ref = qn.astype(np.float64) @ gal.T.astype(np.float64)
+        else:
+            s, i = ops.cosine_topk(dev(q), dev(gal), k, score_mode=NV.FRB_SCORE_REF_COSINE,
+                                   q_norms=ops.row_norms(dev(q)), g_norms=ops.row_norms(dev(gal)))
+            ref = np.array([[OC.cosine_similarity(a, b) for b in gal] for a in q[:16]]) if N <= 5000 else None
+        s, i = s.cpu().numpy(), i.cpu().numpy()
+        kk = min(k, N)
+        assert np.all(i[:, kk:] == -1) and np.all(np.isinf(s[:, kk:]))
+        if ref is None:
+            continue
+        rows = slice(0, ref.shape[0])
+        check_topk(s[rows, :kk], i[rows, :kk], ref, kk, TOL_F32 * (10 if mode == "ip" else 1))
+    if N > 10:  # duplicate rows: the lower index comes first
+        s, i = ops.cosine_topk(dev(gal[1:2]), dev(gal), min(2, k) if k > 1 else 1)
+        assert i[0, 0].item() == 1 and (k == 1 or i[0, 1].item() == N // 2)
+
+
+def bf16_round(x):
+    return torch.from_numpy(x).to(torch.bfloat16).float().numpy()
+
+
+@pytest.mark.parametrize("Q,N,k", [(1, 1, 1), (5, 255, 5), (128, 256, 5), (129, 257, 5), (300, 5000, 5), (64, 70000, 1),
+                                   (1000, 33333, 16)])
+def test_bf16_tensor_core_kernel_vs_oracle(Q, N, k):
+    from facerecognition_b200 import ops, _native as NV
+    rng = np.random.default_rng(Q + N)
+    gal = unit(rng.standard_normal((N, 512)))
+    q = gal[rng.integers(0, N, Q)] + 0.03 * rng.standard_normal((Q, 512)).astype(np.float32)
+    q[::5] = rng.standard_normal((len(q[::5]), 512)).astype(np.float32)
+    q *= rng.uniform(0.5, 4.0, (Q, 1)).astype(np.float32)                           # the kernel normalises
+    gal_bf16 = ops.normalize_rows(dev(gal), NV.FRB_QNORM_NONE, torch.bfloat16)
+    s, i = ops.cosine_topk(dev(q), gal_bf16, k, qnorm_mode=NV.FRB_QNORM_CLAMP)
+    s, i = s.cpu().numpy(), i.cpu().numpy()
+    kk = min(k, N)
+    assert np.all(i[:, kk:] == -1)
+    # (1) against the fp32 reference scores (what the reference's numpy would give): 1e-3
+    ref32 = OC.l2_normalize(q).astype(np.float64) @ gal.T.astype(np.float64)
+    check_topk(s[:, :kk], i[:, :kk], ref32, kk, TOL_BF16)
+    # (2) against exact arithmetic on the bf16-rounded operands: only fp32 accumulation error remains
+    q16 = ops.normalize_rows(dev(q), NV.FRB_QNORM_CLAMP, torch.bfloat16).float().cpu().numpy()   # the prologue's own rounding
+    assert np.abs(q16 - OC.l2_normalize(q)).max() <= 2.0 ** -8
+    ref16 = q16.astype(np.float64) @ gal_bf16.float().cpu().numpy().T.astype(np.float64)
+    check_topk(s[:, :kk], i[:, :kk], ref16, kk, 2e-6)
+
+
+def test_bf16_ties_and_idx_base():
+    from facerecognition_b200 import ops, _native as NV
+    rng = np.random.default_rng(3)
+    gal = unit(rng.standard_normal((3000, 512)))
+    gal[2900] = gal[17]
+    gal[300] = gal[17]
+    g16 = ops.normalize_rows(dev(gal), NV.FRB_QNORM_NONE, torch.bfloat16)
+    s, i = ops.cosine_topk(dev(gal[17:18]), g16, 3, qnorm_mode=NV.FRB_QNORM_CLAMP, idx_base=10_000_000_000)
+    assert [int(x) - 10_000_000_000 for x in i[0]] == [17, 300, 2900] and s[0, 0] == s[0, 1] == s[0, 2]
+
+
+def test_faiss_mode_and_facenet_matcher(tmp_path):
+    import facerecognition_b200 as F
+    rng = np.random.default_rng(12)
+    emb = rng.standard_normal((500, 512)).astype(np.float32) * rng.uniform(0.5, 2, (500, 1)).astype(np.float32)
+    p = str(tmp_path / "arcface_index.faiss")
+    index = F.build_faiss_index(emb, p)
+    assert index.ntotal == 500
+    eng = F.RecognitionEngine(model_path=None, faiss_index_path=p, threshold=0.5, use_face_detection=False)
+    rows = OC.build_flat_ip(emb)
+    for e in [emb[7] * 0.3, emb[400] + 0.05 * rng.standard_normal(512).astype(np.float32), rng.standard_normal(512).astype(np.float32)]:
+        name, score, res = eng.recognize_with_faiss(e, 5)
+        rname, rscore, rres = OC.recognize_with_faiss(rows, None, e, 5, 0.5)
+        assert name == rname and abs(score - rscore) <= TOL_F32 and [r[0] for r in res] == [r[0] for r in rres]
+    s, i = index.search(rows[:3], 2)
+    assert list(i[:, 0]) == [0, 1, 2]
+    db = {f"n{i}": emb[i] for i in range(60)}
+    for e in [emb[9] * 2, rng.standard_normal(512).astype(np.float32)]:
+        got = F.match_facenet(db, e, 0.5)
+        name, score, dist, top = OC.facenet_match(db, e, 0.5)
+        assert got["identity"] == name and abs(got["confidence"] - score) <= TOL_F32
+        assert [t[0] for t in got["top_k"]] == [t[0] for t in top]
+        np.testing.assert_allclose([t[2] for t in got["top_k"]], [t[2] for t in top], atol=1e-4)
+
+
+def test_full_size_1m_gallery_properties():
+    """BASELINE configs[2]: 1M x 512 bf16 gallery, 4096 queries, top-5 — checked through size-independent
+    properties: planted queries return their source row first; scores are sorted; ids are unique and in
+    range; a 64-query slice agrees with the exact fp32 FFMA kernel run on the same bf16 rows."""
+    from facerecognition_b200 import ops, _native as NV
+    N, Q, k = 1_000_000, 4096, 5
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    gal = torch.randn((N, 512), generator=gen, device="cuda")
+    gal16 = ops.normalize_rows(gal, NV.FRB_QNORM_CLAMP, torch.bfloat16)
+    gen = torch.Generator(device="cuda").manual_seed(4321)
+    src = torch.randint(0, N, (Q,), generator=gen, device="cuda")
+    q = ops.normalize_rows(gal[src].contiguous(), NV.FRB_QNORM_CLAMP) + 0.03 * torch.randn((Q, 512), generator=gen, device="cuda")
+    n_rand = Q // 10
+    q[:n_rand] = torch.randn((n_rand, 512), generator=gen, device="cuda")
+    del gal
+    s, i = ops.cosine_topk(q.contiguous(), gal16, k, qnorm_mode=NV.FRB_QNORM_CLAMP)
+    assert torch.equal(i[n_rand:, 0], src[n_rand:])                         # planted source wins
+    assert bool((s[n_rand:, 0] > 0.75).all()) and bool((s[:n_rand, 0] < 0.5).all())
+    assert bool((s[:, :-1] >= s[:, 1:]).all())                              # sorted
+    assert bool(((i >= 0) & (i < N)).all())
+    srt = i.sort(dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())                          # unique ids per query
+    # slice cross-check against exact fp32 arithmetic on the same stored rows (FFMA kernel)
+    sub = q[1000:1064].contiguous()
+    qn = ops.normalize_rows(sub, NV.FRB_QNORM_CLAMP, torch.bfloat16).float()
+    s2, i2 = ops.cosine_topk(qn, gal16.float()[:200_000].contiguous(), k)
+    s3, i3 = ops.cosine_topk(sub, gal16[:200_000].contiguous(), k, qnorm_mode=NV.FRB_QNORM_CLAMP)
+    assert torch.allclose(s2, s3, atol=2e-6, rtol=0)
+    assert bool(((i2 == i3) | ((s2 - s3).abs() <= 2e-6)).all())

@@ -1,0 +1,222 @@
+"""LBPH parity on the GPU, through the C ABI (facerecognition_b200.ops / .lbph -> libfrb200.so):
+LBP codes and u16 histograms bit-exact against the oracle; chi-square within 1e-5 relative of the
+oracle (itself pinned on cv2.compareHist) and of cv2.compareHist directly; predict() semantics."""
+import cv2
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5          # north_star: chi-square within 1e-5 relative of OpenCV's compareHist
+DBL_MAX = np.finfo(np.float64).max
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def synth_faces(seed, n, h, w):
+    rng = np.random.default_rng(seed)
+    out = np.zeros((n, h, w), np.uint8)
+    for i in range(n):
+        kind = i % 4
+        if kind == 0:
+            img = rng.integers(0, 255, (h, w), dtype=np.uint8)
+            c = (i // 4) % max(1, h // 10)
+            img[c * 10:(c + 1) * 10, :] = 255                       # test_lbph_logic.py:26-28 stripe
+        elif kind == 1:
+            img = cv2.GaussianBlur(rng.integers(0, 256, (h, w), dtype=np.uint8), (0, 0), 1.0 + (i % 5))
+        elif kind == 2:
+            img = np.zeros((h, w), np.uint8)
+            for _ in range(20):
+                y0, x0 = rng.integers(0, h), rng.integers(0, w)
+                img[y0:y0 + rng.integers(3, 40), x0:x0 + rng.integers(3, 40)] = rng.choice([0, 1, 2, 3, 7, 127, 128, 254, 255])
+        else:
+            img = rng.integers(0, 4, (h, w), dtype=np.uint8)         # values 0..3: exercises the centre==1 threshold
+        out[i] = img
+    return out
+
+
+@pytest.mark.parametrize("tag", ["s100", "s112", "s57x83"])
+def test_codes_and_hist_bit_exact_on_golden(lbph_golden, oracle_lbph, tag):
+    from facerecognition_b200 import ops
+    faces = lbph_golden[f"{tag}_faces"]
+    codes = ops.lbp_codes(dev(faces)).cpu().numpy()
+    np.testing.assert_array_equal(codes[0].astype(np.int32), lbph_golden[f"{tag}_codes0"])
+    for i, f in enumerate(faces):
+        np.testing.assert_array_equal(codes[i].astype(np.int32), oracle_lbph.c_elbp(f))
+    hist, px = ops.lbp_hist(dev(faces))
+    assert px == int(lbph_golden[f"{tag}_cell_px"])
+    np.testing.assert_array_equal(hist.cpu().numpy(), lbph_golden[f"{tag}_hist"])
+
+
+@pytest.mark.parametrize("shape,n", [((100, 100), 257), ((112, 112), 130), ((3, 3), 5), ((10, 10), 9), ((64, 200), 33),
+                                     ((131, 97), 17), ((18, 18), 300)])
+def test_codes_and_hist_bit_exact_seeded(oracle_lbph, shape, n):
+    from facerecognition_b200 import ops
+    faces = synth_faces(11 + shape[0], n, *shape)
+    want_hist, want_px = oracle_lbph.c_lbp_hist(faces)
+    hist, px = ops.lbp_hist(dev(faces))
+    assert px == want_px
+    np.testing.assert_array_equal(hist.cpu().numpy(), want_hist)
+    codes = ops.lbp_codes(dev(faces[:8])).cpu().numpy()
+    for i in range(min(8, n)):
+        np.testing.assert_array_equal(codes[i].astype(np.int32), oracle_lbph.c_elbp(faces[i]))
+
+
+def test_flat_images_and_other_grids(oracle_lbph, lbph_golden):
+    from facerecognition_b200 import ops
+    flat = np.stack([np.full((12, 12), v, np.uint8) for v in range(256)])
+    codes = ops.lbp_codes(dev(flat)).cpu().numpy()
+    np.testing.assert_array_equal(codes[:, 3, 3].astype(np.int32), lbph_golden["flat_codes"])
+    faces = synth_faces(3, 12, 100, 100)
+    for gx, gy in [(4, 4), (8, 4), (1, 1), (7, 5)]:
+        want, wpx = oracle_lbph.c_lbp_hist(faces, 1, 8, gx, gy)
+        got, px = ops.lbp_hist(dev(faces), 1, 8, gx, gy)
+        assert px == wpx
+        np.testing.assert_array_equal(got.cpu().numpy(), want)
+
+
+def test_unaligned_image_batches(oracle_lbph):
+    """rows*cols not a multiple of 16 -> the byte-wise staging path."""
+    from facerecognition_b200 import ops
+    faces = synth_faces(5, 7, 33, 35)
+    want, _ = oracle_lbph.c_lbp_hist(faces)
+    np.testing.assert_array_equal(ops.lbp_hist(dev(faces))[0].cpu().numpy(), want)
+
+
+def test_chisq_distances_vs_oracle_and_cv2(oracle_lbph, lbph_golden):
+    from facerecognition_b200 import ops
+    for tag in ["s100", "s112", "s57x83"]:
+        hist, px = lbph_golden[f"{tag}_hist"], int(lbph_golden[f"{tag}_cell_px"])
+        d = ops.chisq_dist(dev(hist), px, dev(hist), px).cpu().numpy().astype(np.float64)
+        ref = lbph_golden[f"{tag}_cv2_chisq"]                      # the real cv2.compareHist
+        np.testing.assert_allclose(d, ref, rtol=REL, atol=0)
+        assert np.all(np.diag(d) == 0.0)                           # identical histograms -> exactly 0, like OpenCV
+
+
+def test_chisq_topk_matches_scan_and_first_wins_ties(oracle_lbph):
+    from facerecognition_b200 import ops
+    faces = synth_faces(21, 700, 100, 100)
+    hist, px = oracle_lbph.c_lbp_hist(faces)
+    gal = hist.copy()
+    gal[650] = gal[40]                                             # duplicate rows far apart (different CTA chunks)
+    gal[41] = gal[40]
+    q = np.concatenate([hist[[40, 5, 699]], oracle_lbph.c_lbp_hist(synth_faces(99, 13, 100, 100))[0]])
+    dist, idx = ops.chisq_topk(dev(q), px, dev(gal), px, k=5)
+    dist, idx = dist.cpu().numpy().astype(np.float64), idx.cpu().numpy()
+    for r in range(q.shape[0]):
+        ref = oracle_lbph.c_chisq_scan_u16(gal, px, q[r], px)
+        order = np.lexsort((np.arange(len(ref)), ref))[:5]
+        np.testing.assert_allclose(dist[r], ref[order], rtol=REL)
+        # identical except stated near-ties: positions whose reference gap is below the tolerance
+        for j in range(5):
+            if idx[r, j] != order[j]:
+                assert abs(ref[idx[r, j]] - ref[order[j]]) <= REL * ref[order[j]]
+    assert list(idx[0, :3]) == [40, 41, 650] and np.all(dist[0, :3] == 0.0)
+    full = ops.chisq_dist(dev(q), px, dev(gal), px).cpu().numpy()
+    np.testing.assert_array_equal(full.min(1), dist[:, 0].astype(np.float32))   # top-1 == min of the full scan
+
+
+def test_chisq_mixed_cell_sizes_and_edge_cases(oracle_lbph):
+    from facerecognition_b200 import ops
+    g_hist, g_px = oracle_lbph.c_lbp_hist(synth_faces(1, 40, 112, 112))
+    q_hist, q_px = oracle_lbph.c_lbp_hist(synth_faces(2, 6, 100, 100))
+    assert g_px != q_px
+    d = ops.chisq_dist(dev(q_hist), q_px, dev(g_hist), g_px).cpu().numpy().astype(np.float64)
+    ref = np.stack([oracle_lbph.c_chisq_scan_u16(g_hist, g_px, q, q_px) for q in q_hist])
+    np.testing.assert_allclose(d, ref, rtol=REL)
+    # k larger than the gallery -> (+inf, -1) padding; empty gallery -> all padding
+    dist, idx = ops.chisq_topk(dev(q_hist), q_px, dev(g_hist[:3]), g_px, k=5)
+    assert np.all(idx.cpu().numpy()[:, 3:] == -1) and np.isinf(dist.cpu().numpy()[:, 3:]).all()
+    dist, idx = ops.chisq_topk(dev(q_hist), q_px, torch.zeros((0, 16384), dtype=torch.uint16, device="cuda"), g_px, k=2)
+    assert np.all(idx.cpu().numpy() == -1)
+    # idx_base shifts ids (what a shard reports)
+    _, i0 = ops.chisq_topk(dev(q_hist), q_px, dev(g_hist), g_px, k=3)
+    _, i1 = ops.chisq_topk(dev(q_hist), q_px, dev(g_hist), g_px, k=3, idx_base=1000)
+    assert torch.equal(i0 + 1000, i1)
+
+
+def test_recognizer_protocol_matches_oracle(oracle_lbph, lbph_golden, tmp_path):
+    import facerecognition_b200 as F
+    faces = list(lbph_golden["s100_faces"])
+    labels = np.arange(len(faces), dtype=np.int32) + 100
+    model = F.train_lbph_model(faces, labels, 1, 8, 8, 8)           # models/lbphmodel/train_lbph.py signature
+    ref = oracle_lbph.OracleLBPH()
+    ref.train(faces, labels)
+    for i, f in enumerate(faces):
+        assert model.predict(f) == (100 + i, 0.0)
+    fresh = synth_faces(77, 24, 100, 100)
+    for f in fresh:
+        lab, conf = model.predict(f)
+        rlab, rconf = ref.predict(f)
+        assert lab == rlab and abs(conf - rconf) <= REL * rconf
+    labs, confs = model.predict_batch(list(fresh))
+    assert [int(x) for x in labs] == [ref.predict(f)[0] for f in fresh]
+    # recognize_face wrapper (inference_lbph.py:4-18): strict '<'
+    lab, conf = model.predict(fresh[0])
+    assert F.recognize_face(model, fresh[0], conf + 1)["status"] == "known"
+    assert F.recognize_face(model, fresh[0], conf) == {"label": None, "confidence": conf, "status": "unknown"}
+    # model threshold -> (-1, DBL_MAX)
+    model.setThreshold(0.0)
+    assert model.predict(faces[0]) == (-1, DBL_MAX)
+    model.setThreshold(DBL_MAX)
+    # update() appends; duplicates keep the first label
+    model.update([faces[2]], np.array([999], np.int32))
+    assert model.predict(faces[2]) == (102, 0.0)
+    # getHistograms is OpenCV's float view
+    np.testing.assert_array_equal(model.getHistograms()[1].ravel(), ref.hists[1])
+    # evaluate_lbph / find_optimal_threshold mirrors
+    acc, cov, used, confs = F.evaluate_lbph(model, faces, labels, 1.0)
+    assert (acc, cov, used) == (1.0, 1.0, len(faces)) and np.all(confs == 0.0)
+    thr, score, rows = F.find_optimal_threshold(model, faces, labels, min_coverage=0.3)
+    assert thr == 40 and score == 1.0 and len(rows) == 17
+    # save / read round trip through the OpenCV FileStorage layout
+    p = str(tmp_path / "lbph_model.xml")
+    model.save(p)
+    assert "<opencv_lbphfaces>" in open(p).read(4096)
+    m2 = F.LBPHFaceRecognizer_create()
+    m2.read(p)
+    assert m2.size == model.size and m2.predict(fresh[3]) == model.predict(fresh[3])
+    with pytest.raises(F.lbph.LBPHError):
+        F.LBPHFaceRecognizer_create().predict(faces[0])
+    with pytest.raises(F.lbph.LBPHError):
+        model.train(faces, labels[:-1])
+
+
+def test_mixed_size_gallery(oracle_lbph):
+    import facerecognition_b200 as F
+    a, b = synth_faces(31, 9, 100, 100), synth_faces(32, 8, 112, 112)
+    faces = [a[0], b[0], a[1], b[1], a[2]] + list(a[3:]) + list(b[2:])
+    labels = np.arange(len(faces), dtype=np.int32)
+    model = F.train_lbph_model(faces, labels)
+    ref = oracle_lbph.OracleLBPH()
+    ref.train(faces, labels)
+    for f in [a[1], b[1], synth_faces(33, 1, 100, 100)[0], synth_faces(34, 1, 112, 112)[0]]:
+        lab, conf = model.predict(f)
+        rlab, rconf = ref.predict(f)
+        assert lab == rlab and abs(conf - rconf) <= REL * max(rconf, 1e-30)
+
+
+def test_baseline_config1_shape_train_predict_1k(oracle_lbph):
+    """BASELINE configs[0]: LBPH (1, 8, 8x8) train + predict on 1k synthetic 100x100 faces."""
+    import facerecognition_b200 as F
+    faces = synth_faces(2024, 1000, 100, 100)
+    labels = (np.arange(1000) // 10).astype(np.int32)
+    model = F.train_lbph_model(list(faces), labels)
+    labs, confs = model.predict_batch(torch.from_numpy(faces).cuda())
+    first = {}
+    hist, _ = oracle_lbph.c_lbp_hist(faces)
+    for i, h in enumerate(hist):
+        first.setdefault(h.tobytes(), i)
+    assert np.all(confs == 0.0)
+    assert [int(x) for x in labs] == [int(labels[first[h.tobytes()]]) for h in hist]
+    probe = synth_faces(4048, 64, 100, 100)
+    labs, confs = model.predict_batch(list(probe))
+    ph, px = oracle_lbph.c_lbp_hist(probe)
+    for r in range(64):
+        ref = oracle_lbph.c_chisq_scan_u16(hist, px, ph[r], px)
+        j = int(np.argmin(ref))
+        assert abs(confs[r] - ref[j]) <= REL * ref[j]
+        assert labs[r] == labels[j] or abs(ref[j] - np.partition(ref, 1)[1]) <= REL * ref[j]

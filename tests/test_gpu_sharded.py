@@ -1,0 +1,51 @@
+"""Sharding by identity: R local searches with global id offsets + frb_topk_merge give exactly the
+unsharded answer for any R (single process, shards emulated on one GPU; the multi-process
+all-gather plumbing is covered by tests/test_host_logic.py under gloo)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("R", [2, 3, 8])
+def test_cosine_shards_merge_to_unsharded_result(R):
+    from facerecognition_b200 import ops, _native as NV
+    from facerecognition_b200.sharded import shard_bounds
+    gen = torch.Generator(device="cuda").manual_seed(R)
+    N, Q, k = 50_001, 200, 5
+    gal = ops.normalize_rows(torch.randn((N, 512), generator=gen, device="cuda"), NV.FRB_QNORM_CLAMP, torch.bfloat16)
+    gal[N - 1] = gal[5]                                                    # tie across the first and last shard
+    q = torch.randn((Q, 512), generator=gen, device="cuda")
+    q[0] = gal[5].float()
+    full_s, full_i = ops.cosine_topk(q, gal, k, qnorm_mode=NV.FRB_QNORM_CLAMP)
+    cs, ci = [], []
+    for r in range(R):
+        lo, hi = shard_bounds(N, R, r)
+        s, i = ops.cosine_topk(q, gal[lo:hi].contiguous(), k, qnorm_mode=NV.FRB_QNORM_CLAMP, idx_base=lo)
+        cs.append(s); ci.append(i)
+    ms, mi = ops.topk_merge(torch.stack(cs).contiguous(), torch.stack(ci).contiguous(), largest=True)
+    assert torch.equal(mi, full_i) and torch.equal(ms, full_s)
+    assert mi[0, 0].item() == 5 and mi[0, 1].item() == N - 1
+
+
+@pytest.mark.parametrize("R", [2, 8])
+def test_chisq_shards_merge_to_unsharded_result(R):
+    from facerecognition_b200 import ops
+    from facerecognition_b200.sharded import shard_bounds
+    rng = np.random.default_rng(R)
+    N, Q, px = 3001, 9, 144
+    gal = rng.multinomial(px, np.ones(256) / 256, size=(N, 64)).astype(np.uint16).reshape(N, -1)
+    q = rng.multinomial(px, np.ones(256) / 256, size=(Q, 64)).astype(np.uint16).reshape(Q, -1)
+    gal[N - 2] = gal[3]
+    q[0] = gal[3]
+    g, qd = torch.from_numpy(gal).cuda(), torch.from_numpy(q).cuda()
+    full_d, full_i = ops.chisq_topk(qd, px, g, px, k=3)
+    cd, ci = [], []
+    for r in range(R):
+        lo, hi = shard_bounds(N, R, r)
+        d, i = ops.chisq_topk(qd, px, g[lo:hi].contiguous(), px, k=3, idx_base=lo)
+        cd.append(d); ci.append(i)
+    md, mi = ops.topk_merge(torch.stack(cd).contiguous(), torch.stack(ci).contiguous(), largest=False)
+    assert torch.equal(mi, full_i) and torch.equal(md, full_d)
+    assert [int(x) for x in mi[0, :2]] == [3, N - 2] and md[0, 0].item() == 0.0

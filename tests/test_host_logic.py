@@ -1,0 +1,124 @@
+"""Host-side logic that needs no GPU: shard partitioning, the gather/merge plumbing under gloo with
+world_size 2, gallery file formats, the mutation-tracking gallery dict."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_bounds_cover_rows_exactly_once():
+    from facerecognition_b200.sharded import shard_bounds
+    for n in [0, 1, 7, 8, 9, 1000, 1_000_000, 100_000_000]:
+        for r in [1, 2, 3, 4, 8]:
+            spans = [shard_bounds(n, r, i) for i in range(r)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert all(0 <= lo <= hi for lo, hi in spans)
+            assert max(hi - lo for lo, hi in spans) == (n + r - 1) // r if n else True
+
+
+def _np_merge(all_s, all_i, largest):
+    """numpy stand-in for frb_topk_merge (same total order: key, then lowest id; id < 0 is padding)."""
+    R, Q, k = all_s.shape
+    s = all_s.permute(1, 0, 2).reshape(Q, R * k).numpy()
+    i = all_i.permute(1, 0, 2).reshape(Q, R * k).numpy()
+    key = np.where(i < 0, np.inf, -s if largest else s)
+    order = np.lexsort((i, key), axis=1)[:, :k]
+    return torch.from_numpy(np.take_along_axis(s, order, 1)), torch.from_numpy(np.take_along_axis(i, order, 1))
+
+
+def _worker(rank, world, port, q_out):
+    try:
+        _worker_body(rank, world, port, q_out)
+    except Exception as e:  # surface the failure instead of a queue timeout
+        q_out.put((rank, repr(e)))
+
+
+def _worker_body(rank, world, port, q_out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from facerecognition_b200.sharded import ShardedSearch, shard_bounds
+    from oracle import cosine as OC
+    rng = np.random.default_rng(5)
+    gal = rng.standard_normal((203, 64)).astype(np.float32)
+    gal[150] = gal[20]                                   # tie across shards: lowest global id must win
+    qs = np.concatenate([gal[[20, 199, 0]], rng.standard_normal((5, 64)).astype(np.float32)])
+    lo, hi = shard_bounds(len(gal), world, rank)
+
+    def local(q, k):
+        s, i = OC.flat_ip_search(gal[lo:hi], q.numpy(), k)
+        return torch.from_numpy(s), torch.from_numpy(np.where(i >= 0, i + lo, i))
+
+    out_s, out_i = ShardedSearch(local, _np_merge, True).search(torch.from_numpy(qs), 5)
+    ref_s, ref_i = OC.flat_ip_search(gal, qs, 5)
+    ok = bool(np.array_equal(out_i.numpy(), ref_i) and np.allclose(out_s.numpy(), ref_s, atol=1e-6))
+    ok = ok and out_i[0, 0].item() == 20 and out_i[0, 1].item() == 150
+    q_out.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_sharded_search_gloo_world2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, True), (1, True)]
+
+
+def test_faiss_flat_ip_file_roundtrip(tmp_path):
+    from facerecognition_b200 import formats
+    rows = np.random.default_rng(0).standard_normal((37, 512)).astype(np.float32)
+    p = str(tmp_path / "arcface_index.faiss")
+    formats.write_faiss_flat_ip(p, rows)
+    raw = open(p, "rb").read()
+    assert raw[:4] == b"IxFI" and len(raw) == 4 + 4 + 8 * 3 + 1 + 4 + 8 + rows.nbytes
+    np.testing.assert_array_equal(formats.read_faiss_flat_ip(p), rows)
+    open(p, "wb").write(b"IxHN" + raw[4:])
+    with pytest.raises(ValueError, match="unsupported FAISS index"):
+        formats.read_faiss_flat_ip(p)
+
+
+def test_embedding_db_format_roundtrip(tmp_path):
+    from facerecognition_b200 import formats
+    db = {"alice": np.ones(512, np.float32), "bob": np.arange(512, dtype=np.float32)}
+    p = str(tmp_path / "sub" / "arcface_embeddings_db.npy")
+    formats.save_embedding_db(p, db)
+    back = np.load(p, allow_pickle=True).item()          # how the reference loads it (recognition_engine.py:135)
+    assert list(back) == ["alice", "bob"] and np.array_equal(back["bob"], db["bob"])
+    assert list(formats.load_embedding_db(p)) == ["alice", "bob"]
+
+
+def test_infer_cell_px_from_opencv_float_histograms(oracle_lbph, lbph_golden):
+    from facerecognition_b200.formats import _infer_cell_px
+    for tag in ["s100", "s112", "s57x83"]:
+        px = int(lbph_golden[f"{tag}_cell_px"])
+        hf = oracle_lbph.hist_to_f32(lbph_golden[f"{tag}_hist"], px)
+        for row in hf:
+            assert _infer_cell_px(row) == px
+            np.testing.assert_array_equal(np.round(row.astype(np.float64) * px).astype(np.uint16), np.round(row * px))
+
+
+def test_gallery_dict_tracks_mutations():
+    from facerecognition_b200.recognition_engine import _GalleryDict
+    d = _GalleryDict({"a": 1})
+    v = d.version
+    d["b"] = 2; assert d.version > v; v = d.version
+    del d["a"]; assert d.version > v; v = d.version
+    d.update(c=3); assert d.version > v; v = d.version
+    d.pop("c"); assert d.version > v; v = d.version
+    d.clear(); assert d.version > v and len(d) == 0

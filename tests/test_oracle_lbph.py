@@ -1,0 +1,105 @@
+"""oracle/lbph_oracle.c + oracle/lbph.py: two independent restatements of OpenCV-contrib's LBPH agree with each
+other and with the committed fixtures; the chi-square stage is pinned on the REAL cv2.compareHist.
+(The LBP-code/histogram stage is PARITY UNPINNED: no cv2.face exists here to run.)"""
+import cv2
+import numpy as np
+import pytest
+
+SIZES = ["s100", "s112", "s57x83"]
+
+
+def test_tap_constants(oracle_lbph):
+    O = oracle_lbph
+    taps = O.c_taps(1, 8)
+    hexw = lambda v: int(np.float32(v).view(np.uint32))
+    A, B, C = 0x3E5413CD, 0x3EFFFFFF, 0x3DAFB0CE       # the constants hard-coded in csrc/lbp_hist.cu
+    assert [hexw(taps[1][w]) for w in ("w1", "w2", "w3", "w4")] == [A, B, C, A]
+    assert [hexw(taps[3][w]) for w in ("w1", "w2", "w3", "w4")] == [B, A, A, C]
+    assert [hexw(taps[5][w]) for w in ("w1", "w2", "w3", "w4")] == [A, C, B, A]
+    assert [hexw(taps[7][w]) for w in ("w1", "w2", "w3", "w4")] == [C, A, A, B]
+    assert [(int(t["fy"]), int(t["fx"])) for t in taps] == [(0, 1), (-1, 0), (-1, 0), (-1, -1), (-1, -1), (0, -1), (1, -1), (0, 0)]
+    for n, (fx, fy, cx, cy, w1, w2, w3, w4) in enumerate(O.np_taps(1, 8)):
+        t = taps[n]
+        assert (fx, fy, cx, cy) == (t["fx"], t["fy"], t["cx"], t["cy"])
+        assert [hexw(x) for x in (w1, w2, w3, w4)] == [hexw(t[w]) for w in ("w1", "w2", "w3", "w4")]
+
+
+def test_compare_identities_used_by_the_kernel():
+    """(t > c) || |t - c| < FLT_EPSILON  <=>  t >= thr(c), thr(1) = 1 - 2^-24, thr(c) = c otherwise;
+    and the axis bits reduce to neighbour >= centre.  Both are relied on by csrc/lbp_hist.cu."""
+    eps = np.float32(np.finfo(np.float32).eps)
+    for e in range(256):
+        c = np.float32(e)
+        base = int(c.view(np.uint32))
+        near = np.array([base + d for d in range(-64, 65) if base + d >= 0], np.uint32).view(np.float32)
+        t = np.concatenate([near, np.random.default_rng(e).uniform(0, 256, 4000).astype(np.float32)])
+        ref = (t > c) | (np.abs((t - c).astype(np.float32)) < eps)
+        thr = np.float32(1 - 2.0 ** -24) if e == 1 else c
+        assert np.array_equal(ref, t >= thr)
+    w2 = np.uint32(0x248D3132).view(np.float32)
+    b, c, e = np.meshgrid(*(np.arange(256, dtype=np.float32),) * 3, indexing="ij")
+    t = (b + (w2 * c).astype(np.float32)).astype(np.float32)
+    assert np.array_equal((t > e) | (np.abs((t - e).astype(np.float32)) < eps), b >= e)
+
+
+@pytest.mark.parametrize("tag", SIZES)
+def test_c_and_numpy_restatements_agree_with_fixture(oracle_lbph, lbph_golden, tag):
+    O, g = oracle_lbph, lbph_golden
+    faces = g[f"{tag}_faces"]
+    hist, px = O.c_lbp_hist(faces)
+    assert px == int(g[f"{tag}_cell_px"])
+    np.testing.assert_array_equal(hist, g[f"{tag}_hist"])
+    np.testing.assert_array_equal(O.c_elbp(faces[0]), g[f"{tag}_codes0"])
+    for f in faces:
+        codes = O.np_elbp(f)
+        np.testing.assert_array_equal(codes, O.c_elbp(f))
+        h, p = O.np_spatial_hist(codes)
+        assert p == px
+        np.testing.assert_array_equal(h, O.c_lbp_hist(f)[0][0])
+    # every cell holds exactly cell_px pixels
+    assert np.all(hist.reshape(len(faces), 64, 256).sum(-1) == px)
+
+
+def test_flat_images_give_gray_level_dependent_codes(oracle_lbph, lbph_golden):
+    O, g = oracle_lbph, lbph_golden
+    codes = np.array([O.c_elbp(np.full((5, 5), v, np.uint8))[1, 1] for v in range(256)])
+    np.testing.assert_array_equal(codes, g["flat_codes"])
+    assert {0: 255, 2: 223, 3: 247, 7: 221, 127: 221, 128: 223, 254: 221, 255: 255}.items() <= dict(enumerate(codes.tolist())).items()
+
+
+@pytest.mark.parametrize("tag", SIZES)
+def test_chisq_is_pinned_on_cv2_comparehist(oracle_lbph, lbph_golden, tag):
+    O, g = oracle_lbph, lbph_golden
+    hf = O.hist_to_f32(g[f"{tag}_hist"], int(g[f"{tag}_cell_px"]))
+    n = hf.shape[0]
+    live = np.array([[cv2.compareHist(hf[i], hf[j], cv2.HISTCMP_CHISQR_ALT) for j in range(n)] for i in range(n)])
+    np.testing.assert_array_equal(live, g[f"{tag}_cv2_chisq"])          # fixture == this box's OpenCV
+    mine = np.stack([O.c_chisq_scan(hf, hf[i]) for i in range(n)])
+    np.testing.assert_allclose(mine, live, rtol=1e-12, atol=0)
+    assert np.all(np.diag(mine) == 0.0)                                  # self-match is exactly 0
+    u16 = np.stack([O.c_chisq_scan_u16(g[f"{tag}_hist"], int(g[f"{tag}_cell_px"]), g[f"{tag}_hist"][i],
+                                       int(g[f"{tag}_cell_px"])) for i in range(n)])
+    np.testing.assert_allclose(u16, live, rtol=1e-12)
+    assert abs(O.np_chisq_alt(hf[0], hf[1]) - live[0, 1]) <= 1e-12 * live[0, 1]
+
+
+def test_predict_semantics(oracle_lbph, lbph_golden):
+    O, g = oracle_lbph, lbph_golden
+    faces = g["s100_faces"]
+    labels = np.arange(len(faces), dtype=np.int32) + 100
+    m = O.OracleLBPH()
+    m.train(list(faces), labels)
+    for i, f in enumerate(faces):
+        assert m.predict(f) == (100 + i, 0.0)
+    # duplicate gallery rows: strict '<' keeps the FIRST one
+    m2 = O.OracleLBPH()
+    m2.train([faces[3], faces[5], faces[3]], np.array([7, 8, 9], np.int32))
+    assert m2.predict(faces[3]) == (7, 0.0)
+    # model threshold rejects everything -> (-1, DBL_MAX)
+    m2.threshold = 0.0
+    lab, d = m2.predict(faces[3])
+    assert lab == -1 and d == np.finfo(np.float64).max
+    # update() appends
+    m2.threshold = np.finfo(np.float64).max
+    m2.update([faces[6]], np.array([11], np.int32))
+    assert m2.predict(faces[6]) == (11, 0.0) and m2.hists.shape[0] == 4
