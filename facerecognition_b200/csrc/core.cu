@@ -107,13 +107,14 @@ __device__ __forceinline__ __nv_bfloat16 cast_out<__nv_bfloat16>(float v) { retu
 
 template <typename OutT>
 __global__ void __launch_bounds__(256) normalize_rows_kernel(const float *__restrict__ x, int64_t rows, int dim,
-                                                             int mode, OutT *__restrict__ out)
+                                                             int mode, OutT *__restrict__ out, float *__restrict__ neg_inf_fill)
 {
     int lane = threadIdx.x & 31;
     int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t r = warp; r < rows; r += nwarps) {
         const float *row = x + r * dim;
+        if (neg_inf_fill && lane == 0) neg_inf_fill[r] = -INFINITY;  // per-row scratch reset riding on this launch
         float denom = 1.f;
         if (mode != FRB_QNORM_NONE) {
             float n = sqrtf(row_sumsq(row, dim, lane));
@@ -161,6 +162,25 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const float *__restrict
         os[q * k + j] = s[j];
         oi[q * k + j] = id[j];
     }
+}
+
+int normalize_rows_impl(const float *x, int64_t rows, int dim, int mode, void *out, int out_dtype, float *neg_inf_fill,
+                        cudaStream_t st)
+{
+    FRB_CHECK_ARG(rows >= 0 && dim > 0, "frb_normalize_rows: rows=%lld dim=%d", (long long)rows, dim);
+    FRB_CHECK_ARG(mode >= FRB_QNORM_NONE && mode <= FRB_QNORM_EPS, "frb_normalize_rows: mode=%d", mode);
+    FRB_CHECK_ARG(out_dtype == FRB_F32 || out_dtype == FRB_BF16, "frb_normalize_rows: out_dtype=%d", out_dtype);
+    if (rows == 0) return FRB_OK;
+    FRB_CHECK_ARG(x && out, "frb_normalize_rows: null pointer");
+    int64_t blocks = (rows + 7) / 8;
+    int grid = (int)(blocks < (int64_t)sm_count() * 8 ? blocks : (int64_t)sm_count() * 8);
+    if (grid < 1) grid = 1;
+    if (out_dtype == FRB_F32)
+        normalize_rows_kernel<float><<<grid, 256, 0, st>>>(x, rows, dim, mode, (float *)out, neg_inf_fill);
+    else
+        normalize_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, rows, dim, mode, (__nv_bfloat16 *)out, neg_inf_fill);
+    FRB_LAUNCH_OK("normalize_rows_kernel");
+    return FRB_OK;
 }
 
 }  // namespace frb
@@ -229,21 +249,7 @@ int frb_row_norms_f32(const float *x, int64_t rows, int dim, float *out, void *s
 
 int frb_normalize_rows(const float *x, int64_t rows, int dim, int mode, void *out, int out_dtype, void *stream)
 {
-    FRB_CHECK_ARG(rows >= 0 && dim > 0, "frb_normalize_rows: rows=%lld dim=%d", (long long)rows, dim);
-    FRB_CHECK_ARG(mode >= FRB_QNORM_NONE && mode <= FRB_QNORM_EPS, "frb_normalize_rows: mode=%d", mode);
-    FRB_CHECK_ARG(out_dtype == FRB_F32 || out_dtype == FRB_BF16, "frb_normalize_rows: out_dtype=%d", out_dtype);
-    if (rows == 0) return FRB_OK;
-    FRB_CHECK_ARG(x && out, "frb_normalize_rows: null pointer");
-    int64_t blocks = (rows + 7) / 8;
-    int grid = (int)(blocks < (int64_t)sm_count() * 8 ? blocks : (int64_t)sm_count() * 8);
-    if (grid < 1) grid = 1;
-    if (out_dtype == FRB_F32)
-        normalize_rows_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, dim, mode, (float *)out);
-    else
-        normalize_rows_kernel<__nv_bfloat16>
-            <<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, dim, mode, (__nv_bfloat16 *)out);
-    FRB_LAUNCH_OK("normalize_rows_kernel");
-    return FRB_OK;
+    return normalize_rows_impl(x, rows, dim, mode, out, out_dtype, nullptr, (cudaStream_t)stream);
 }
 
 int frb_topk_merge(const float *cs, const int64_t *ci, int n_lists, int64_t n_query, int k, int largest,

@@ -22,6 +22,8 @@
 // TMEM: 2 accumulator stages x 256 columns, so the epilogue of tile t overlaps the MMAs of tile t+1.
 #include "frb_common.cuh"
 
+#include <stdlib.h>
+
 #include <cuda.h>  // CUtensorMap + enums (types only; the encode entry point is fetched at run time)
 
 namespace frb {
@@ -35,6 +37,7 @@ constexpr int kTcMaxKBlocks = 8;  // dim <= 512
 constexpr uint32_t kTcABytesPerKb = kTcBlockM * kTcBlockK * 2;  // 16 KB
 constexpr uint32_t kTcBBytesPerStage = kTcBlockN * kTcBlockK * 2;  // 32 KB
 constexpr int kTcMaxStages = 8;
+constexpr int kTcPrefetchDist = 6;  // gallery tiles (256 rows = 256 KB) kept ahead of the TMA loads in L2
 constexpr size_t kTcSmemLimit = 227 * 1024;
 
 struct TcBarriers {
@@ -82,6 +85,11 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// pull one box of the gallery into L2 only (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap *map, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint64_t *bar)
@@ -127,19 +135,94 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr)
 // kind::f16 instruction descriptor: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), both K-major, N>>3 at 17, M>>4 at 24
 constexpr uint32_t kTcIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcBlockN >> 3) << 17) | ((uint32_t)(kTcBlockM >> 4) << 24);
 
+
+// ---- register-resident best-k list for k <= kTcRegK (the common top-1 / top-5 case) ---------------
+// s[] stays sorted descending over all kTcRegK slots; an element is admitted when it beats s[k-1]
+// (strictly, so an equal score with a later row stays behind), dropped into the last slot and bubbled
+// up with predicated swaps: no local memory, ~6 instructions per slot, executed only on admissions.
+constexpr int kTcRegK = 8;
+
+__device__ __forceinline__ float reg_kth(const float (&s)[kTcRegK], int k)
+{
+    float r = s[0];
+#pragma unroll
+    for (int j = 1; j < kTcRegK; j++) r = (k == j + 1) ? s[j] : r;
+    return r;
+}
+
+__device__ __forceinline__ void reg_insert(float (&s)[kTcRegK], int (&id)[kTcRegK], float v, int idx)
+{
+    s[kTcRegK - 1] = v;
+    id[kTcRegK - 1] = idx;
+#pragma unroll
+    for (int j = kTcRegK - 1; j > 0; --j) {
+        const bool sw = s[j] > s[j - 1];
+        const float ts = s[j - 1];
+        const int ti = id[j - 1];
+        s[j - 1] = sw ? s[j] : ts;
+        id[j - 1] = sw ? id[j] : ti;
+        s[j] = sw ? ts : s[j];
+        id[j] = sw ? ti : id[j];
+    }
+}
+
+__device__ __forceinline__ float max32(const float *v)
+{
+    float m[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) m[j] = fmaxf(v[j], v[j + 16]);
+#pragma unroll
+    for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+        for (int j = 0; j < w; j++) m[j] = fmaxf(m[j], m[j + w]);
+    return m[0];
+}
+
+// ---- cross-CTA admission threshold ---------------------------------------------------------------
+// thr[q] holds a lower bound on query q's final k-th best score, stored one ulp BELOW a score that k
+// rows are already known to reach (so an equal score from another gallery group still gets in and the
+// lowest-row tie order is preserved).  Every unit starts from it instead of from -inf; without it each
+// unit re-learns its threshold and, with 32 independent lists per warp, nearly every 32-column chunk
+// takes the (slow, divergent) admission path.  It only ever discards rows that cannot be in the
+// final top-k, so results do not depend on timing.
+__device__ __forceinline__ float next_below(float x)
+{
+    if (x == -INFINITY) return x;
+    if (x == 0.f) return -1.17549435e-38f;
+    const int b = __float_as_int(x);
+    return __int_as_float(x > 0.f ? b - 1 : b + 1);
+}
+__device__ __forceinline__ void atomic_max_f32(float *addr, float v)
+{
+    if (v >= 0.f)
+        atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+    else
+        atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ float ld_relaxed_f32(const float *addr)
+{
+    float v;
+    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(addr));
+    return v;
+}
+
 struct TcParams {
     int64_t n_query, n_gallery;
     int k_blocks;          // dim / 64
     int stages;            // B ring depth
     int64_t n_qtiles, n_tiles, tiles_per_group, n_groups;
     int k;
+    int prefetch_dist;     // gallery tiles prefetched into L2 ahead of the TMA loads (0 = off)
     int64_t idx_base;
+    float *thr;            // [n_query] shared admission thresholds, -inf on entry
     float *cand_scores;    // [n_groups, n_query, k]
     int64_t *cand_idx;
 };
 
+template <bool REG_LIST>
 __global__ void __launch_bounds__(kTcThreads, 1)
-cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g, const TcParams p)
+cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
+                 const __grid_constant__ CUtensorMap tmap_pf, const TcParams p)
 {
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment
@@ -154,6 +237,7 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_g) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_pf) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; s++) {
@@ -192,7 +276,17 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 for (int kb = 0; kb < p.k_blocks; kb++)
                     tma_load_2d(smem_a + (size_t)kb * kTcABytesPerKb, &tmap_q, &bars->a_full, kb * kTcBlockK, (int)(qt * kTcBlockM));
                 a_phase ^= 1;
+                // L2 prefetch.  The query tiles that share this gallery group walk it in lockstep, so every
+                // line's first touch would pay DRAM latency in all of them at once; instead tile t + p.prefetch_dist
+                // is pulled into L2 ahead of time, the duty split round-robin over the sharing query tiles.
+                for (int64_t t = t0 + qt; t < t0 + p.prefetch_dist && t < t1; t += p.n_qtiles) {
+                    for (int c = 0; c < p.k_blocks * kTcBlockK; c += 256) tma_prefetch_l2_2d(&tmap_pf, c, (int)(t * kTcBlockN));
+                }
                 for (int64_t t = t0; t < t1; t++) {
+                    const int64_t tp = t + p.prefetch_dist;
+                    if (tp < t1 && (tp - t0) % p.n_qtiles == qt) {
+                        for (int c = 0; c < p.k_blocks * kTcBlockK; c += 256) tma_prefetch_l2_2d(&tmap_pf, c, (int)(tp * kTcBlockN));
+                    }
                     for (int kb = 0; kb < p.k_blocks; kb++) {
                         mbar_wait(&bars->empty[stage], phase ^ 1);
                         mbar_expect_tx(&bars->full[stage], kTcBBytesPerStage);
@@ -244,46 +338,88 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const int row = ew * 32 + lane;                // query row inside the tile == TMEM lane
         int acc = 0;
         uint32_t acc_phase = 0;
-        float best_s[FRB_MAX_K];
-        int64_t best_i[FRB_MAX_K];
+        // REG_LIST: k <= 8, list in registers with 32-bit row offsets relative to the unit's first row;
+        // otherwise a local-memory list (k up to FRB_MAX_K), touched only on admissions.
+        float rs[kTcRegK];
+        int ri[kTcRegK];
+        float best_s[REG_LIST ? 1 : FRB_MAX_K];
+        int64_t best_i[REG_LIST ? 1 : FRB_MAX_K];
         for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
             const int64_t qt = u % p.n_qtiles, grp = u / p.n_qtiles;
             const int64_t t0 = grp * p.tiles_per_group;
             const int64_t t1 = (t0 + p.tiles_per_group < p.n_tiles) ? t0 + p.tiles_per_group : p.n_tiles;
-            list_init<true>(best_s, best_i, p.k);
-            float kth = -INFINITY;
+            const int64_t unit_n0 = t0 * kTcBlockN;
+            if (REG_LIST) {
+#pragma unroll
+                for (int j = 0; j < kTcRegK; j++) { rs[j] = -INFINITY; ri[j] = -1; }
+            } else {
+                list_init<true>(best_s, best_i, p.k);
+            }
+            const int64_t q = qt * kTcBlockM + row;
+            const bool q_live = q < p.n_query;
+            float kth = -INFINITY;                                   // this unit's own k-th best
+            float gthr = q_live ? ld_relaxed_f32(p.thr + q) : INFINITY;  // dead rows admit nothing
+            float adm = gthr;                                        // admit v > adm = max(kth, gthr)
+            float published = gthr;
             for (int64_t t = t0; t < t1; t++) {
                 mbar_wait(&bars->tmem_full[acc], acc_phase);
                 tcgen05_fence_after();
                 const int64_t n0 = t * kTcBlockN;
                 const int valid = (int)((p.n_gallery - n0) < kTcBlockN ? (p.n_gallery - n0) : kTcBlockN);
+                const int col0 = (int)(n0 - unit_n0);
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kTcBlockN;
 #pragma unroll 1
                 for (int c0 = 0; c0 < kTcBlockN; c0 += 32) {
                     float v[32];
                     tmem_ld_32x32(taddr + (uint32_t)c0, v);
-                    if (c0 + 32 <= valid) {
+                    if (c0 + 32 > valid) {  // ragged last tile: TMA zero-filled rows must not compete
 #pragma unroll
-                        for (int j = 0; j < 32; j++)
-                            if (v[j] > kth) kth = list_insert_stream<true>(best_s, best_i, p.k, v[j], p.idx_base + n0 + c0 + j);
-                    } else {
+                        for (int j = 0; j < 32; j++) v[j] = (c0 + j < valid) ? v[j] : -INFINITY;
+                    }
+                    if (max32(v) > adm) {   // rare once the thresholds have warmed up
 #pragma unroll
-                        for (int j = 0; j < 32; j++)
-                            if (c0 + j < valid && v[j] > kth)
-                                kth = list_insert_stream<true>(best_s, best_i, p.k, v[j], p.idx_base + n0 + c0 + j);
+                        for (int j = 0; j < 32; j++) {
+                            if (v[j] > adm) {
+                                if (REG_LIST) {
+                                    reg_insert(rs, ri, v[j], col0 + c0 + j);
+                                    kth = reg_kth(rs, p.k);
+                                } else {
+                                    kth = list_insert_stream<true>(best_s, best_i, p.k, v[j], p.idx_base + n0 + c0 + j);
+                                }
+                                adm = fmaxf(kth, gthr);
+                            }
+                        }
                     }
                 }
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                // exchange thresholds once per tile: publish ours if it improved, pick up the others'
+                if (q_live) {
+                    const float mine = next_below(kth);
+                    if (mine > published) {
+                        atomic_max_f32(p.thr + q, mine);
+                        published = mine;
+                    }
+                    gthr = fmaxf(gthr, ld_relaxed_f32(p.thr + q));
+                    adm = fmaxf(kth, gthr);
+                }
             }
-            const int64_t q = qt * kTcBlockM + row;
-            if (q < p.n_query) {
+            if (q_live) {
                 const int64_t o = (grp * p.n_query + q) * p.k;
-                for (int j = 0; j < p.k; j++) {
-                    p.cand_scores[o + j] = best_s[j];
-                    p.cand_idx[o + j] = best_i[j];
+                if (REG_LIST) {
+#pragma unroll
+                    for (int j = 0; j < kTcRegK; j++)
+                        if (j < p.k) {
+                            p.cand_scores[o + j] = rs[j];
+                            p.cand_idx[o + j] = ri[j] < 0 ? (int64_t)-1 : p.idx_base + unit_n0 + ri[j];
+                        }
+                } else {
+                    for (int j = 0; j < p.k; j++) {
+                        p.cand_scores[o + j] = best_s[j];
+                        p.cand_idx[o + j] = best_i[j];
+                    }
                 }
             }
         }
@@ -316,7 +452,8 @@ static EncodeTiledFn get_encode_fn()
 }
 
 // row-major bf16 [rows, dim] -> boxes of (64 of K) x box_rows rows, 128-byte swizzled, zero fill out of bounds
-static int make_bf16_map(CUtensorMap *map, const void *base, int64_t rows, int dim, int box_rows)
+static int make_bf16_map(CUtensorMap *map, const void *base, int64_t rows, int dim, int box_rows, int box_cols = kTcBlockK,
+                         CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B)
 {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) {
@@ -325,10 +462,10 @@ static int make_bf16_map(CUtensorMap *map, const void *base, int64_t rows, int d
     }
     cuuint64_t dims[2] = {(cuuint64_t)dim, (cuuint64_t)(rows > 0 ? rows : 1)};
     cuuint64_t strides[1] = {(cuuint64_t)dim * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kTcBlockK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld dim=%d)", (int)r, (long long)rows, dim);
@@ -339,7 +476,7 @@ static int make_bf16_map(CUtensorMap *map, const void *base, int64_t rows, int d
 
 struct TcPlan {
     int64_t n_qtiles, n_tiles, tiles_per_group, n_groups;
-    size_t qbf16_bytes, idx_bytes, score_bytes;
+    size_t qbf16_bytes, thr_bytes, idx_bytes, score_bytes;
 };
 
 static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
@@ -359,6 +496,7 @@ static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
     pl.n_groups = (pl.n_tiles + pl.tiles_per_group - 1) / pl.tiles_per_group;
     size_t n = (size_t)pl.n_groups * (size_t)nq * (size_t)k;
     pl.qbf16_bytes = align_up((size_t)pl.n_qtiles * kTcBlockM * (size_t)dim * 2, 1024);
+    pl.thr_bytes = align_up((size_t)nq * sizeof(float), 256);
     pl.idx_bytes = align_up(n * sizeof(int64_t), 256);
     pl.score_bytes = align_up(n * sizeof(float), 256);
     return pl;
@@ -367,7 +505,7 @@ static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
 size_t cosine_tc_workspace_bytes(int64_t n_query, int64_t n_gallery, int dim, int k)
 {
     TcPlan pl = tc_plan(n_query, n_gallery, dim, k);
-    return pl.qbf16_bytes + pl.idx_bytes + pl.score_bytes;
+    return pl.qbf16_bytes + pl.thr_bytes + pl.idx_bytes + pl.score_bytes;
 }
 
 int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16, int64_t ng, int dim, int qnorm_mode, int k,
@@ -388,17 +526,24 @@ int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16,
     TcPlan pl = tc_plan(nq, ng, dim, k);
     char *w = (char *)ws;
     __nv_bfloat16 *qb = (__nv_bfloat16 *)w;
-    int64_t *ci = (int64_t *)(w + pl.qbf16_bytes);
-    float *cs = (float *)(w + pl.qbf16_bytes + pl.idx_bytes);
+    float *thr = (float *)(w + pl.qbf16_bytes);
+    int64_t *ci = (int64_t *)(w + pl.qbf16_bytes + pl.thr_bytes);
+    float *cs = (float *)(w + pl.qbf16_bytes + pl.thr_bytes + pl.idx_bytes);
 
     // prologue: L2-normalise in fp32, round to bf16 (rows beyond n_query are never read: TMA zero-fills)
-    int rc = frb_normalize_rows(queries, nq, dim, qnorm_mode, qb, FRB_BF16, st);
+    // the same launch resets the shared admission thresholds to -inf
+    int rc = normalize_rows_impl(queries, nq, dim, qnorm_mode, qb, FRB_BF16, thr, st);
     if (rc != FRB_OK) return rc;
 
-    CUtensorMap tq, tg;
+    CUtensorMap tq, tg, tpf;
     rc = make_bf16_map(&tq, qb, nq, dim, kTcBlockM);
     if (rc != FRB_OK) return rc;
     rc = make_bf16_map(&tg, ng > 0 ? gallery_bf16 : (const void *)qb, ng, dim, kTcBlockN);
+    if (rc != FRB_OK) return rc;
+
+    // prefetch view of the gallery: unswizzled boxes of (up to) 256 of K x 256 rows, L2 only
+    rc = make_bf16_map(&tpf, ng > 0 ? gallery_bf16 : (const void *)qb, ng, dim, kTcBlockN, dim < 256 ? dim : 256,
+                       CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc != FRB_OK) return rc;
 
     TcParams p;
@@ -418,11 +563,18 @@ int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16,
     p.tiles_per_group = pl.tiles_per_group;
     p.n_groups = pl.n_groups;
     p.k = k;
+    p.prefetch_dist = kTcPrefetchDist;
+    if (const char *e = getenv("FRB_TC_PREFETCH_DIST")) p.prefetch_dist = atoi(e);  // tuning knob for experiments
     p.idx_base = idx_base;
+    p.thr = thr;
     p.cand_scores = cs;
     p.cand_idx = ci;
     const size_t smem = 1024 + a_bytes + (size_t)stages * kTcBBytesPerStage + sizeof(TcBarriers);
-    FRB_CUDA_OK(cudaFuncSetAttribute(cosine_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool reg_list = k <= kTcRegK;
+    if (reg_list)
+        FRB_CUDA_OK(cudaFuncSetAttribute(cosine_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+        FRB_CUDA_OK(cudaFuncSetAttribute(cosine_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int sms = sm_count();
     int64_t n_units = pl.n_qtiles * pl.n_groups;
     int grid = (int)(n_units < sms ? n_units : sms);
@@ -432,7 +584,10 @@ int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16,
     }
     {
         ProfileScope prof(FRB_K_COSINE_TC, st);
-        cosine_tc_kernel<<<grid, kTcThreads, smem, st>>>(tq, tg, p);
+        if (reg_list)
+            cosine_tc_kernel<true><<<grid, kTcThreads, smem, st>>>(tq, tg, tpf, p);
+        else
+            cosine_tc_kernel<false><<<grid, kTcThreads, smem, st>>>(tq, tg, tpf, p);
     }
     FRB_LAUNCH_OK("cosine_tc_kernel");
     return frb_topk_merge(cs, ci, (int)pl.n_groups, nq, k, /*largest=*/1, out_scores, out_idx, st);

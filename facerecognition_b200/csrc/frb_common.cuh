@@ -18,6 +18,10 @@ void set_error(const char *fmt, ...);
 
 int sm_count();  // cached multiProcessorCount of the current device
 
+// frb_normalize_rows with an optional per-row float scratch that the same launch resets to -inf
+int normalize_rows_impl(const float *x, int64_t rows, int dim, int mode, void *out, int out_dtype, float *neg_inf_fill,
+                        cudaStream_t st);
+
 #define FRB_CHECK_ARG(cond, ...)                \
     do {                                        \
         if (!(cond)) {                          \
