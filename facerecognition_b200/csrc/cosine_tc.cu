@@ -166,6 +166,19 @@ __device__ __forceinline__ void reg_insert(float (&s)[kTcRegK], int (&id)[kTcReg
     }
 }
 
+// v[j] for a run-time j without spilling v[] to local memory: 5-level select tree (31 SEL)
+__device__ __forceinline__ float select32(const float *v, int j)
+{
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = (j & 16) ? v[i + 16] : v[i];
+#pragma unroll
+    for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+        for (int i = 0; i < w; i++) a[i] = (j & w) ? a[i + w] : a[i];
+    return a[0];
+}
+
 __device__ __forceinline__ float max32(const float *v)
 {
     float m[16];
@@ -210,7 +223,9 @@ struct TcParams {
     int64_t n_query, n_gallery;
     int k_blocks;          // dim / 64
     int stages;            // B ring depth
-    int64_t n_qtiles, n_tiles, tiles_per_group, n_groups;
+    int64_t n_qtiles, tiles_per_group, n_groups;  // units of THIS launch = n_qtiles * n_groups
+    int64_t tile_begin, tile_end;                 // gallery tiles [tile_begin, tile_end) are scanned by this launch
+    int64_t group_base;                           // candidate lists go to group slot group_base + grp
     int k;
     int prefetch_dist;     // gallery tiles prefetched into L2 ahead of the TMA loads (0 = off)
     int64_t idx_base;
@@ -269,8 +284,8 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             uint32_t phase = 0, a_phase = 0;
             for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const int64_t qt = u % p.n_qtiles, grp = u / p.n_qtiles;
-                const int64_t t0 = grp * p.tiles_per_group;
-                const int64_t t1 = (t0 + p.tiles_per_group < p.n_tiles) ? t0 + p.tiles_per_group : p.n_tiles;
+                const int64_t t0 = p.tile_begin + grp * p.tiles_per_group;
+                const int64_t t1 = (t0 + p.tiles_per_group < p.tile_end) ? t0 + p.tiles_per_group : p.tile_end;
                 mbar_wait(&bars->a_empty, a_phase ^ 1);  // previous unit's MMAs have finished reading A
                 mbar_expect_tx(&bars->a_full, (uint32_t)p.k_blocks * kTcABytesPerKb);
                 for (int kb = 0; kb < p.k_blocks; kb++)
@@ -304,8 +319,8 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             uint32_t phase = 0, a_phase = 0, acc_phase = 0;
             for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const int64_t grp = u / p.n_qtiles;
-                const int64_t t0 = grp * p.tiles_per_group;
-                const int64_t t1 = (t0 + p.tiles_per_group < p.n_tiles) ? t0 + p.tiles_per_group : p.n_tiles;
+                const int64_t t0 = p.tile_begin + grp * p.tiles_per_group;
+                const int64_t t1 = (t0 + p.tiles_per_group < p.tile_end) ? t0 + p.tiles_per_group : p.tile_end;
                 mbar_wait(&bars->a_full, a_phase);
                 a_phase ^= 1;
                 tcgen05_fence_after();
@@ -346,8 +361,8 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         int64_t best_i[REG_LIST ? 1 : FRB_MAX_K];
         for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
             const int64_t qt = u % p.n_qtiles, grp = u / p.n_qtiles;
-            const int64_t t0 = grp * p.tiles_per_group;
-            const int64_t t1 = (t0 + p.tiles_per_group < p.n_tiles) ? t0 + p.tiles_per_group : p.n_tiles;
+            const int64_t t0 = p.tile_begin + grp * p.tiles_per_group;
+            const int64_t t1 = (t0 + p.tiles_per_group < p.tile_end) ? t0 + p.tiles_per_group : p.tile_end;
             const int64_t unit_n0 = t0 * kTcBlockN;
             if (REG_LIST) {
 #pragma unroll
@@ -377,14 +392,21 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         for (int j = 0; j < 32; j++) v[j] = (c0 + j < valid) ? v[j] : -INFINITY;
                     }
                     if (max32(v) > adm) {   // rare once the thresholds have warmed up
+                        // candidate mask first (straight-line), then visit this lane's candidates in column
+                        // order; the warp iterates max-popcount times instead of walking 32 branchy checks
+                        uint32_t cand = 0;
 #pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            if (v[j] > adm) {
+                        for (int j = 0; j < 32; j++) cand |= (v[j] > adm) ? (1u << j) : 0u;
+                        while (cand) {
+                            const int j = __ffs(cand) - 1;
+                            cand &= cand - 1;
+                            const float x = select32(v, j);
+                            if (x > adm) {
                                 if (REG_LIST) {
-                                    reg_insert(rs, ri, v[j], col0 + c0 + j);
+                                    reg_insert(rs, ri, x, col0 + c0 + j);
                                     kth = reg_kth(rs, p.k);
                                 } else {
-                                    kth = list_insert_stream<true>(best_s, best_i, p.k, v[j], p.idx_base + n0 + c0 + j);
+                                    kth = list_insert_stream<true>(best_s, best_i, p.k, x, p.idx_base + n0 + c0 + j);
                                 }
                                 adm = fmaxf(kth, gthr);
                             }
@@ -407,7 +429,7 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 }
             }
             if (q_live) {
-                const int64_t o = (grp * p.n_query + q) * p.k;
+                const int64_t o = ((p.group_base + grp) * p.n_query + q) * p.k;
                 if (REG_LIST) {
 #pragma unroll
                     for (int j = 0; j < kTcRegK; j++)
@@ -474,10 +496,31 @@ static int make_bf16_map(CUtensorMap *map, const void *base, int64_t rows, int d
     return FRB_OK;
 }
 
+// Two launches of the same kernel.  A short warm-up pass scans the first few gallery tiles so that every
+// query has a realistic admission threshold before the main pass starts (otherwise all CTAs begin with
+// -inf thresholds at the same moment and spend their first tiles on the slow admission path); the main
+// pass covers the remaining tiles.  Both write candidate lists into one [n_groups, Q, k] array.
+struct TcPass {
+    int64_t tile_begin, tile_end, tiles_per_group, n_groups, group_base;
+};
+
 struct TcPlan {
-    int64_t n_qtiles, n_tiles, tiles_per_group, n_groups;
+    int64_t n_qtiles, n_tiles, n_groups;  // n_groups = total candidate lists per query
+    TcPass warm, main;                     // warm.n_groups == 0: single pass
     size_t qbf16_bytes, thr_bytes, idx_bytes, score_bytes;
 };
+
+static void tc_split(int64_t tile_begin, int64_t tile_end, int64_t want_groups, int64_t group_base, TcPass *ps)
+{
+    const int64_t tiles = tile_end - tile_begin;
+    if (want_groups > tiles) want_groups = tiles;
+    if (want_groups < 1) want_groups = 1;
+    ps->tile_begin = tile_begin;
+    ps->tile_end = tile_end;
+    ps->tiles_per_group = tiles > 0 ? (tiles + want_groups - 1) / want_groups : 1;
+    ps->n_groups = tiles > 0 ? (tiles + ps->tiles_per_group - 1) / ps->tiles_per_group : 1;
+    ps->group_base = group_base;
+}
 
 static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
 {
@@ -487,13 +530,25 @@ static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
     pl.n_qtiles = (nq + kTcBlockM - 1) / kTcBlockM;
     pl.n_tiles = (ng + kTcBlockN - 1) / kTcBlockN;
     if (pl.n_tiles < 1) pl.n_tiles = 1;
-    // ~16 units per CTA for balance; a unit's gallery group is shared (through L2) by all query tiles
+    // warm-up: ~1/64 of the gallery, 4..32 tiles, one wave of CTAs
+    int64_t warm_tiles = 0;
+    if (pl.n_tiles >= 64) {
+        warm_tiles = pl.n_tiles / 64;
+        if (warm_tiles < 4) warm_tiles = 4;
+        if (warm_tiles > 32) warm_tiles = 32;
+    }
+    if (warm_tiles > 0) {
+        int64_t wg = sms / pl.n_qtiles;
+        if (wg < 1) wg = 1;
+        tc_split(0, warm_tiles, wg, 0, &pl.warm);
+    } else {
+        pl.warm = TcPass{0, 0, 1, 0, 0};
+    }
+    // main: ~16 units per CTA for balance; a unit's gallery group is shared (through L2) by all query tiles
     int64_t want_groups = ((int64_t)sms * 16 + pl.n_qtiles - 1) / pl.n_qtiles;
-    if (want_groups > pl.n_tiles) want_groups = pl.n_tiles;
     if (want_groups > 1024) want_groups = 1024;
-    if (want_groups < 1) want_groups = 1;
-    pl.tiles_per_group = (pl.n_tiles + want_groups - 1) / want_groups;
-    pl.n_groups = (pl.n_tiles + pl.tiles_per_group - 1) / pl.tiles_per_group;
+    tc_split(warm_tiles, pl.n_tiles, want_groups, pl.warm.n_groups, &pl.main);
+    pl.n_groups = pl.warm.n_groups + pl.main.n_groups;
     size_t n = (size_t)pl.n_groups * (size_t)nq * (size_t)k;
     pl.qbf16_bytes = align_up((size_t)pl.n_qtiles * kTcBlockM * (size_t)dim * 2, 1024);
     pl.thr_bytes = align_up((size_t)nq * sizeof(float), 256);
@@ -559,9 +614,6 @@ int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16,
     }
     p.stages = stages;
     p.n_qtiles = pl.n_qtiles;
-    p.n_tiles = pl.n_tiles;
-    p.tiles_per_group = pl.tiles_per_group;
-    p.n_groups = pl.n_groups;
     p.k = k;
     p.prefetch_dist = kTcPrefetchDist;
     if (const char *e = getenv("FRB_TC_PREFETCH_DIST")) p.prefetch_dist = atoi(e);  // tuning knob for experiments
@@ -575,21 +627,25 @@ int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16,
         FRB_CUDA_OK(cudaFuncSetAttribute(cosine_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else
         FRB_CUDA_OK(cudaFuncSetAttribute(cosine_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int sms = sm_count();
-    int64_t n_units = pl.n_qtiles * pl.n_groups;
-    int grid = (int)(n_units < sms ? n_units : sms);
-    if (ng == 0) {
-        // nothing to scan: emit empty lists through the merge of zero-row groups
-        p.n_tiles = 0;
-    }
-    {
+    const int sms = sm_count();
+    const TcPass passes[2] = {pl.warm, pl.main};
+    for (int ip = 0; ip < 2; ip++) {
+        const TcPass &ps = passes[ip];
+        if (ps.n_groups == 0) continue;
+        p.tiles_per_group = ps.tiles_per_group;
+        p.n_groups = ps.n_groups;
+        p.tile_begin = ps.tile_begin;
+        p.tile_end = ng > 0 ? ps.tile_end : ps.tile_begin;  // empty gallery: units run with no tiles and emit empty lists
+        p.group_base = ps.group_base;
+        const int64_t n_units = pl.n_qtiles * ps.n_groups;
+        const int grid = (int)(n_units < sms ? n_units : sms);
         ProfileScope prof(FRB_K_COSINE_TC, st);
         if (reg_list)
             cosine_tc_kernel<true><<<grid, kTcThreads, smem, st>>>(tq, tg, tpf, p);
         else
             cosine_tc_kernel<false><<<grid, kTcThreads, smem, st>>>(tq, tg, tpf, p);
+        FRB_LAUNCH_OK("cosine_tc_kernel");
     }
-    FRB_LAUNCH_OK("cosine_tc_kernel");
     return frb_topk_merge(cs, ci, (int)pl.n_groups, nq, k, /*largest=*/1, out_scores, out_idx, st);
 }
 
