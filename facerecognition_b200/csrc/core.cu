@@ -107,14 +107,16 @@ __device__ __forceinline__ __nv_bfloat16 cast_out<__nv_bfloat16>(float v) { retu
 
 template <typename OutT>
 __global__ void __launch_bounds__(256) normalize_rows_kernel(const float *__restrict__ x, int64_t rows, int dim,
-                                                             int mode, OutT *__restrict__ out, float *__restrict__ neg_inf_fill)
+                                                             int mode, OutT *__restrict__ out, float *__restrict__ neg_inf_fill,
+                                                             int *__restrict__ zero_fill)
 {
     int lane = threadIdx.x & 31;
     int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t r = warp; r < rows; r += nwarps) {
         const float *row = x + r * dim;
-        if (neg_inf_fill && lane == 0) neg_inf_fill[r] = -INFINITY;  // per-row scratch reset riding on this launch
+        if (neg_inf_fill && lane == 0) neg_inf_fill[r] = -INFINITY;  // per-row scratch resets riding on this launch
+        if (zero_fill && lane == 0) zero_fill[r] = 0;
         float denom = 1.f;
         if (mode != FRB_QNORM_NONE) {
             float n = sqrtf(row_sumsq(row, dim, lane));
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const float *__restrict
 }
 
 int normalize_rows_impl(const float *x, int64_t rows, int dim, int mode, void *out, int out_dtype, float *neg_inf_fill,
-                        cudaStream_t st)
+                        int *zero_fill, cudaStream_t st)
 {
     FRB_CHECK_ARG(rows >= 0 && dim > 0, "frb_normalize_rows: rows=%lld dim=%d", (long long)rows, dim);
     FRB_CHECK_ARG(mode >= FRB_QNORM_NONE && mode <= FRB_QNORM_EPS, "frb_normalize_rows: mode=%d", mode);
@@ -176,10 +178,71 @@ int normalize_rows_impl(const float *x, int64_t rows, int dim, int mode, void *o
     int grid = (int)(blocks < (int64_t)sm_count() * 8 ? blocks : (int64_t)sm_count() * 8);
     if (grid < 1) grid = 1;
     if (out_dtype == FRB_F32)
-        normalize_rows_kernel<float><<<grid, 256, 0, st>>>(x, rows, dim, mode, (float *)out, neg_inf_fill);
+        normalize_rows_kernel<float><<<grid, 256, 0, st>>>(x, rows, dim, mode, (float *)out, neg_inf_fill, zero_fill);
     else
-        normalize_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, rows, dim, mode, (__nv_bfloat16 *)out, neg_inf_fill);
+        normalize_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, rows, dim, mode, (__nv_bfloat16 *)out, neg_inf_fill, zero_fill);
     FRB_LAUNCH_OK("normalize_rows_kernel");
+    return FRB_OK;
+}
+
+// Compact candidate merge: query q owns cnt[q] unordered (score, row) candidates at cand[q * cap ...].
+// One warp per query: lanes take candidates round-robin into private sorted lists, then k rounds of a
+// warp-wide arg-best over the lane heads.  Total order (key, then lowest row) => order-independent result.
+template <bool LARGEST>
+__global__ void __launch_bounds__(256) topk_merge_compact_kernel(const float *__restrict__ cs, const int64_t *__restrict__ ci,
+                                                                 const int *__restrict__ cnt, int64_t cap, int64_t n_query,
+                                                                 int k, float *__restrict__ os, int64_t *__restrict__ oi)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= n_query) return;
+    int64_t n = cnt[q];
+    if (n > cap) n = cap;
+    float s[FRB_MAX_K];
+    int64_t id[FRB_MAX_K];
+    list_init<LARGEST>(s, id, k);
+    for (int64_t i = lane; i < n; i += 32) {
+        const float v = cs[q * cap + i];
+        const int64_t idx = ci[q * cap + i];
+        if (idx < 0 || !better<LARGEST>(v, idx, s[k - 1], id[k - 1])) continue;
+        int p = k - 1;
+        while (p > 0 && better<LARGEST>(v, idx, s[p - 1], id[p - 1])) {
+            s[p] = s[p - 1];
+            id[p] = id[p - 1];
+            --p;
+        }
+        s[p] = v;
+        id[p] = idx;
+    }
+    int head = 0;
+    for (int r = 0; r < k; r++) {
+        float v = head < k ? s[head] : worst_value<LARGEST>();
+        int64_t idx = head < k ? id[head] : -1;
+        const int64_t mine = idx;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int64_t oidx = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (better<LARGEST>(ov, oidx, v, idx)) { v = ov; idx = oidx; }
+        }
+        if (idx >= 0 && mine == idx) head++;
+        if (lane == 0) {
+            os[q * k + r] = idx >= 0 ? v : worst_value<LARGEST>();
+            oi[q * k + r] = idx;
+        }
+    }
+}
+
+int topk_merge_compact(const float *cs, const int64_t *ci, const int *cnt, int64_t cap, int64_t n_query, int k, int largest,
+                       float *os, int64_t *oi, cudaStream_t st)
+{
+    if (n_query == 0) return FRB_OK;
+    const int grid = (int)((n_query + 7) / 8);
+    if (largest)
+        topk_merge_compact_kernel<true><<<grid, 256, 0, st>>>(cs, ci, cnt, cap, n_query, k, os, oi);
+    else
+        topk_merge_compact_kernel<false><<<grid, 256, 0, st>>>(cs, ci, cnt, cap, n_query, k, os, oi);
+    FRB_LAUNCH_OK("topk_merge_compact_kernel");
     return FRB_OK;
 }
 
@@ -249,7 +312,7 @@ int frb_row_norms_f32(const float *x, int64_t rows, int dim, float *out, void *s
 
 int frb_normalize_rows(const float *x, int64_t rows, int dim, int mode, void *out, int out_dtype, void *stream)
 {
-    return normalize_rows_impl(x, rows, dim, mode, out, out_dtype, nullptr, (cudaStream_t)stream);
+    return normalize_rows_impl(x, rows, dim, mode, out, out_dtype, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int frb_topk_merge(const float *cs, const int64_t *ci, int n_lists, int64_t n_query, int k, int largest,

@@ -225,12 +225,13 @@ struct TcParams {
     int stages;            // B ring depth
     int64_t n_qtiles, tiles_per_group, n_groups;  // units of THIS launch = n_qtiles * n_groups
     int64_t tile_begin, tile_end;                 // gallery tiles [tile_begin, tile_end) are scanned by this launch
-    int64_t group_base;                           // candidate lists go to group slot group_base + grp
     int k;
     int prefetch_dist;     // gallery tiles prefetched into L2 ahead of the TMA loads (0 = off)
     int64_t idx_base;
     float *thr;            // [n_query] shared admission thresholds, -inf on entry
-    float *cand_scores;    // [n_groups, n_query, k]
+    int *cand_cnt;         // [n_query] candidates appended so far, 0 on entry
+    int64_t cand_cap;      // slots per query = (total groups) * k: every unit can always append its whole list
+    float *cand_scores;    // [n_query, cand_cap] unordered
     int64_t *cand_idx;
 };
 
@@ -429,18 +430,28 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 }
             }
             if (q_live) {
-                const int64_t o = ((p.group_base + grp) * p.n_query + q) * p.k;
+                // append this unit's admitted rows to the query's compact candidate buffer
+                int nv = 0;
                 if (REG_LIST) {
 #pragma unroll
-                    for (int j = 0; j < kTcRegK; j++)
-                        if (j < p.k) {
-                            p.cand_scores[o + j] = rs[j];
-                            p.cand_idx[o + j] = ri[j] < 0 ? (int64_t)-1 : p.idx_base + unit_n0 + ri[j];
-                        }
+                    for (int j = 0; j < kTcRegK; j++) nv += (j < p.k && ri[j] >= 0) ? 1 : 0;
                 } else {
-                    for (int j = 0; j < p.k; j++) {
-                        p.cand_scores[o + j] = best_s[j];
-                        p.cand_idx[o + j] = best_i[j];
+                    for (int j = 0; j < p.k; j++) nv += best_i[j] >= 0 ? 1 : 0;
+                }
+                if (nv > 0) {
+                    const int64_t o = q * p.cand_cap + atomicAdd(p.cand_cnt + q, nv);
+                    if (REG_LIST) {
+#pragma unroll
+                        for (int j = 0; j < kTcRegK; j++)
+                            if (j < nv) {
+                                p.cand_scores[o + j] = rs[j];
+                                p.cand_idx[o + j] = p.idx_base + unit_n0 + ri[j];
+                            }
+                    } else {
+                        for (int j = 0; j < nv; j++) {
+                            p.cand_scores[o + j] = best_s[j];
+                            p.cand_idx[o + j] = best_i[j];
+                        }
                     }
                 }
             }
@@ -507,7 +518,7 @@ struct TcPass {
 struct TcPlan {
     int64_t n_qtiles, n_tiles, n_groups;  // n_groups = total candidate lists per query
     TcPass warm, main;                     // warm.n_groups == 0: single pass
-    size_t qbf16_bytes, thr_bytes, idx_bytes, score_bytes;
+    size_t qbf16_bytes, thr_bytes, cnt_bytes, idx_bytes, score_bytes;
 };
 
 static void tc_split(int64_t tile_begin, int64_t tile_end, int64_t want_groups, int64_t group_base, TcPass *ps)
@@ -552,6 +563,7 @@ static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
     size_t n = (size_t)pl.n_groups * (size_t)nq * (size_t)k;
     pl.qbf16_bytes = align_up((size_t)pl.n_qtiles * kTcBlockM * (size_t)dim * 2, 1024);
     pl.thr_bytes = align_up((size_t)nq * sizeof(float), 256);
+    pl.cnt_bytes = align_up((size_t)nq * sizeof(int), 256);
     pl.idx_bytes = align_up(n * sizeof(int64_t), 256);
     pl.score_bytes = align_up(n * sizeof(float), 256);
     return pl;
@@ -560,7 +572,7 @@ static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
 size_t cosine_tc_workspace_bytes(int64_t n_query, int64_t n_gallery, int dim, int k)
 {
     TcPlan pl = tc_plan(n_query, n_gallery, dim, k);
-    return pl.qbf16_bytes + pl.thr_bytes + pl.idx_bytes + pl.score_bytes;
+    return pl.qbf16_bytes + pl.thr_bytes + pl.cnt_bytes + pl.idx_bytes + pl.score_bytes;
 }
 
 int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16, int64_t ng, int dim, int qnorm_mode, int k,
@@ -582,12 +594,13 @@ int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16,
     char *w = (char *)ws;
     __nv_bfloat16 *qb = (__nv_bfloat16 *)w;
     float *thr = (float *)(w + pl.qbf16_bytes);
-    int64_t *ci = (int64_t *)(w + pl.qbf16_bytes + pl.thr_bytes);
-    float *cs = (float *)(w + pl.qbf16_bytes + pl.thr_bytes + pl.idx_bytes);
+    int *cnt = (int *)(w + pl.qbf16_bytes + pl.thr_bytes);
+    int64_t *ci = (int64_t *)(w + pl.qbf16_bytes + pl.thr_bytes + pl.cnt_bytes);
+    float *cs = (float *)(w + pl.qbf16_bytes + pl.thr_bytes + pl.cnt_bytes + pl.idx_bytes);
 
     // prologue: L2-normalise in fp32, round to bf16 (rows beyond n_query are never read: TMA zero-fills)
-    // the same launch resets the shared admission thresholds to -inf
-    int rc = normalize_rows_impl(queries, nq, dim, qnorm_mode, qb, FRB_BF16, thr, st);
+    // the same launch resets the shared admission thresholds (-inf) and the candidate counters (0)
+    int rc = normalize_rows_impl(queries, nq, dim, qnorm_mode, qb, FRB_BF16, thr, cnt, st);
     if (rc != FRB_OK) return rc;
 
     CUtensorMap tq, tg, tpf;
@@ -619,14 +632,26 @@ int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16,
     if (const char *e = getenv("FRB_TC_PREFETCH_DIST")) p.prefetch_dist = atoi(e);  // tuning knob for experiments
     p.idx_base = idx_base;
     p.thr = thr;
+    p.cand_cnt = cnt;
+    p.cand_cap = pl.n_groups * k;
     p.cand_scores = cs;
     p.cand_idx = ci;
     const size_t smem = 1024 + a_bytes + (size_t)stages * kTcBBytesPerStage + sizeof(TcBarriers);
     const bool reg_list = k <= kTcRegK;
-    if (reg_list)
-        FRB_CUDA_OK(cudaFuncSetAttribute(cosine_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else
-        FRB_CUDA_OK(cudaFuncSetAttribute(cosine_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        // opt in to >48 KB dynamic shared memory once per (device, kernel variant, size)
+        static thread_local int attr_dev[2] = {-1, -1};
+        static thread_local size_t attr_smem[2] = {0, 0};
+        const int v = reg_list ? 1 : 0;
+        if (attr_dev[v] != dev || attr_smem[v] < smem) {
+            if (reg_list)
+                FRB_CUDA_OK(cudaFuncSetAttribute(cosine_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else
+                FRB_CUDA_OK(cudaFuncSetAttribute(cosine_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_dev[v] = dev;
+            attr_smem[v] = smem;
+        }
+    }
     const int sms = sm_count();
     const TcPass passes[2] = {pl.warm, pl.main};
     for (int ip = 0; ip < 2; ip++) {
@@ -636,7 +661,6 @@ int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16,
         p.n_groups = ps.n_groups;
         p.tile_begin = ps.tile_begin;
         p.tile_end = ng > 0 ? ps.tile_end : ps.tile_begin;  // empty gallery: units run with no tiles and emit empty lists
-        p.group_base = ps.group_base;
         const int64_t n_units = pl.n_qtiles * ps.n_groups;
         const int grid = (int)(n_units < sms ? n_units : sms);
         ProfileScope prof(FRB_K_COSINE_TC, st);
@@ -646,7 +670,7 @@ int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16,
             cosine_tc_kernel<false><<<grid, kTcThreads, smem, st>>>(tq, tg, tpf, p);
         FRB_LAUNCH_OK("cosine_tc_kernel");
     }
-    return frb_topk_merge(cs, ci, (int)pl.n_groups, nq, k, /*largest=*/1, out_scores, out_idx, st);
+    return topk_merge_compact(cs, ci, cnt, p.cand_cap, nq, k, /*largest=*/1, out_scores, out_idx, st);
 }
 
 }  // namespace frb

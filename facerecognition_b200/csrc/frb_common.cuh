@@ -18,9 +18,13 @@ void set_error(const char *fmt, ...);
 
 int sm_count();  // cached multiProcessorCount of the current device
 
-// frb_normalize_rows with an optional per-row float scratch that the same launch resets to -inf
+// frb_normalize_rows with optional per-row scratch arrays that the same launch resets (-inf floats, zero ints)
 int normalize_rows_impl(const float *x, int64_t rows, int dim, int mode, void *out, int out_dtype, float *neg_inf_fill,
-                        cudaStream_t st);
+                        int *zero_fill, cudaStream_t st);
+
+// merge of compact per-query candidate buffers: cand[q * cap + i], i < cnt[q]  (core.cu)
+int topk_merge_compact(const float *cs, const int64_t *ci, const int *cnt, int64_t cap, int64_t n_query, int k, int largest,
+                       float *os, int64_t *oi, cudaStream_t st);
 
 #define FRB_CHECK_ARG(cond, ...)                \
     do {                                        \
