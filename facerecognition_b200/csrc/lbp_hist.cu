@@ -12,7 +12,9 @@
 //   * axis bits (n = 0,2,4,6): the weights degenerate to (1, ~6e-17, 0, 0), so bit = neighbour >= centre;
 //   * diagonal bits: for an integer centre c in 0..255, (t > c) || |t - c| < 2^-23  <=>  t >= thr(c) with
 //     thr(1) = 1 - 2^-24 and thr(c) = c otherwise (float spacing at c >= 2 is >= 2^-23).
-// The blend itself uses __fmul_rn / __fadd_rn in OpenCV's left-to-right order so ptxas cannot contract it.
+// The blend itself uses __fmul_rn / __fadd_rn (and their packed f32x2 forms) in OpenCV's left-to-right order;
+// this file is compiled with --fmad=false because nvcc DOES contract __fmul2_rn + __fadd2_rn into FFMA2
+// otherwise (seen in SASS), which would round once where OpenCV rounds twice.
 //
 // Layout.  One CTA per image at a time (persistent, grid-stride).  The image is staged in shared
 // memory; warp w owns cell-row ("band") w: lanes walk down image columns with a rolling 3x3 window
@@ -79,64 +81,246 @@ __global__ void __launch_bounds__(256) lbp_codes_kernel(const uint8_t *__restric
 }
 
 // ---- codes + grid histograms ----------------------------------------------------------------------
-constexpr int kLbpThreads = 256;
+// The kernel is issue-bound (the exact float32 blend is ~17 flops per code, plus 8 compares), so the design
+// goal is the fewest issue slots per code:
+//   * every float op is a packed f32x2 instruction (FMUL2 / FADD2, sm_100a): a thread walks the SAME pair of
+//     code columns down TWO cell rows ("bands") half a grid apart, lane .x = upper band, lane .y = lower
+//     band, so both lanes always execute the same instruction stream and no operand ever needs re-pairing;
+//   * a source row is loaded once (two 16-bit shared loads per lane), converted once, and the products it
+//     contributes to its neighbours' blends are formed once (A*v, B*v; C*v for the centres); three row slots
+//     rotate through an unrolled-by-3 loop so nothing is copied;
+//   * compares are subtractions whose SIGN is the (inverted) bit: axis bits  nb - c, diagonal bits
+//     t - thr with thr = c - 2^-24 rounded to float32 (== c for c >= 2, 1 - 2^-24 for c = 1, < 0 for c = 0:
+//     exactly the thr(c) of the header comment); a funnel shift per bit collects the signs;
+//   * a u32 counter word holds bin `code` of BOTH lanes' cells (low half = upper band, high half = lower band), so
+//     lane .x always adds 1 and lane .y always adds 0x10000 at word `code` of the cell pair: no value select, no
+//     predicate (a column past the grid goes to a scratch pair).  Pairs are 260 words apart, so the popular codes
+//     (0, 255, ...) of neighbouring cells fall into banks 4 apart; the write-out splits the halves and stores
+//     128 bits per cell.
+constexpr unsigned kLbpPairVec = 65;  // uint4 groups per cell pair: 256 counters + 16 bytes of bank skew
+constexpr int kLbpMaxThreads = 224;  // 7 warps: 8x8 grid on 112x112 = 208 work items; 3 CTAs/SM at <= 96 registers
 
-__global__ void __launch_bounds__(kLbpThreads) lbp_hist_kernel(const uint8_t *__restrict__ img, int64_t count, int rows,
-                                                               int cols, int grid_x, int grid_y, int img_smem_bytes,
-                                                               uint16_t *__restrict__ out)
+__device__ __forceinline__ uint32_t lbp_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lbp_mbar_wait(uint64_t *bar, uint32_t parity)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    uint8_t *s_img = smem;
-    uint32_t *s_hist = reinterpret_cast<uint32_t *>(smem + img_smem_bytes);  // [grid_y*grid_x][128] u16 pairs
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LBP_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra LBP_DONE;\n\t"
+        "bra LBP_WAIT;\n\t"
+        "LBP_DONE:\n\t"
+        "}" ::"r"(lbp_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// one elected thread: arm the barrier with the byte count and start a 1-D bulk (TMA) copy global -> shared
+__device__ __forceinline__ void lbp_bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lbp_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(lbp_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(lbp_smem_u32(bar))
+                 : "memory");
+}
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kLbpThreads >> 5;
-    const int ocols = cols - 2, orows = rows - 2;
-    const int cw = ocols / grid_x, ch = orows / grid_y;
-    const int used_cols = cw * grid_x;
-    const int hist_words = grid_x * grid_y * 128;
-    const int img_bytes = rows * cols;
-    const bool vec_ok = ((img_bytes & 15) == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0);
+struct LbpRow2 {
+    float2 v[4];  // raw pixels of source columns x0..x0+3 (lane .x / .y = the two bands)
+    float2 b[4];  // B * v
+    float2 a[2];  // A * v for the two centre columns x0+1, x0+2
+};
 
-    for (int w = tid; w < hist_words / 4; w += kLbpThreads) reinterpret_cast<uint4 *>(s_hist)[w] = make_uint4(0, 0, 0, 0);
+__device__ __forceinline__ float2 f2(float x) { return make_float2(x, x); }
 
-    for (int64_t b = blockIdx.x; b < count; b += gridDim.x) {
-        // stage the image (128-bit when every image starts 16-byte aligned)
-        const uint8_t *src = img + b * img_bytes;
-        if (vec_ok) {
-            const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
-            for (int w = tid; w < img_bytes / 16; w += kLbpThreads) reinterpret_cast<uint4 *>(s_img)[w] = __ldg(s4 + w);
-        } else {
-            for (int w = tid; w < img_bytes; w += kLbpThreads) s_img[w] = __ldg(src + w);
+// Rounded product that ptxas cannot contract into a following add.  ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2
+// into FFMA2 despite the explicit .rn, also with -fmad=false (seen in SASS); that would round once where OpenCV
+// rounds twice.  fma(a, b, +0) rounds a*b exactly once, equals the product for every non-negative product
+// (all of ours; it differs from mul only in turning -0 into +0, which is why no optimiser may rewrite it as a
+// mul), and an FMA result cannot be fused a second time.
+__device__ __forceinline__ float2 mul2_exact(float2 a, float2 b) { return __ffma2_rn(a, b, f2(0.0f)); }
+
+template <bool ALIGNED16>
+__device__ __forceinline__ void lbp_load_row2(LbpRow2 &r, const uint8_t *px, const uint8_t *py)
+{
+    const float2 A = f2(__uint_as_float(0x3e5413cdu)), B = f2(__uint_as_float(0x3effffffu));
+    unsigned mx[4], my[4];  // 0x4B0000pp: the byte in the mantissa of 2^23
+    if (ALIGNED16) {
+        const unsigned lx = *reinterpret_cast<const uint16_t *>(px), hx = *reinterpret_cast<const uint16_t *>(px + 2);
+        const unsigned ly = *reinterpret_cast<const uint16_t *>(py), hy = *reinterpret_cast<const uint16_t *>(py + 2);
+        mx[0] = __byte_perm(lx, 0x4B000000u, 0x7540); mx[1] = __byte_perm(lx, 0x4B000000u, 0x7541);
+        mx[2] = __byte_perm(hx, 0x4B000000u, 0x7540); mx[3] = __byte_perm(hx, 0x4B000000u, 0x7541);
+        my[0] = __byte_perm(ly, 0x4B000000u, 0x7540); my[1] = __byte_perm(ly, 0x4B000000u, 0x7541);
+        my[2] = __byte_perm(hy, 0x4B000000u, 0x7540); my[3] = __byte_perm(hy, 0x4B000000u, 0x7541);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            mx[i] = 0x4B000000u | px[i];
+            my[i] = 0x4B000000u | py[i];
         }
-        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        r.v[i] = __fadd2_rn(make_float2(__uint_as_float(mx[i]), __uint_as_float(my[i])), f2(-8388608.0f));
+        r.b[i] = mul2_exact(B, r.v[i]);
+    }
+    r.a[0] = mul2_exact(A, r.v[1]);
+    r.a[1] = mul2_exact(A, r.v[2]);
+}
 
-        for (int band = warp; band < grid_y; band += nwarps) {
-            const int y0 = band * ch;  // first code row of the band == first source row of its window
-            for (int x = lane; x < used_cols; x += 32) {
-                uint32_t *cell = s_hist + (band * grid_x + x / cw) * 128;
-                const uint8_t *p = s_img + y0 * cols + x;
-                float a = u8_to_f32(p[0]), bb = u8_to_f32(p[1]), c = u8_to_f32(p[2]);
-                p += cols;
-                float d = u8_to_f32(p[0]), e = u8_to_f32(p[1]), f = u8_to_f32(p[2]);
-                for (int y = 0; y < ch; y++) {
-                    p += cols;
-                    float g = u8_to_f32(p[0]), h = u8_to_f32(p[1]), i = u8_to_f32(p[2]);
-                    unsigned code = lbp_code_r1p8(a, bb, c, d, e, f, g, h, i);
-                    atomicAdd(cell + (code >> 1), 1u + (code & 1u) * 0xFFFFu);
-                    a = d; bb = e; c = f;
-                    d = g; e = h; f = i;
+// Adds the codes of the two centre columns (both lanes) of `mid` to their cell pairs.  Same blends, same order
+// as lbp_code_r1p8.  pair_last[q]: shared-space byte address of bin 255 of column q's cell pair.
+struct LbpCells {
+    unsigned pair_last[2];
+};
+
+__device__ __forceinline__ unsigned sign_in(unsigned acc, float r)
+{
+    return __funnelshift_l(__float_as_uint(r), acc, 1);  // (acc << 1) | sign(r)
+}
+
+// not_code < 256 (exactly eight sign bits were shifted into a zero), so bin = 255 - not_code and the counter
+// address is one multiply-add off the pair's LAST word.  volatile keeps the reduction ordered against the block
+// barriers; no memory clobber, so the next row's shared loads may be scheduled above it.
+__device__ __forceinline__ void lbp_hist_add(unsigned pair_last, unsigned not_code, unsigned one)
+{
+    const unsigned addr = pair_last - (not_code << 2);
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(one));
+}
+
+__device__ __forceinline__ void lbp_emit_row2(const LbpRow2 &top, const LbpRow2 &mid, const LbpRow2 &bot, const LbpCells &cells)
+{
+    const float2 A = f2(__uint_as_float(0x3e5413cdu)), C = f2(__uint_as_float(0x3dafb0ceu));
+    const float2 a0 = mul2_exact(A, mid.v[0]), a3 = mul2_exact(A, mid.v[3]);
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const float2 e = mid.v[q + 1], m1 = f2(-1.0f);
+        // -(thr(centre)) = 2^-24 - e; the products by -1 below are exact, so these FMAs round once like the FADDs they replace
+        const float2 nthr = __ffma2_rn(e, m1, f2(5.9604644775390625e-08f));
+        const float2 Ce = mul2_exact(C, mid.v[q + 1]);
+        const float2 aL = q == 0 ? a0 : mid.a[0];          // A * mid[q]
+        const float2 aR = q == 0 ? mid.a[1] : a3;          // A * mid[q + 2]
+        // n=1 (NE): A*N + B*NE + C*e + A*E        n=3 (NW): B*NW + A*N + A*W + C*e
+        // n=5 (SW): A*W + C*e + B*SW + A*S        n=7 (SE): C*e + A*E + A*S + B*SE
+        const float2 t1 = __fadd2_rn(__fadd2_rn(__fadd2_rn(top.a[q], top.b[q + 2]), Ce), aR);
+        const float2 t3 = __fadd2_rn(__fadd2_rn(__fadd2_rn(top.b[q], top.a[q]), aL), Ce);
+        const float2 t5 = __fadd2_rn(__fadd2_rn(__fadd2_rn(aL, Ce), bot.b[q]), bot.a[q]);
+        const float2 t7 = __fadd2_rn(__fadd2_rn(__fadd2_rn(Ce, aR), bot.a[q]), bot.b[q + 2]);
+        const float2 r7 = __fadd2_rn(t7, nthr), r6 = __ffma2_rn(e, m1, bot.v[q + 1]);
+        const float2 r5 = __fadd2_rn(t5, nthr), r4 = __ffma2_rn(e, m1, mid.v[q]);
+        const float2 r3 = __fadd2_rn(t3, nthr), r2 = __ffma2_rn(e, m1, top.v[q + 1]);
+        const float2 r1 = __fadd2_rn(t1, nthr), r0 = __ffma2_rn(e, m1, mid.v[q + 2]);
+        unsigned ax = 0, ay = 0;  // sign bits = NOT code
+        ax = sign_in(ax, r7.x); ay = sign_in(ay, r7.y);
+        ax = sign_in(ax, r6.x); ay = sign_in(ay, r6.y);
+        ax = sign_in(ax, r5.x); ay = sign_in(ay, r5.y);
+        ax = sign_in(ax, r4.x); ay = sign_in(ay, r4.y);
+        ax = sign_in(ax, r3.x); ay = sign_in(ay, r3.y);
+        ax = sign_in(ax, r2.x); ay = sign_in(ay, r2.y);
+        ax = sign_in(ax, r1.x); ay = sign_in(ay, r1.y);
+        ax = sign_in(ax, r0.x); ay = sign_in(ay, r0.y);
+        lbp_hist_add(cells.pair_last[q], ax, 1u);
+        lbp_hist_add(cells.pair_last[q], ay, 0x10000u);
+    }
+}
+
+template <bool ALIGNED16>
+__global__ void __launch_bounds__(kLbpMaxThreads, 3) lbp_hist_kernel(const uint8_t *__restrict__ img, int64_t count, int rows,
+                                                                     int cols, int grid_x, int grid_y, int img_smem_bytes,
+                                                                     uint16_t *__restrict__ out)
+{
+    // shared: [2 mbarriers][image buffer 0][image buffer 1][counters]
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem);
+    uint8_t *s_img0 = smem + 16;
+    // [half * grid_x cell pairs + 1 scratch pair][256 bins] u32 = (upper band count) | (lower band count) << 16
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(smem + 16 + 2 * img_smem_bytes);
+
+    const unsigned tid = threadIdx.x, nthreads = blockDim.x;
+    const unsigned ocols = cols - 2, orows = rows - 2;
+    const unsigned gx = grid_x, gy = grid_y;
+    const unsigned cw = ocols / gx, ch = orows / gy;
+    const unsigned used_cols = cw * gx;
+    const unsigned strips = (used_cols + 1) >> 1;
+    const unsigned half = (gy + 1) >> 1;  // lane .y works `half` bands below lane .x
+    const unsigned items = strips * half;
+    const unsigned pairs = half * gx;
+    const unsigned hist_vec = (pairs + 1) * kLbpPairVec;  // uint4 groups, scratch pair included
+    const unsigned img_bytes = rows * cols;
+    // images that start 16-byte aligned are staged by the TMA (1-D bulk copy), one image ahead of the compute
+    const bool bulk_ok = ((img_bytes & 15) == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0);
+    const unsigned hist_addr = lbp_smem_u32(s_hist);
+
+    for (unsigned w = tid; w < hist_vec; w += nthreads) reinterpret_cast<uint4 *>(s_hist)[w] = make_uint4(0, 0, 0, 0);
+    // a buffer is read 2 bytes past the last pixel by the right-most strip: keep that defined
+    if (tid < 32) s_img0[(tid >> 4) * img_smem_bytes + img_smem_bytes - 16 + (tid & 15)] = 0;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lbp_smem_u32(&s_bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lbp_smem_u32(&s_bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (bulk_ok && tid == 0 && (int64_t)blockIdx.x < count)
+        lbp_bulk_load(s_img0, img + (int64_t)blockIdx.x * img_bytes, img_bytes, &s_bar[0]);
+
+    unsigned n = 0;
+    for (int64_t b = blockIdx.x; b < count; b += gridDim.x, n++) {
+        const unsigned buf = n & 1;
+        const uint8_t *s_img = s_img0 + buf * img_smem_bytes;
+        if (bulk_ok) {
+            // the other buffer was last read while image n-1 was coded, two block barriers ago
+            if (tid == 0 && b + gridDim.x < count)
+                lbp_bulk_load(s_img0 + (buf ^ 1) * img_smem_bytes, img + (b + gridDim.x) * img_bytes, img_bytes, &s_bar[buf ^ 1]);
+            lbp_mbar_wait(&s_bar[buf], (n >> 1) & 1);
+        } else {
+            const uint8_t *src = img + b * img_bytes;
+            uint8_t *dst = s_img0 + buf * img_smem_bytes;
+            for (unsigned w = tid; w < img_bytes; w += nthreads) dst[w] = __ldg(src + w);
+            __syncthreads();
+        }
+
+        for (unsigned it = tid; it < items; it += nthreads) {
+            const unsigned band = it / strips, x0 = (it - band * strips) * 2;
+            const bool two = x0 + 1 < used_cols;
+            const bool lane_y = band + half < gy;  // false only for the last band of an odd grid: its high halves are never read
+            const unsigned cx0 = x0 / cw, cx1 = (x0 + 1) / cw;
+            LbpCells cells;
+            cells.pair_last[0] = hist_addr + (band * gx + cx0) * (kLbpPairVec * 16) + 1020;
+            cells.pair_last[1] = hist_addr + (two ? band * gx + cx1 : pairs) * (kLbpPairVec * 16) + 1020;
+            const uint8_t *p = s_img + band * ch * cols + x0;
+            const unsigned dy = lane_y ? half * ch * cols : 0;  // an absent lower band re-reads the upper one
+            LbpRow2 r[3];
+            lbp_load_row2<ALIGNED16>(r[0], p, p + dy);
+            lbp_load_row2<ALIGNED16>(r[1], p + cols, p + cols + dy);
+            p += 2 * cols;
+            for (unsigned y = 0; y < ch; y += 3) {
+#pragma unroll
+                for (int ph = 0; ph < 3; ph++) {
+                    if (y + ph < ch) {
+                        lbp_load_row2<ALIGNED16>(r[(ph + 2) % 3], p, p + dy);
+                        p += cols;
+                        lbp_emit_row2(r[ph % 3], r[(ph + 1) % 3], r[(ph + 2) % 3], cells);
+                    }
                 }
             }
         }
         __syncthreads();
 
-        // write-out (already in [cell][bin] u16 order) and clear for the next image
-        uint4 *dst = reinterpret_cast<uint4 *>(out + b * (int64_t)hist_words * 2);
-        for (int w = tid; w < hist_words / 4; w += kLbpThreads) {
-            dst[w] = reinterpret_cast<uint4 *>(s_hist)[w];
-            reinterpret_cast<uint4 *>(s_hist)[w] = make_uint4(0, 0, 0, 0);
+        // write-out: 8 bins of a cell pair per step = two 16-byte groups -> low halves to the upper cell, high halves
+        // to the lower cell ([cell][bin] u16 order, 128-bit stores); the same thread clears them for the next image
+        uint4 *dst = reinterpret_cast<uint4 *>(out + b * (int64_t)gx * gy * 256);
+        for (unsigned w = tid; w < pairs * 32; w += nthreads) {
+            const unsigned pair = w >> 5, j = w & 31;
+            uint4 *grp = reinterpret_cast<uint4 *>(s_hist) + pair * kLbpPairVec + 2 * j;
+            const uint4 u = grp[0], v = grp[1];
+            grp[0] = make_uint4(0, 0, 0, 0);
+            grp[1] = make_uint4(0, 0, 0, 0);
+            dst[pair * 32 + j] = make_uint4(__byte_perm(u.x, u.y, 0x5410), __byte_perm(u.z, u.w, 0x5410),
+                                            __byte_perm(v.x, v.y, 0x5410), __byte_perm(v.z, v.w, 0x5410));
+            if (pair + half * gx < gx * gy)
+                dst[(pair + half * gx) * 32 + j] = make_uint4(__byte_perm(u.x, u.y, 0x7632), __byte_perm(u.z, u.w, 0x7632),
+                                                               __byte_perm(v.x, v.y, 0x7632), __byte_perm(v.z, v.w, 0x7632));
         }
-        // the barrier after the next staging pass orders these stores before the next atomics
+        __syncthreads();  // counters are clear before the next image's atomics
     }
 }
 
@@ -187,23 +371,39 @@ int frb_lbp_hist_u8(const uint8_t *images, int64_t count, int rows, int cols, in
     }
     if (count == 0) return FRB_OK;
     FRB_CHECK_ARG(images && out_hist, "frb_lbp_hist_u8: null pointer");
-    const int img_smem = (int)align_up((size_t)rows * cols, 16);
-    const size_t smem = (size_t)img_smem + (size_t)grid_x * grid_y * 512;
+    // +16: the right-most column pair reads up to 2 bytes past the image (zeroed, never used in a code it emits)
+    const int img_smem = (int)align_up((size_t)rows * cols, 16) + 16;
+    // counters: one u32 per (cell pair, bin), pairs = ceil(grid_y / 2) * grid_x, plus one scratch pair
+    const size_t smem = 16 + 2 * (size_t)img_smem + ((size_t)grid_x * ((grid_y + 1) / 2) + 1) * (kLbpPairVec * 16);
     if (smem > 227 * 1024) {
         set_error("frb_lbp_hist_u8: image %dx%d with grid %dx%d needs %zu B of shared memory (> 227 KB)", rows, cols,
                   grid_x, grid_y, smem);
         return FRB_ERR_UNSUPPORTED;
     }
-    FRB_CUDA_OK(cudaFuncSetAttribute(lbp_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    const bool aligned16 = (cols % 2) == 0;
+    if (aligned16)
+        FRB_CUDA_OK(cudaFuncSetAttribute(lbp_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+        FRB_CUDA_OK(cudaFuncSetAttribute(lbp_hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // one thread per (band pair, column pair) when that fits a CTA
+    const int items = ((cw * grid_x + 1) / 2) * ((grid_y + 1) / 2);
+    int threads = (items + 31) / 32 * 32;
+    if (threads < 64) threads = 64;
+    if (threads > kLbpMaxThreads) threads = kLbpMaxThreads;
+    int per_sm = 1;  // persistent grid = exactly the CTAs that can be resident
+    if (aligned16)
+        FRB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbp_hist_kernel<true>, threads, smem));
+    else
+        FRB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbp_hist_kernel<false>, threads, smem));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
     int64_t cap = (int64_t)sm_count() * per_sm;
     int grid = (int)(count < cap ? count : cap);
     {
         ProfileScope prof(FRB_K_LBP_HIST, (cudaStream_t)stream);
-        lbp_hist_kernel<<<grid, kLbpThreads, smem, (cudaStream_t)stream>>>(images, count, rows, cols, grid_x, grid_y, img_smem,
-                                                                           out_hist);
+        if (aligned16)
+            lbp_hist_kernel<true><<<grid, threads, smem, (cudaStream_t)stream>>>(images, count, rows, cols, grid_x, grid_y, img_smem, out_hist);
+        else
+            lbp_hist_kernel<false><<<grid, threads, smem, (cudaStream_t)stream>>>(images, count, rows, cols, grid_x, grid_y, img_smem, out_hist);
     }
     FRB_LAUNCH_OK("lbp_hist_kernel");
     return FRB_OK;
