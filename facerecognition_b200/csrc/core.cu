@@ -134,8 +134,8 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float *__rest
 // One thread per query merges n_lists sorted candidate lists of length k (k <= FRB_MAX_K).
 template <bool LARGEST>
 __global__ void __launch_bounds__(128) topk_merge_kernel(const float *__restrict__ cs, const int64_t *__restrict__ ci,
-                                                         int n_lists, int64_t n_query, int k,
-                                                         float *__restrict__ os, int64_t *__restrict__ oi)
+                                                         int64_t s_stride, int64_t i_stride, int n_lists, int64_t n_query,
+                                                         int k, float *__restrict__ os, int64_t *__restrict__ oi)
 {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_query) return;
@@ -143,8 +143,8 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const float *__restrict
     int64_t id[FRB_MAX_K];
     list_init<LARGEST>(s, id, k);
     for (int l = 0; l < n_lists; l++) {
-        const float *ls = cs + ((int64_t)l * n_query + q) * k;
-        const int64_t *li = ci + ((int64_t)l * n_query + q) * k;
+        const float *ls = cs + (int64_t)l * s_stride + q * k;     // strides in elements between consecutive lists
+        const int64_t *li = ci + (int64_t)l * i_stride + q * k;
         for (int j = 0; j < k; j++) {
             float v = ls[j];
             int64_t idx = li[j];
@@ -315,20 +315,35 @@ int frb_normalize_rows(const float *x, int64_t rows, int dim, int mode, void *ou
     return normalize_rows_impl(x, rows, dim, mode, out, out_dtype, nullptr, nullptr, (cudaStream_t)stream);
 }
 
+static int topk_merge_launch(const char *fn, const float *cs, const int64_t *ci, int64_t s_stride, int64_t i_stride, int n_lists,
+                             int64_t n_query, int k, int largest, float *os, int64_t *oi, void *stream)
+{
+    FRB_CHECK_ARG(n_lists >= 1 && n_query >= 0 && k >= 1 && k <= FRB_MAX_K, "%s: n_lists=%d n_query=%lld k=%d", fn, n_lists,
+                  (long long)n_query, k);
+    if (n_query == 0) return FRB_OK;
+    FRB_CHECK_ARG(cs && ci && os && oi, "%s: null pointer", fn);
+    FRB_CHECK_ARG(s_stride >= n_query * k && i_stride >= n_query * k, "%s: list strides %lld / %lld < n_query * k", fn,
+                  (long long)s_stride, (long long)i_stride);
+    int grid = (int)((n_query + 127) / 128);
+    if (largest)
+        topk_merge_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(cs, ci, s_stride, i_stride, n_lists, n_query, k, os, oi);
+    else
+        topk_merge_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(cs, ci, s_stride, i_stride, n_lists, n_query, k, os, oi);
+    FRB_LAUNCH_OK("topk_merge_kernel");
+    return FRB_OK;
+}
+
 int frb_topk_merge(const float *cs, const int64_t *ci, int n_lists, int64_t n_query, int k, int largest,
                    float *os, int64_t *oi, void *stream)
 {
-    FRB_CHECK_ARG(n_lists >= 1 && n_query >= 0 && k >= 1 && k <= FRB_MAX_K,
-                  "frb_topk_merge: n_lists=%d n_query=%lld k=%d", n_lists, (long long)n_query, k);
-    if (n_query == 0) return FRB_OK;
-    FRB_CHECK_ARG(cs && ci && os && oi, "frb_topk_merge: null pointer");
-    int grid = (int)((n_query + 127) / 128);
-    if (largest)
-        topk_merge_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(cs, ci, n_lists, n_query, k, os, oi);
-    else
-        topk_merge_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(cs, ci, n_lists, n_query, k, os, oi);
-    FRB_LAUNCH_OK("topk_merge_kernel");
-    return FRB_OK;
+    return topk_merge_launch("frb_topk_merge", cs, ci, n_query * k, n_query * k, n_lists, n_query, k, largest, os, oi, stream);
+}
+
+int frb_topk_merge_strided(const float *cs, const int64_t *ci, int64_t score_list_stride, int64_t idx_list_stride, int n_lists,
+                           int64_t n_query, int k, int largest, float *os, int64_t *oi, void *stream)
+{
+    return topk_merge_launch("frb_topk_merge_strided", cs, ci, score_list_stride, idx_list_stride, n_lists, n_query, k, largest,
+                             os, oi, stream);
 }
 
 }  // extern "C"

@@ -101,6 +101,33 @@ def topk_merge(cand_scores: torch.Tensor, cand_idx: torch.Tensor, largest: bool)
     return scores, idx
 
 
+def packed_candidates(n_query: int, k: int, device: torch.device, n_lists: int = 1
+                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """One byte buffer [n_lists, record] whose record is {ids i64 [Q, k] | scores f32 [Q, k]} (ids first, so both
+    views are naturally aligned), plus the (scores, idx) views of list 0 when n_lists == 1.  A single all-gather of
+    such records feeds `topk_merge_packed`."""
+    rec = n_query * k * 12
+    rec_pad = (rec + 15) // 16 * 16
+    buf = torch.empty((n_lists, rec_pad), dtype=torch.uint8, device=device)
+    idx = buf[0, :n_query * k * 8].view(torch.int64).view(n_query, k)
+    scores = buf[0, n_query * k * 8:rec].view(torch.float32).view(n_query, k)
+    return buf, scores, idx
+
+
+def topk_merge_packed(buf: torch.Tensor, n_query: int, k: int, largest: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """frb_topk_merge_strided over the [R, record] buffer produced by `packed_candidates` + one all-gather."""
+    dev = _require_cuda(buf)
+    assert buf.dtype == torch.uint8 and buf.dim() == 2 and buf.shape[1] % 16 == 0 and buf.shape[1] >= n_query * k * 12
+    r, rec = buf.shape
+    scores = torch.empty((n_query, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((n_query, k), dtype=torch.int64, device=dev)
+    base = buf.data_ptr()
+    with torch.cuda.device(dev):
+        N.call("frb_topk_merge_strided", ctypes.c_void_p(base + n_query * k * 8), ctypes.c_void_p(base), _I64(rec // 4),
+               _I64(rec // 8), r, _I64(n_query), k, 1 if largest else 0, _p(scores), _p(idx), _stream(dev))
+    return scores, idx
+
+
 def lbp_codes(images: torch.Tensor, radius: int = 1, neighbors: int = 8) -> torch.Tensor:
     """frb_lbp_codes_u8: u8 [B, H, W] -> u8 [B, H-2, W-2] LBP codes (OpenCV elbp_ semantics)."""
     dev = _require_cuda(images)

@@ -2,9 +2,9 @@
 
 One process per GPU (torch.distributed, NCCL over NVLink).  Rank r owns gallery rows
 [shard_bounds(N, R, r)); queries are replicated; every rank runs the local fused search with
-idx_base = its first row, so candidates carry GLOBAL row ids; ONE all-gather of the [Q, k] (score, id)
-lists follows and every rank merges the R lists with frb_topk_merge (ties -> lowest global id, so the
-answer is identical for any R).  Nothing else crosses NVLink: shards are loaded once and never move.
+idx_base = its first row, so candidates carry GLOBAL row ids; ONE all-gather of the packed [Q, k] (id, score)
+records follows and every rank merges the R lists in place with frb_topk_merge_strided (ties -> lowest global
+id, so the answer is identical for any R).  Nothing else crosses NVLink: shards are loaded once and never move.
 
 `local_search` and `merge` are injectable so the host-side plumbing (bounds, id offsets, gather layout)
 can be exercised with the gloo backend on a CPU-only box; the product wiring below binds them to the
@@ -25,29 +25,55 @@ def shard_bounds(n_rows: int, world_size: int, rank: int) -> Tuple[int, int]:
     return lo, min(lo + per, n_rows)
 
 
-class ShardedSearch:
-    """local top-k -> all_gather -> merge.  Works for cosine (largest=True) and chi-square (largest=False)."""
+def _record_layout(n_query: int, k: int) -> Tuple[int, int, int]:
+    """Byte layout of one rank's candidate record: ids i64 [Q, k] first, then scores f32 [Q, k], padded to 16."""
+    idx_bytes = n_query * k * 8
+    rec = idx_bytes + n_query * k * 4
+    return idx_bytes, rec, (rec + 15) // 16 * 16
 
-    def __init__(self, local_search: Callable[[torch.Tensor, int], Tuple[torch.Tensor, torch.Tensor]],
-                 merge: Callable[[torch.Tensor, torch.Tensor, bool], Tuple[torch.Tensor, torch.Tensor]],
-                 largest: bool, group: Optional[dist.ProcessGroup] = None):
+
+class ShardedSearch:
+    """local top-k -> ONE all_gather -> merge.  Works for cosine (largest=True) and chi-square (largest=False).
+
+    Each rank packs its [Q, k] ids and scores into one byte record, so a single collective moves both; the merge
+    reads the gathered [R, record] buffer in place (frb_topk_merge_strided).  `local_search` / `merge` are the
+    injectable tensor-level forms used by the CPU (gloo) tests; `local_into` / `merge_packed` are the zero-copy
+    product forms."""
+
+    def __init__(self, local_search: Optional[Callable[[torch.Tensor, int], Tuple[torch.Tensor, torch.Tensor]]],
+                 merge: Optional[Callable[[torch.Tensor, torch.Tensor, bool], Tuple[torch.Tensor, torch.Tensor]]],
+                 largest: bool, group: Optional[dist.ProcessGroup] = None,
+                 local_into: Optional[Callable[[torch.Tensor, int, torch.Tensor, torch.Tensor], None]] = None,
+                 merge_packed: Optional[Callable[[torch.Tensor, int, int, bool], Tuple[torch.Tensor, torch.Tensor]]] = None):
         self.local_search, self.merge, self.largest, self.group = local_search, merge, largest, group
+        self.local_into, self.merge_packed = local_into, merge_packed
 
     def world(self) -> int:
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
 
     def search(self, queries: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        scores, idx = self.local_search(queries, k)          # [Q, k] with global ids
         world = self.world()
+        n_query = queries.shape[0]
         if world == 1:
-            return scores, idx
-        all_s = torch.empty((world,) + tuple(scores.shape), dtype=scores.dtype, device=scores.device)
-        all_i = torch.empty((world,) + tuple(idx.shape), dtype=idx.dtype, device=idx.device)
-        # one all-gather per payload; the output slices alias all_s / all_i, so the [R, Q, k] layout
-        # frb_topk_merge expects is produced in place (works for NCCL and for gloo in the CPU tests)
-        dist.all_gather(list(all_s.unbind(0)), scores.contiguous(), group=self.group)
-        dist.all_gather(list(all_i.unbind(0)), idx.contiguous(), group=self.group)
-        return self.merge(all_s, all_i, self.largest)          # [R, Q, k] -> [Q, k]
+            return self.local_search(queries, k)               # [Q, k] with global ids
+        idx_bytes, rec, rec_pad = _record_layout(n_query, k)
+        rank = dist.get_rank(self.group)
+        gathered = torch.empty((world, rec_pad), dtype=torch.uint8, device=queries.device)
+        mine = gathered[rank]                                   # in-place all-gather: my record sits in my slot
+        my_idx = mine[:idx_bytes].view(torch.int64).view(n_query, k)
+        my_scores = mine[idx_bytes:rec].view(torch.float32).view(n_query, k)
+        if self.local_into is not None:
+            self.local_into(queries, k, my_scores, my_idx)
+        else:
+            scores, idx = self.local_search(queries, k)
+            my_scores.copy_(scores)
+            my_idx.copy_(idx)
+        dist.all_gather_into_tensor(gathered.view(-1), mine, group=self.group)   # the ONE collective of the path
+        if self.merge_packed is not None:
+            return self.merge_packed(gathered, n_query, k, self.largest)
+        all_i = gathered[:, :idx_bytes].contiguous().view(torch.int64).view(world, n_query, k)
+        all_s = gathered[:, idx_bytes:rec].contiguous().view(torch.float32).view(world, n_query, k)
+        return self.merge(all_s, all_i, self.largest)           # [R, Q, k] -> [Q, k]
 
 
 def cosine_sharded(gallery_shard: torch.Tensor, row_offset: int, *, qnorm_mode: int = 0,
@@ -59,7 +85,11 @@ def cosine_sharded(gallery_shard: torch.Tensor, row_offset: int, *, qnorm_mode: 
     def local(q: torch.Tensor, k: int):
         return ops.cosine_topk(q, gallery_shard, k, score_mode=N.FRB_SCORE_IP, qnorm_mode=qnorm_mode, idx_base=row_offset)
 
-    return ShardedSearch(local, ops.topk_merge, True, group)
+    def local_into(q: torch.Tensor, k: int, scores: torch.Tensor, idx: torch.Tensor):
+        ops.cosine_topk(q, gallery_shard, k, score_mode=N.FRB_SCORE_IP, qnorm_mode=qnorm_mode, idx_base=row_offset,
+                        out=(scores, idx))
+
+    return ShardedSearch(local, ops.topk_merge, True, group, local_into=local_into, merge_packed=ops.topk_merge_packed)
 
 
 def chisq_sharded(hist_shard: torch.Tensor, cell_px: int, row_offset: int, *, q_cell_px: Optional[int] = None,
@@ -70,4 +100,4 @@ def chisq_sharded(hist_shard: torch.Tensor, cell_px: int, row_offset: int, *, q_
     def local(q_hist: torch.Tensor, k: int):
         return ops.chisq_topk(q_hist, q_cell_px or cell_px, hist_shard, cell_px, k, idx_base=row_offset)
 
-    return ShardedSearch(local, ops.topk_merge, False, group)
+    return ShardedSearch(local, ops.topk_merge, False, group, merge_packed=ops.topk_merge_packed)

@@ -122,6 +122,14 @@ int frb_cosine_topk(const float *queries_dev, int64_t n_query, const void *galle
 int frb_topk_merge(const float *cand_scores_dev, const int64_t *cand_idx_dev, int n_lists, int64_t n_query,
                    int k, int largest, float *out_scores_dev, int64_t *out_idx_dev, void *stream);
 
+/* Same merge over lists that are not back to back: list l's scores start at cand_scores + l * score_list_stride
+ * and its ids at cand_idx + l * idx_list_stride (strides in ELEMENTS, each >= n_query * k).  This is the layout
+ * ONE all-gather of a packed per-rank record {ids i64 [n_query, k] | scores f32 [n_query, k]} leaves behind
+ * (facerecognition_b200/sharded.py), so the cross-GPU exchange is a single collective. */
+int frb_topk_merge_strided(const float *cand_scores_dev, const int64_t *cand_idx_dev, int64_t score_list_stride,
+                           int64_t idx_list_stride, int n_lists, int64_t n_query, int k, int largest,
+                           float *out_scores_dev, int64_t *out_idx_dev, void *stream);
+
 /* ---- LBPH path (K2, K3) ---------------------------------------------------------------- */
 
 /* LBP codes, OpenCV elbp_ semantics (radius 1, 8 neighbours, float32 bilinear diagonals,

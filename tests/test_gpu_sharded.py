@@ -27,6 +27,13 @@ def test_cosine_shards_merge_to_unsharded_result(R):
     ms, mi = ops.topk_merge(torch.stack(cs).contiguous(), torch.stack(ci).contiguous(), largest=True)
     assert torch.equal(mi, full_i) and torch.equal(ms, full_s)
     assert mi[0, 0].item() == 5 and mi[0, 1].item() == N - 1
+    # the packed-record layout one all-gather leaves behind (sharded.py) merges in place to the same answer
+    buf, _, _ = ops.packed_candidates(Q, k, q.device, n_lists=R)
+    for r in range(R):
+        buf[r, :Q * k * 8].view(torch.int64).copy_(ci[r].reshape(-1))
+        buf[r, Q * k * 8:Q * k * 12].view(torch.float32).copy_(cs[r].reshape(-1))
+    ps, pi = ops.topk_merge_packed(buf, Q, k, largest=True)
+    assert torch.equal(pi, full_i) and torch.equal(ps, full_s)
 
 
 @pytest.mark.parametrize("R", [2, 8])
