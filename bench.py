@@ -289,6 +289,8 @@ def main():
     ap.add_argument("--queries", type=int, default=N_QUERY, help="queries per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lbph", action="store_true")
+    ap.add_argument("--min-warm-seconds", type=float, default=1.0,
+                    help="keep warming until this much time has passed under load (clock samples); 0 for ncu launch lists")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -342,7 +344,7 @@ def main():
         # ---- device-resident leg: inputs already in HBM ---------------------------------------------
         t_w = time.perf_counter()
         done = 0
-        while done < warmup or time.perf_counter() - t_w < 1.0:      # >= W steps and >= 1 s under load (clock samples)
+        while done < warmup or time.perf_counter() - t_w < args.min_warm_seconds:      # >= W steps and >= 1 s under load (clock samples)
             s, i = search.search(q_dev, TOPK)
             done += 1
             if done % 16 == 0:

@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""BASELINE.json configs other than the headline one (bench.py is configs[2]), measured through the public API.
+
+    python profiles/run_configs.py c1 c2 c5           # one GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P \
+        profiles/run_configs.py c4 c5                  # gallery sharded by identity over the ranks
+
+Prints one JSON line per config (rank 0).  Every config also checks its own answers (planted rows / self-matches /
+the CPU oracle on a sample) and reports `ok`.  CPU baselines are the oracle ports, timed on the box's host cores.
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import bench as B
+from facerecognition_b200 import _native as NV
+from facerecognition_b200 import ops
+from facerecognition_b200.sharded import chisq_sharded, cosine_sharded, shard_bounds
+
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+LOCAL = int(os.environ.get("LOCAL_RANK", "0"))
+DEV = torch.device("cuda", LOCAL)
+PEAKS = B.measured_peaks()
+
+
+def barrier():
+    if WORLD > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x):
+    t = torch.tensor([x], dtype=torch.float64, device=DEV)
+    if WORLD > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def emit(line):
+    if RANK == 0:
+        line["n_gpus"] = WORLD
+        print(json.dumps(line), flush=True)
+
+
+def device_ms(fn, steps):
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    for a, b in ev:
+        a.record()
+        out = fn()
+        b.record()
+    barrier()
+    return max_over_ranks(sum(a.elapsed_time(b) for a, b in ev)) / steps, out
+
+
+# ---- configs[0]: LBPH train + predict, 1k synthetic 100x100 faces, through the cv2.face-shaped API ---------------
+def c1():
+    from facerecognition_b200.lbph import train_lbph_model
+    from oracle import lbph as OL
+    faces = B.synthetic_faces(torch, 1000, 100, 100, DEV).cpu().numpy()
+    fresh = B.synthetic_faces(torch, 1000, 100, 100, DEV, seed=77).cpu().numpy()
+    labels = np.repeat(np.arange(100, dtype=np.int32), 10)
+    face_list = [f for f in faces]
+    train_lbph_model(face_list, labels)                                   # warm-up (module load, allocator)
+    t0 = time.perf_counter()
+    model = train_lbph_model(face_list, labels)
+    torch.cuda.synchronize()
+    t_train = time.perf_counter() - t0
+    model.predict(faces[0])
+    t0 = time.perf_counter()
+    single = [model.predict(f) for f in faces[:200]]                      # the reference's call pattern: one image per call
+    t_single = (time.perf_counter() - t0) / 200
+    t0 = time.perf_counter()
+    lab_b, dist_b = model.predict_batch(face_list)
+    lab_f, dist_f = model.predict_batch([f for f in fresh])
+    t_batch = time.perf_counter() - t0
+    ok = bool((dist_b == 0.0).all()) and all(d == 0.0 for _, d in single)   # every training face matches itself at distance 0
+    # CPU: the oracle's C restatement of OpenCV LBPH (1 thread, as cv2.face runs): extract all, then predict a sample
+    t0 = time.perf_counter()
+    hist, px = OL.c_lbp_hist(faces)
+    t_cpu_train = time.perf_counter() - t0
+    gal_f32 = OL.hist_to_f32(hist, px)
+    n_s = 100
+    hq, _ = OL.c_lbp_hist(fresh[:n_s])
+    qf32 = OL.hist_to_f32(hq, px)
+    t0 = time.perf_counter()
+    cpu_lab = []
+    for j in range(n_s):
+        d = OL.c_chisq_scan(gal_f32, qf32[j])
+        cpu_lab.append((int(labels[int(np.argmin(d))]), float(d.min())))
+    t_cpu_pred = (time.perf_counter() - t0) / n_s + t_cpu_train / 1000
+    agree = all(int(lab_f[j]) == cpu_lab[j][0] and abs(dist_f[j] - cpu_lab[j][1]) <= 1e-5 * max(cpu_lab[j][1], 1e-12) for j in range(n_s))
+    emit({"config": "configs[0]: LBPH (r=1, n=8, grid 8x8) train + predict, 1k synthetic 100x100 faces",
+          "train_faces_per_s": 1000 / t_train, "predict_single_call_per_s": 1 / t_single, "predict_batch_faces_per_s": 2000 / t_batch,
+          "api": "train_lbph_model / LBPHFaceRecognizer.predict / predict_batch (host numpy in, host results out)",
+          "cpu_baseline": {"train_faces_per_s": 1000 / t_cpu_train, "predict_per_s": 1 / t_cpu_pred, "cores": 1, "kind": "port",
+                           "sample": f"oracle C restatement of OpenCV LBPH: extract 1000 faces; {n_s} predicts against the 1000-face gallery"},
+          "ok": ok and agree, "self_match_distance_zero": ok, "matches_cpu_oracle_on_sample": agree})
+
+
+# ---- configs[1]: ArcFace 512-d cosine identification, 10k-identity dict DB, 256-query batch, fp32 ------------------
+def c2():
+    from facerecognition_b200.recognition_engine import RecognitionEngine
+    from oracle import cosine as OC
+    rng = np.random.default_rng(10)
+    n_id, n_q = 10_000, 256
+    gal = OC.l2_normalize(rng.standard_normal((n_id, 512)).astype(np.float32))
+    db = {f"id_{i:05d}": gal[i] for i in range(n_id)}
+    src = rng.integers(0, n_id, n_q)
+    q = gal[src] + 0.03 * rng.standard_normal((n_q, 512)).astype(np.float32)
+    q[:26] = rng.standard_normal((26, 512)).astype(np.float32)
+    q = OC.l2_normalize(q)
+    eng = RecognitionEngine(model_path=None, db_path=None, threshold=0.5, use_face_detection=False)
+    eng.db = db
+    eng.recognize_embeddings(q)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        res = eng.recognize_embeddings(q)
+    t_batch = (time.perf_counter() - t0) / 20
+    t0 = time.perf_counter()
+    for j in range(64):
+        one = eng.recognize_with_db(q[j])
+    t_single = (time.perf_counter() - t0) / 64
+    # kernel only, device-resident
+    g = eng.gallery()
+    qd = torch.from_numpy(q).to(g.rows.device)
+    qn = ops.row_norms(qd)
+    ms, _ = device_ms(lambda: ops.cosine_topk(qd, g.rows, 5, score_mode=NV.FRB_SCORE_REF_COSINE, q_norms=qn, g_norms=g.norms), 50)
+    # reference semantics on a sample (the reference's own loop is ~130 ms per query)
+    n_s = 8
+    t0 = time.perf_counter()
+    ref = [OC.recognize_with_db(db, q[j], 0.5) for j in list(range(n_s // 2)) + list(range(n_q - n_s // 2, n_q))]
+    t_ref = (time.perf_counter() - t0) / n_s
+    got = [res[j] for j in list(range(n_s // 2)) + list(range(n_q - n_s // 2, n_q))]
+    ok = all(a[0] == b[0] and abs(a[1] - b[1]) <= 1e-5 and [n for n, _ in a[2]] == [n for n, _ in b[2]] for a, b in zip(got, ref))
+    planted = all(res[j][0] == f"id_{src[j]:05d}" for j in range(26, n_q))
+    unknown = sum(r[0] == "Unknown" for r in res[:26])
+    t0 = time.perf_counter()
+    for _ in range(5):
+        OC.batched_topk_fast(q, gal, 5)
+    t_np = (time.perf_counter() - t0) / 5
+    emit({"config": "configs[1]: ArcFace 512-d cosine identification, 10k-identity gallery, 256-query batch, fp32, threshold 0.5",
+          "queries_per_s_api_batch": n_q / t_batch, "queries_per_s_api_single": 1 / t_single, "kernel_ms": ms,
+          "queries_per_s_kernel": n_q / (ms * 1e-3), "gflop": 2 * n_q * n_id * 512 / 1e9,
+          "api": "RecognitionEngine.recognize_embeddings (batched recognize_with_db) / recognize_with_db; host numpy in, tuples out",
+          "cpu_baseline": {"reference_loop_queries_per_s": 1 / t_ref, "numpy_batched_queries_per_s": n_q / t_np, "cores": os.cpu_count(),
+                           "kind": "port", "sample": f"oracle.cosine.recognize_with_db on {n_s} queries (1 thread, as the reference); numpy sgemm+top-k on all 256"},
+          "ok": ok and planted, "matches_reference_semantics_on_sample": ok, "planted_top1_correct": planted,
+          "random_queries_reported_unknown": f"{unknown}/26"})
+
+
+# ---- configs[3]: 100M-embedding bf16 gallery sharded by identity, NCCL all-gather top-k merge -------------------------
+def c4(n_total=100_000_000, n_query=4096, steps=5):
+    lo, hi = shard_bounds(n_total, WORLD, RANK)
+    free, _ = torch.cuda.mem_get_info(DEV)
+    if (hi - lo) * 1024 > free - (8 << 30):
+        emit({"config": "configs[3]", "skipped": f"shard of {hi - lo} rows does not fit {free >> 30} GiB free"})
+        return
+    gen_q = torch.Generator(device=DEV).manual_seed(4321)
+    src = torch.randint(0, n_total, (n_query,), generator=gen_q, device=DEV)
+    noise = torch.randn((n_query, 512), generator=gen_q, device=DEV)
+    queries = torch.zeros((n_query, 512), dtype=torch.float32, device=DEV)
+    shard = torch.empty((hi - lo, 512), dtype=torch.bfloat16, device=DEV)
+    t0 = time.perf_counter()
+    for b in range(lo // B.BLOCK_ROWS, (hi + B.BLOCK_ROWS - 1) // B.BLOCK_ROWS):      # only the blocks this rank owns
+        r0, r1 = b * B.BLOCK_ROWS, min((b + 1) * B.BLOCK_ROWS, n_total)
+        gen = torch.Generator(device=DEV).manual_seed(1234 + b)
+        rows = ops.normalize_rows(torch.randn((r1 - r0, 512), generator=gen, device=DEV), NV.FRB_QNORM_CLAMP)
+        a, e = max(lo, r0), min(hi, r1)
+        sel = (src >= a) & (src < e)
+        if bool(sel.any()):
+            queries[sel] = rows[src[sel] - r0] + 0.03 * noise[sel]
+        shard[a - lo:e - lo] = ops.normalize_rows(rows[a - r0:e - r0].contiguous(), NV.FRB_QNORM_NONE, torch.bfloat16)
+    if WORLD > 1:
+        dist.all_reduce(queries)                     # every planted query was filled by exactly one rank
+    n_rand = n_query // 10
+    queries[:n_rand] = torch.randn((n_rand, 512), generator=torch.Generator(device=DEV).manual_seed(99), device=DEV)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t0
+    search = cosine_sharded(shard, lo, qnorm_mode=NV.FRB_QNORM_CLAMP)
+    for _ in range(2):
+        s, i = search.search(queries, 5)
+    NV.profile_enable(True)
+    NV.profile_read(NV.K_COSINE_TC)
+    ms, (s, i) = device_ms(lambda: search.search(queries, 5), steps)
+    k_ms, k_n = NV.profile_read(NV.K_COSINE_TC)
+    NV.profile_enable(False)
+    ok = bool(torch.equal(i[n_rand:, 0], src[n_rand:]))
+    rand_max = float(s[:n_rand, 0].max())
+    flops = 2.0 * n_query * (hi - lo) * 512
+    ach = flops / (k_ms / steps * 1e-3) / 1e12
+    lat = {}
+    for nq in (1, 256):
+        qs = queries[n_rand:n_rand + nq].contiguous()
+        search.search(qs, 5)
+        lat[f"ms_q{nq}"], _ = device_ms(lambda: search.search(qs, 5), 3)
+    emit({"config": f"configs[3]: {n_total}-embedding bf16 gallery sharded by identity over {WORLD} GPU(s), 4096-query batch, top-5, "
+                    "one NCCL all-gather + merge", "queries_per_s": n_query / (ms * 1e-3), "ms_per_step": ms,
+          "rows_per_gpu": hi - lo, "shard_gb": (hi - lo) * 1024 / 1e9, "generate_s": t_gen,
+          "roofline": {"bound": "tensor", "achieved": ach, "peak": PEAKS["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                       "frac": ach / PEAKS["bf16_tflops_sustained"], "frac_of_burst": ach / PEAKS["bf16_tflops"],
+                       "note": "rank 0's cosine_tc_kernel launches, event-timed; sustained peak (35-300 ms steps)", "traffic": None},
+          "kernel_share_of_step": k_ms / steps / ms, "latency": lat, "ok": ok, "planted_top1_correct": ok,
+          "best_random_query_score": rand_max})
+    del shard
+
+
+# ---- configs[4]: LBPH extract + chi-square NN, 1024-frame 112x112 batch vs 1M-histogram gallery, sharded ---------------
+def c5(n_total=1_000_000, n_frames=1024, steps=2):
+    lo, hi = shard_bounds(n_total, WORLD, RANK)
+    free, _ = torch.cuda.mem_get_info(DEV)
+    if (hi - lo) * 32768 > free - (8 << 30):
+        emit({"config": "configs[4]", "skipped": f"shard of {hi - lo} histograms does not fit {free >> 30} GiB free"})
+        return
+    blk = 32768
+    hist = torch.empty((hi - lo, 16384), dtype=torch.uint16, device=DEV)
+    frames = torch.zeros((n_frames, 112, 112), dtype=torch.uint8, device=DEV)
+    gen_q = torch.Generator(device=DEV).manual_seed(555)
+    src = torch.randint(0, n_total, (n_frames,), generator=gen_q, device=DEV)
+    px = 169
+    for b in range(lo // blk, (hi + blk - 1) // blk):
+        r0, r1 = b * blk, min((b + 1) * blk, n_total)
+        faces = B.synthetic_faces(torch, r1 - r0, 112, 112, DEV, seed=9000 + b)
+        a, e = max(lo, r0), min(hi, r1)
+        h, px = ops.lbp_hist(faces[a - r0:e - r0].contiguous())
+        hist[a - lo:e - lo] = h
+        sel = (src >= a) & (src < e)
+        if bool(sel.any()):
+            frames[sel] = faces[src[sel] - r0]
+    if WORLD > 1:
+        f32 = frames.int()
+        dist.all_reduce(f32)
+        frames = f32.to(torch.uint8)
+    # half of the frames are exact gallery faces (distance 0), the other half get noise so the scan has to work
+    noisy = torch.arange(n_frames, device=DEV) % 2 == 1
+    jitter = torch.randint(0, 3, frames.shape, generator=gen_q, device=DEV, dtype=torch.uint8)
+    frames[noisy] = torch.clamp(frames[noisy].int() + jitter[noisy].int() - 1, 0, 255).to(torch.uint8)
+    search = chisq_sharded(hist, px, lo)
+
+    def step():
+        qh, qpx = ops.lbp_hist(frames)
+        return search.search(qh, 1)
+
+    step()
+    NV.profile_enable(True)
+    NV.profile_read(NV.K_CHISQ)
+    ms, (d, i) = device_ms(step, steps)
+    k_ms, k_n = NV.profile_read(NV.K_CHISQ)
+    NV.profile_enable(False)
+    exact = ~noisy
+    ok = bool((d[exact, 0] == 0).all()) and bool(((i[exact, 0] == src[exact]) | (d[exact, 0] == 0)).all())
+    noisy_hit = float((i[noisy, 0] == src[noisy]).float().mean())
+    pairs = n_frames * (hi - lo)
+    gbs = pairs * 32768 / (k_ms / steps * 1e-3) / 1e9
+    line = {"config": f"configs[4]: LBPH extract + chi-square NN, {n_frames}-frame 112x112 batch vs {n_total}-histogram gallery sharded over {WORLD} GPU(s)",
+            "faces_per_s": n_frames / (ms * 1e-3), "ms_per_step": ms, "rows_per_gpu": hi - lo, "shard_gb": (hi - lo) * 32768 / 1e9,
+            "pairs_per_s_per_gpu": pairs / (k_ms / steps * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": PEAKS["hbm_gbs"], "unit": "GB/s", "frac": gbs / PEAKS["hbm_gbs"],
+                         "note": "reference-equivalent accounting: 32768 B per (frame, gallery histogram) pair; the batched kernel re-reads "
+                                 "a gallery chunk from L2 across queries, so achieved can exceed the DRAM peak (it is MUFU-bound)", "traffic": None},
+            "kernel_share_of_step": k_ms / steps / ms, "ok": ok, "exact_frames_distance_zero": ok, "noisy_frames_top1_is_source": noisy_hit}
+    if RANK == 0 and WORLD == 1:
+        # CPU: the C oracle (1 thread, as cv2.face): extract the frames, scan a 2000-histogram sub-gallery for 8 frames
+        from oracle import lbph as OL
+        fr = frames[:64].cpu().numpy()
+        t0 = time.perf_counter()
+        hq, _ = OL.c_lbp_hist(fr)
+        t_ext = (time.perf_counter() - t0) / 64
+        sub = hist[:2000].cpu().numpy()
+        t0 = time.perf_counter()
+        for j in range(8):
+            OL.c_chisq_scan_u16(sub, px, hq[j], px)
+        t_pair = (time.perf_counter() - t0) / (8 * 2000)
+        line["cpu_baseline"] = {"faces_per_s": 1 / (t_ext + t_pair * n_total), "extract_ms": t_ext * 1e3, "us_per_histogram_compare": t_pair * 1e6,
+                                "cores": 1, "kind": "port", "sample": "oracle C: extract 64 frames; 8 frames x 2000-histogram sub-gallery, "
+                                "extrapolated linearly to the 1M gallery"}
+    emit(line)
+    del hist
+
+
+def main():
+    torch.cuda.set_device(LOCAL)
+    if WORLD > 1:
+        dist.init_process_group("nccl", device_id=DEV)
+    which = sys.argv[1:] or ["c1", "c2", "c5"]
+    for name in which:
+        if name in ("c1", "c2") and (WORLD > 1):
+            continue                                  # single-GPU configs
+        if name in ("c1", "c2") and RANK != 0:
+            continue
+        {"c1": c1, "c2": c2, "c4": c4, "c5": c5}[name]()
+        torch.cuda.empty_cache()
+    if WORLD > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
