@@ -7,65 +7,181 @@
 // Arithmetic.  With integer counts g (gallery, n_g pixels per cell) and c (query, n_q pixels per cell),
 //     d = (2 / n_g) * sum_j (g_j - q~_j)^2 / (g_j + q~_j),   q~ = c * n_g / n_q,
 // so the kernel streams raw u16 counts (32 KiB per gallery row instead of OpenCV's 64 KiB of float32).
-// Bins with g = q~ = 0 must contribute exactly 0 (OpenCV skips |h+q| <= DBL_EPSILON): q~ is clamped to
-// 2^-70, so there d^2 = 2^-140 flushes to zero (mul.ftz) and 0 * rcp(2^-70) = 0.  Identical histograms
-// therefore give exactly 0.0, as in OpenCV.  Per bin: PRMT, FADD (u16 -> f32 via the 2^23 trick),
-// FADD d, FADD s, FMUL.FTZ, MUFU.RCP, FFMA.
+// Bins with g = q~ = 0 must contribute exactly 0 (OpenCV skips |h+q| <= DBL_EPSILON): the difference is formed
+// from the unclamped query (exactly 0 there) and only the sum is clamped away from 0.  Identical histograms
+// therefore give exactly 0.0, as in OpenCV.
 //
-// Layout.  One CTA = (query, chunk of gallery rows).  512 threads; thread t keeps the query bins
-// {(j*512 + t)*8 .. +8} in registers and reads the same bins of 4 gallery rows at a time with 128-bit
-// coalesced loads (a warp covers 512 contiguous bytes of a row per load).  Row partials are reduced
-// with a segmented warp butterfly (6 shuffles for 4 rows) and one shared-memory exchange per 32 rows;
-// warp 0 keeps the running best-k list.  The query index varies fastest across the grid so CTAs that
-// share a gallery chunk run together and re-read it from L2.
+// Layout.  One CTA = (query, chunk of gallery rows), 16 warps.  Whole gallery rows (contiguous, 32 KiB at 16384
+// bins) stream into a ring of shared-memory slots through 1-D TMA bulk copies (mbarrier full/empty per slot);
+// the warps take turns issuing them, four rows ahead of the row being consumed.  Thread t keeps the query bins {(j*512 + t)*8 .. +8} in
+// registers and reads the same bins of a row with 128-bit shared loads (a warp covers 512 contiguous bytes:
+// conflict-free).  Row partials are reduced with a segmented warp butterfly (6 shuffles for 4 rows) and one
+// shared-memory exchange per 32 rows; warp 0 keeps the running best-k list.  The query index varies fastest
+// across the grid so CTAs that share a gallery chunk run together and re-read it from L2.
+//
+// Per-bin arithmetic (the kernel is FP32/MUFU-bound once a chunk is shared by many queries): all float ops are
+// packed f32x2, and ONE reciprocal serves two bins:  a^2/s + c^2/t = (a^2 t + c^2 s) * rcp(s t).
+// Empty-empty bins use s = 2^-40 (so s t >= 2^-80 stays normal) and an exact d = 0, hence contribute exactly 0.
+// When both histograms have the same cell size (INTQ, the usual case) counts are integers and
+//     d = (2^23 + g) - (2^23 + c)   and   s = d + max(2c, 2^-40)
+// are exact without a separate u16 -> f32 conversion.
 #include "frb_common.cuh"
 
 namespace frb {
 
 constexpr int kChiThreads = 512;
 constexpr int kChiWarps = kChiThreads / 32;
+constexpr int kChiBlock = kChiThreads;
 constexpr int kChiRowsPerGroup = 4;
-constexpr int kChiBatch = 32;  // rows per shared-memory exchange
+constexpr int kChiBatch = 24;  // rows per shared-memory exchange (two 12-row blocks)
+constexpr int kChiSlots = 6;   // shared-memory ring of whole rows
 
-__device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p)
+__device__ __forceinline__ uint32_t chi_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void chi_mbar_wait(uint64_t *bar, uint32_t parity)
 {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "CHI_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra CHI_DONE;\n\t"
+        "bra CHI_WAIT;\n\t"
+        "CHI_DONE:\n\t"
+        "}" ::"r"(chi_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void chi_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(chi_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void chi_bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(chi_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(chi_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(chi_smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ float2 chi_f2(float x) { return make_float2(x, x); }
+// the two u16 counts of a word as 2^23 + count (exact): the count sits in the mantissa of 2^23
+__device__ __forceinline__ float2 chi_magic(uint32_t w)
+{
+    return make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)), __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)));
+}
+__device__ __forceinline__ float chi_rcp(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 
-__device__ __forceinline__ float u16lo_to_f32(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)) - 8388608.0f; }
-__device__ __forceinline__ float u16hi_to_f32(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)) - 8388608.0f; }
-
-__device__ __forceinline__ float chi_term(float g, float q)
+// Four bins: gallery words wa (bins 0,1) and wb (bins 2,3).  INTQ: qa/qb = -(2^23 + c), ta/tb = max(2c, 2^-40);
+// otherwise qa/qb = -c~ and ta/tb = max(c~, 2^-40) with c~ the query count rescaled to the gallery's cell size.
+template <bool INTQ>
+__device__ __forceinline__ float2 chi_quad(uint32_t wa, uint32_t wb, float2 qa, float2 ta, float2 qb, float2 tb, float2 acc)
 {
-    float d = g - q;
-    float s = g + q;
-    float dd, r;
-    asm("mul.ftz.f32 %0, %1, %1;" : "=f"(dd) : "f"(d));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
-    return dd * r;
+    float2 ga = chi_magic(wa), gb = chi_magic(wb);
+    float2 da, db, sa, sb;
+    if (INTQ) {
+        da = __fadd2_rn(ga, qa);
+        db = __fadd2_rn(gb, qb);
+        sa = __fadd2_rn(da, ta);
+        sb = __fadd2_rn(db, tb);
+    } else {
+        ga = __fadd2_rn(ga, chi_f2(-8388608.0f));
+        gb = __fadd2_rn(gb, chi_f2(-8388608.0f));
+        da = __fadd2_rn(ga, qa);
+        db = __fadd2_rn(gb, qb);
+        sa = __fadd2_rn(ga, ta);
+        sb = __fadd2_rn(gb, tb);
+    }
+    float2 u = __fmul2_rn(__fmul2_rn(da, da), sb);
+    u = __ffma2_rn(__fmul2_rn(db, db), sa, u);
+    const float2 prod = __fmul2_rn(sa, sb);
+    const float2 r = make_float2(chi_rcp(prod.x), chi_rcp(prod.y));
+    return __ffma2_rn(u, r, acc);
 }
 
-__device__ __forceinline__ float chi_word(uint32_t w, float q0, float q1, float acc)
+// ---- twelve rows = two trips round the 6-slot ring, so slots and mbarrier parities are compile-time constants -----
+// Row i of the block (i = 0..11) lives in slot i % 6 during ring phase (i / 6) & 1.  While row i is consumed, warp i
+// requests row i + 4 (slot (i + 4) % 6) once every warp has released that slot's previous tenant (row i - 2).
+// GUARD: the block may run past the chunk's last row (tail block only).  FULL: every thread owns CHUNKS full groups.
+template <int CHUNKS, bool INTQ, bool FULL, bool GUARD>
+__device__ __forceinline__ void chi_block12(const unsigned char *ring, uint64_t *s_full, uint64_t *s_empty, uint32_t row_bytes,
+                                            const uint16_t *__restrict__ gal_chunk, int hist_len, int64_t it0, int64_t n_rows,
+                                            const float2 (&qd)[CHUNKS][4], const float2 (&qs)[CHUNKS][4], const bool (&live)[CHUNKS],
+                                            float (*part)[kChiWarps + 1], int part_row0)
 {
-    acc += chi_term(u16lo_to_f32(w), q0);
-    acc += chi_term(u16hi_to_f32(w), q1);
-    return acc;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+        float p[kChiRowsPerGroup];
+#pragma unroll
+        for (int r = 0; r < kChiRowsPerGroup; r++) {
+            const int i = g * 4 + r;
+            p[r] = 0.f;
+            if (GUARD && it0 + i >= n_rows) continue;
+            if (tid == i * 32) {
+                const int j = i + 4;                       // row to request, relative to the block
+                if (!GUARD || it0 + j < n_rows) {
+                    const int ns = j % 6;
+                    const uint32_t par = (j < 6 || j >= 12) ? 1u : 0u;   // parity of the phase that released the slot
+                    if (j >= 6 || it0 > 0) chi_mbar_wait(&s_empty[ns], par);
+                    chi_bulk_load(const_cast<unsigned char *>(ring) + (size_t)ns * row_bytes, gal_chunk + (it0 + j) * hist_len,
+                                  row_bytes, &s_full[ns]);
+                }
+            }
+            __syncwarp();
+            const int slot = i % 6;
+            chi_mbar_wait(&s_full[slot], (uint32_t)((i / 6) & 1));
+            const uint4 *row4 = reinterpret_cast<const uint4 *>(ring + (size_t)slot * row_bytes);
+            uint4 w[CHUNKS];
+#pragma unroll
+            for (int jj = 0; jj < CHUNKS; jj++) {
+                if (FULL || live[jj])
+                    w[jj] = row4[jj * kChiThreads + tid];
+                else
+                    w[jj] = make_uint4(0, 0, 0, 0);
+            }
+            __syncwarp();
+            if (lane == 0) chi_mbar_arrive(&s_empty[slot]);  // this warp holds its part of the row in registers
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int jj = 0; jj < CHUNKS; jj++) {
+                acc = chi_quad<INTQ>(w[jj].x, w[jj].y, qd[jj][0], qs[jj][0], qd[jj][1], qs[jj][1], acc);
+                acc = chi_quad<INTQ>(w[jj].z, w[jj].w, qd[jj][2], qs[jj][2], qd[jj][3], qs[jj][3], acc);
+            }
+            p[r] = acc.x + acc.y;
+        }
+        // segmented butterfly: 4 row partials x 32 lanes -> lanes 0/8/16/24 hold rows 0/1/2/3
+        const bool hi = lane & 16;
+        float k0 = hi ? p[2] : p[0], k1 = hi ? p[3] : p[1];
+        float s0 = hi ? p[0] : p[2], s1 = hi ? p[1] : p[3];
+        k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+        k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+        const bool hi2 = lane & 8;
+        float kk = hi2 ? k1 : k0, ss = hi2 ? k0 : k1;
+        kk += __shfl_xor_sync(0xffffffffu, ss, 8);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 4);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 2);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 1);
+        if ((lane & 7) == 0) part[part_row0 + g * kChiRowsPerGroup + (lane >> 3)][warp] = kk;
+    }
 }
 
-// CHUNKS: 128-bit loads per thread per row (hist_len <= CHUNKS * 4096).  WRITE_ALL: emit every distance.
-template <int CHUNKS, bool WRITE_ALL>
-__global__ void __launch_bounds__(kChiThreads, 1)
+// CHUNKS: 128-bit groups per thread per row (hist_len <= CHUNKS * 4096).  WRITE_ALL: emit every distance.
+template <int CHUNKS, bool WRITE_ALL, bool INTQ, bool FULL>
+__global__ void __launch_bounds__(kChiBlock, 1)
 chisq_kernel(const uint16_t *__restrict__ qhist, int64_t n_query, float q_scale, const uint16_t *__restrict__ gallery,
              int64_t n_gallery, int hist_len, float out_scale, int64_t rows_per_chunk, int k, int64_t idx_base,
              float *__restrict__ cand_dist, int64_t *__restrict__ cand_idx, float *__restrict__ all_dist)
 {
+    extern __shared__ __align__(128) unsigned char chi_smem[];
     __shared__ float s_part[2][kChiBatch][kChiWarps + 1];
     __shared__ float s_best[FRB_MAX_K];
     __shared__ int64_t s_bidx[FRB_MAX_K];
+    __shared__ __align__(8) uint64_t s_full[kChiSlots], s_empty[kChiSlots];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t q = blockIdx.x;
@@ -73,23 +189,46 @@ chisq_kernel(const uint16_t *__restrict__ qhist, int64_t n_query, float q_scale,
     const int64_t row_begin = chunk * rows_per_chunk;
     int64_t row_end = row_begin + rows_per_chunk;
     if (row_end > n_gallery) row_end = n_gallery;
+    const int64_t n_rows = row_end - row_begin;
     const int vec_per_row = hist_len >> 3;  // uint4 per row
+    const uint32_t row_bytes = (uint32_t)hist_len * 2u;
+    const uint16_t *gal_chunk = gallery + row_begin * hist_len;
 
-    // query bins -> registers (scaled to the gallery's cell size, clamped away from 0)
-    float qv[CHUNKS][8];
+    if (tid == 0) {
+        for (int i = 0; i < kChiSlots; i++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(chi_smem_u32(&s_full[i])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(chi_smem_u32(&s_empty[i])), "n"(kChiWarps));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // the first four rows are requested up front; after that warp i of a 12-row block requests row i + 4
+    if (tid == 0) {
+        for (int64_t i = 0; i < 4 && i < n_rows; i++)
+            chi_bulk_load(chi_smem + (size_t)i * row_bytes, gal_chunk + i * hist_len, row_bytes, &s_full[i]);
+    }
+
+    // ---- query bins -> registers ------------------------------------------------------------------------------
+    float2 qd[CHUNKS][4], qs[CHUNKS][4];
     bool live[CHUNKS];
-    const float tiny = __uint_as_float(0x1C800000u);  // 2^-70
+    const float tiny = __uint_as_float(0x2B800000u);  // 2^-40
 #pragma unroll
     for (int j = 0; j < CHUNKS; j++) {
         const int v = j * kChiThreads + tid;
-        live[j] = v < vec_per_row;
+        live[j] = FULL || v < vec_per_row;
         uint4 w = make_uint4(0, 0, 0, 0);
         if (live[j]) w = __ldg(reinterpret_cast<const uint4 *>(qhist + q * hist_len) + v);
         const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-            qv[j][2 * e] = fmaxf(u16lo_to_f32(ww[e]) * q_scale, tiny);
-            qv[j][2 * e + 1] = fmaxf(u16hi_to_f32(ww[e]) * q_scale, tiny);
+            const float c0 = (float)(ww[e] & 0xFFFFu), c1 = (float)(ww[e] >> 16);
+            if (INTQ) {
+                qd[j][e] = make_float2(-(c0 + 8388608.0f), -(c1 + 8388608.0f));
+                qs[j][e] = make_float2(fmaxf(2.0f * c0, tiny), fmaxf(2.0f * c1, tiny));
+            } else {
+                qd[j][e] = make_float2(-(c0 * q_scale), -(c1 * q_scale));
+                qs[j][e] = make_float2(fmaxf(c0 * q_scale, tiny), fmaxf(c1 * q_scale, tiny));
+            }
         }
     }
 
@@ -99,56 +238,26 @@ chisq_kernel(const uint16_t *__restrict__ qhist, int64_t n_query, float q_scale,
         __syncwarp();
     }
 
-    const uint4 *gal4 = reinterpret_cast<const uint4 *>(gallery);
     int buf = 0;
-    for (int64_t base = row_begin; base < row_end; base += kChiBatch, buf ^= 1) {
+    for (int64_t it0 = 0; it0 < n_rows; it0 += kChiBatch, buf ^= 1) {
+        // a batch = two 12-row blocks (24 rows, one per lane of warp 0 in the final step)
 #pragma unroll 1
-        for (int grp = 0; grp < kChiBatch / kChiRowsPerGroup; grp++) {
-            const int64_t r0 = base + grp * kChiRowsPerGroup;
-            float p[kChiRowsPerGroup];
-            uint4 w[kChiRowsPerGroup][CHUNKS];
-#pragma unroll
-            for (int r = 0; r < kChiRowsPerGroup; r++) {
-                const bool rv = (r0 + r) < row_end;
-#pragma unroll
-                for (int j = 0; j < CHUNKS; j++) {
-                    w[r][j] = make_uint4(0, 0, 0, 0);
-                    if (rv && live[j]) w[r][j] = ld_stream_u4(gal4 + (r0 + r) * vec_per_row + j * kChiThreads + tid);
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < kChiRowsPerGroup; r++) {
-                float acc = 0.f;
-#pragma unroll
-                for (int j = 0; j < CHUNKS; j++) {
-                    acc = chi_word(w[r][j].x, qv[j][0], qv[j][1], acc);
-                    acc = chi_word(w[r][j].y, qv[j][2], qv[j][3], acc);
-                    acc = chi_word(w[r][j].z, qv[j][4], qv[j][5], acc);
-                    acc = chi_word(w[r][j].w, qv[j][6], qv[j][7], acc);
-                }
-                p[r] = acc;
-            }
-            // segmented butterfly: 4 row partials x 32 lanes -> lanes 0/8/16/24 hold rows 0/1/2/3
-            const bool hi = lane & 16;
-            float k0 = hi ? p[2] : p[0], k1 = hi ? p[3] : p[1];
-            float s0 = hi ? p[0] : p[2], s1 = hi ? p[1] : p[3];
-            k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-            k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-            const bool hi2 = lane & 8;
-            float kk = hi2 ? k1 : k0, ss = hi2 ? k0 : k1;
-            kk += __shfl_xor_sync(0xffffffffu, ss, 8);
-            kk += __shfl_xor_sync(0xffffffffu, kk, 4);
-            kk += __shfl_xor_sync(0xffffffffu, kk, 2);
-            kk += __shfl_xor_sync(0xffffffffu, kk, 1);
-            if ((lane & 7) == 0) s_part[buf][grp * kChiRowsPerGroup + (lane >> 3)][warp] = kk;
+        for (int h = 0; h < 2; h++) {
+            const int64_t b0 = it0 + h * 12;
+            if (b0 + 12 <= n_rows)
+                chi_block12<CHUNKS, INTQ, FULL, false>(chi_smem, s_full, s_empty, row_bytes, gal_chunk, hist_len, b0, n_rows, qd, qs,
+                                                       live, s_part[buf], h * 12);
+            else if (b0 < n_rows)
+                chi_block12<CHUNKS, INTQ, FULL, true>(chi_smem, s_full, s_empty, row_bytes, gal_chunk, hist_len, b0, n_rows, qd, qs,
+                                                      live, s_part[buf], h * 12);
         }
         __syncthreads();
         if (warp == 0) {
-            const int64_t row = base + lane;
-            const bool valid = row < row_end;
+            const int64_t row = row_begin + it0 + lane;
+            const bool valid = lane < kChiBatch && row < row_end;
             float d = 0.f;
 #pragma unroll
-            for (int w2 = 0; w2 < kChiWarps; w2++) d += s_part[buf][lane][w2];
+            for (int w2 = 0; w2 < kChiWarps; w2++) d += s_part[buf][lane < kChiBatch ? lane : 0][w2];
             d *= out_scale;
             if (WRITE_ALL) {
                 if (valid) all_dist[q * n_gallery + row] = d;
@@ -160,7 +269,7 @@ chisq_kernel(const uint16_t *__restrict__ qhist, int64_t n_query, float q_scale,
                     const float v = __shfl_sync(0xffffffffu, d, src);
                     if (v < kth) {
                         float nk = 0.f;
-                        if (lane == 0) nk = list_insert_stream<false>(s_best, s_bidx, k, v, idx_base + base + src);
+                        if (lane == 0) nk = list_insert_stream<false>(s_best, s_bidx, k, v, idx_base + row_begin + it0 + src);
                         kth = __shfl_sync(0xffffffffu, nk, 0);
                     }
                 }
@@ -182,7 +291,7 @@ static int64_t chi_chunks(int64_t n_query, int64_t n_gallery, int64_t *rows_per_
 {
     int sms = sm_count();
     if (sms <= 0) sms = 148;
-    // aim for ~4 CTAs per SM in total, each at least one 32-row batch, chunk rows a multiple of 32
+    // ~4 CTAs per SM in total (a whole number of waves when there are few queries), each at least one 24-row batch
     int64_t want = ((int64_t)sms * 4 + n_query - 1) / (n_query > 0 ? n_query : 1);
     if (want < 1) want = 1;
     int64_t max_chunks = (n_gallery + kChiBatch - 1) / kChiBatch;
@@ -190,38 +299,66 @@ static int64_t chi_chunks(int64_t n_query, int64_t n_gallery, int64_t *rows_per_
     if (want > max_chunks) want = max_chunks;
     if (want > 65535) want = 65535;
     int64_t rpc = (n_gallery + want - 1) / want;
-    rpc = (rpc + kChiBatch - 1) / kChiBatch * kChiBatch;
     if (rpc < kChiBatch) rpc = kChiBatch;
     *rows_per_chunk = rpc;
     int64_t chunks = (n_gallery + rpc - 1) / rpc;
     return chunks < 1 ? 1 : chunks;
 }
 
+template <int CHUNKS, bool WRITE_ALL, bool INTQ, bool FULL>
+static int launch_chisq_t(dim3 grid, size_t smem, const uint16_t *qh, int64_t nq, float q_scale, const uint16_t *gal, int64_t ng,
+                          int L, float out_scale, int64_t rpc, int k, int64_t idx_base, float *cd, int64_t *ci, float *all,
+                          cudaStream_t st)
+{
+    static thread_local int attr_dev = -1;
+    static thread_local size_t attr_smem = 0;
+    int dev = 0;
+    FRB_CUDA_OK(cudaGetDevice(&dev));
+    if (attr_dev != dev || attr_smem < smem) {
+        FRB_CUDA_OK(cudaFuncSetAttribute(chisq_kernel<CHUNKS, WRITE_ALL, INTQ, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+        attr_dev = dev;
+        attr_smem = smem;
+    }
+    ProfileScope prof(FRB_K_CHISQ, st);
+    chisq_kernel<CHUNKS, WRITE_ALL, INTQ, FULL><<<grid, kChiBlock, smem, st>>>(qh, nq, q_scale, gal, ng, L, out_scale, rpc, k,
+                                                                              idx_base, cd, ci, all);
+    FRB_LAUNCH_OK("chisq_kernel");
+    return FRB_OK;
+}
+
+template <int CHUNKS, bool WRITE_ALL>
+static int launch_chisq_c(bool intq, bool full, dim3 grid, size_t smem, const uint16_t *qh, int64_t nq, float q_scale,
+                          const uint16_t *gal, int64_t ng, int L, float out_scale, int64_t rpc, int k, int64_t idx_base, float *cd,
+                          int64_t *ci, float *all, cudaStream_t st)
+{
+#define FRB_CHI_ARGS grid, smem, qh, nq, q_scale, gal, ng, L, out_scale, rpc, k, idx_base, cd, ci, all, st
+    if (intq) return full ? launch_chisq_t<CHUNKS, WRITE_ALL, true, true>(FRB_CHI_ARGS) : launch_chisq_t<CHUNKS, WRITE_ALL, true, false>(FRB_CHI_ARGS);
+    return full ? launch_chisq_t<CHUNKS, WRITE_ALL, false, true>(FRB_CHI_ARGS) : launch_chisq_t<CHUNKS, WRITE_ALL, false, false>(FRB_CHI_ARGS);
+#undef FRB_CHI_ARGS
+}
+
 template <bool WRITE_ALL>
-static int launch_chisq(const uint16_t *qh, int64_t nq, float q_scale, const uint16_t *gal, int64_t ng, int L,
-                        float out_scale, int64_t rpc, int64_t chunks, int k, int64_t idx_base, float *cd, int64_t *ci,
-                        float *all, cudaStream_t st)
+static int launch_chisq(const uint16_t *qh, int64_t nq, int q_cell_px, const uint16_t *gal, int64_t ng, int L, int g_cell_px,
+                        int64_t rpc, int64_t chunks, int k, int64_t idx_base, float *cd, int64_t *ci, float *all,
+                        cudaStream_t st)
 {
     dim3 grid((unsigned)nq, (unsigned)chunks);
     const int chunks_per_thread = (L / 8 + kChiThreads - 1) / kChiThreads;
-    ProfileScope prof(FRB_K_CHISQ, st);
-    switch (chunks_per_thread) {
-        case 1:
-            chisq_kernel<1, WRITE_ALL><<<grid, kChiThreads, 0, st>>>(qh, nq, q_scale, gal, ng, L, out_scale, rpc, k, idx_base, cd, ci, all);
-            break;
-        case 2:
-            chisq_kernel<2, WRITE_ALL><<<grid, kChiThreads, 0, st>>>(qh, nq, q_scale, gal, ng, L, out_scale, rpc, k, idx_base, cd, ci, all);
-            break;
-        case 3:
-        case 4:
-            chisq_kernel<4, WRITE_ALL><<<grid, kChiThreads, 0, st>>>(qh, nq, q_scale, gal, ng, L, out_scale, rpc, k, idx_base, cd, ci, all);
-            break;
+    const float q_scale = (float)g_cell_px / (float)q_cell_px;
+    const float out_scale = 2.0f / (float)g_cell_px;
+    const bool intq = q_cell_px == g_cell_px;  // integer counts on both sides: exact differences without a conversion
+    const size_t smem = (size_t)L * 2 * kChiSlots;  // ring of whole rows
+    int c = chunks_per_thread == 3 ? 4 : chunks_per_thread;
+    const bool full = (L / 8) == c * kChiThreads;
+    switch (c) {
+        case 1: return launch_chisq_c<1, WRITE_ALL>(intq, full, grid, smem, qh, nq, q_scale, gal, ng, L, out_scale, rpc, k, idx_base, cd, ci, all, st);
+        case 2: return launch_chisq_c<2, WRITE_ALL>(intq, full, grid, smem, qh, nq, q_scale, gal, ng, L, out_scale, rpc, k, idx_base, cd, ci, all, st);
+        case 4: return launch_chisq_c<4, WRITE_ALL>(intq, full, grid, smem, qh, nq, q_scale, gal, ng, L, out_scale, rpc, k, idx_base, cd, ci, all, st);
         default:
             set_error("chi-square: hist_len=%d exceeds the 16384 bins the kernel keeps in registers", L);
             return FRB_ERR_UNSUPPORTED;
     }
-    FRB_LAUNCH_OK("chisq_kernel");
-    return FRB_OK;
 }
 
 static int check_chisq_args(const char *fn, int64_t nq, int qpx, int64_t ng, int L, int gpx)
@@ -271,9 +408,7 @@ int frb_chisq_topk(const uint16_t *q_hist, int64_t n_query, int q_cell_px, const
     size_t n = (size_t)chunks * (size_t)n_query * (size_t)k;
     int64_t *ci = (int64_t *)workspace;
     float *cd = (float *)((char *)workspace + align_up(n * sizeof(int64_t), 256));
-    const float q_scale = (float)g_cell_px / (float)q_cell_px;
-    const float out_scale = 2.0f / (float)g_cell_px;
-    rc = launch_chisq<false>(q_hist, n_query, q_scale, gallery, n_gallery, hist_len, out_scale, rpc, chunks, k, idx_base,
+    rc = launch_chisq<false>(q_hist, n_query, q_cell_px, gallery, n_gallery, hist_len, g_cell_px, rpc, chunks, k, idx_base,
                              cd, ci, nullptr, (cudaStream_t)stream);
     if (rc != FRB_OK) return rc;
     return frb_topk_merge(cd, ci, (int)chunks, n_query, k, /*largest=*/0, out_dist, out_idx, stream);
@@ -290,9 +425,7 @@ int frb_chisq_dist(const uint16_t *q_hist, int64_t n_query, int q_cell_px, const
                   "frb_chisq_dist: histograms must be 16-byte aligned");
     int64_t rpc;
     int64_t chunks = chi_chunks(n_query, n_gallery, &rpc);
-    const float q_scale = (float)g_cell_px / (float)q_cell_px;
-    const float out_scale = 2.0f / (float)g_cell_px;
-    return launch_chisq<true>(q_hist, n_query, q_scale, gallery, n_gallery, hist_len, out_scale, rpc, chunks, 1, 0, nullptr,
+    return launch_chisq<true>(q_hist, n_query, q_cell_px, gallery, n_gallery, hist_len, g_cell_px, rpc, chunks, 1, 0, nullptr,
                               nullptr, out_dist, (cudaStream_t)stream);
 }
 
