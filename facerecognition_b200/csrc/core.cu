@@ -131,6 +131,58 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float *__rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// Gallery builder: out[g] = mean(rows of group g) / (||mean|| + 1e-8).  One CTA per group; thread t owns dims
+// t, t + 128, ...; rows are added in the order given (ascending sample index), in float32, then divided by the
+// count, as numpy's mean(axis=0) does; sum of squares by a block reduction.  Empty groups stay all-zero.
+constexpr int kGroupThreads = 128;
+constexpr int kGroupMaxPerThread = 8;  // dim <= 1024
+
+__global__ void __launch_bounds__(kGroupThreads) group_mean_renorm_kernel(const float *__restrict__ emb, const int64_t *__restrict__ order,
+                                                                          const int64_t *__restrict__ offsets, int dim,
+                                                                          float *__restrict__ out_f32, __nv_bfloat16 *__restrict__ out_bf16)
+{
+    __shared__ float s_red[kGroupThreads / 32];
+    const int64_t g = blockIdx.x;
+    const int64_t lo = offsets[g], hi = offsets[g + 1];
+    const int tid = threadIdx.x;
+    float acc[kGroupMaxPerThread];
+#pragma unroll
+    for (int j = 0; j < kGroupMaxPerThread; j++) acc[j] = 0.f;
+    for (int64_t i = lo; i < hi; i++) {
+        const float *row = emb + order[i] * dim;
+#pragma unroll
+        for (int j = 0; j < kGroupMaxPerThread; j++) {
+            const int d = tid + j * kGroupThreads;
+            if (d < dim) acc[j] = __fadd_rn(acc[j], __ldg(row + d));
+        }
+    }
+    const float n = (float)(hi - lo);
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < kGroupMaxPerThread; j++) {
+        if (hi > lo) acc[j] = __fdiv_rn(acc[j], n);
+        ss = fmaf(acc[j], acc[j], ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((tid & 31) == 0) s_red[tid >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < kGroupThreads / 32; w++) tot += s_red[w];
+    const float denom = sqrtf(tot) + 1e-8f;
+#pragma unroll
+    for (int j = 0; j < kGroupMaxPerThread; j++) {
+        const int d = tid + j * kGroupThreads;
+        if (d < dim) {
+            const float v = hi > lo ? __fdiv_rn(acc[j], denom) : 0.f;
+            if (out_f32) out_f32[g * dim + d] = v;
+            if (out_bf16) out_bf16[g * dim + d] = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // One thread per query merges n_lists sorted candidate lists of length k (k <= FRB_MAX_K).
 template <bool LARGEST>
 __global__ void __launch_bounds__(128) topk_merge_kernel(const float *__restrict__ cs, const int64_t *__restrict__ ci,
@@ -330,6 +382,20 @@ static int topk_merge_launch(const char *fn, const float *cs, const int64_t *ci,
     else
         topk_merge_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(cs, ci, s_stride, i_stride, n_lists, n_query, k, os, oi);
     FRB_LAUNCH_OK("topk_merge_kernel");
+    return FRB_OK;
+}
+
+int frb_group_mean_renorm(const float *emb, const int64_t *order, const int64_t *offsets, int64_t n_groups, int dim,
+                          float *out_f32, void *out_bf16, void *stream)
+{
+    FRB_CHECK_ARG(n_groups >= 0 && dim > 0 && dim <= kGroupThreads * kGroupMaxPerThread, "frb_group_mean_renorm: n_groups=%lld dim=%d (dim <= %d)",
+                  (long long)n_groups, dim, kGroupThreads * kGroupMaxPerThread);
+    if (n_groups == 0) return FRB_OK;
+    FRB_CHECK_ARG(emb && order && offsets && (out_f32 || out_bf16), "frb_group_mean_renorm: null pointer");
+    FRB_CHECK_ARG(n_groups <= 2147483647LL, "frb_group_mean_renorm: too many groups");
+    group_mean_renorm_kernel<<<(unsigned)n_groups, kGroupThreads, 0, (cudaStream_t)stream>>>(emb, order, offsets, dim, out_f32,
+                                                                                            (__nv_bfloat16 *)out_bf16);
+    FRB_LAUNCH_OK("group_mean_renorm_kernel");
     return FRB_OK;
 }
 

@@ -101,6 +101,19 @@ def topk_merge(cand_scores: torch.Tensor, cand_idx: torch.Tensor, largest: bool)
     return scores, idx
 
 
+def group_mean_renorm(emb: torch.Tensor, order: torch.Tensor, offsets: torch.Tensor, want_bf16: bool = False
+                      ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """frb_group_mean_renorm: f32 [M, D] rows grouped by `order`/`offsets` -> (f32 [G, D], bf16 [G, D] or None)."""
+    dev = _require_cuda(emb, order, offsets)
+    assert emb.dtype == torch.float32 and emb.dim() == 2 and order.dtype == torch.int64 and offsets.dtype == torch.int64
+    g, d = offsets.shape[0] - 1, emb.shape[1]
+    out = torch.empty((g, d), dtype=torch.float32, device=dev)
+    out16 = torch.empty((g, d), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    with torch.cuda.device(dev):
+        N.call("frb_group_mean_renorm", _p(emb), _p(order), _p(offsets), _I64(g), d, _p(out), _p(out16), _stream(dev))
+    return out, out16
+
+
 def packed_candidates(n_query: int, k: int, device: torch.device, n_lists: int = 1
                       ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """One byte buffer [n_lists, record] whose record is {ids i64 [Q, k] | scores f32 [Q, k]} (ids first, so both

@@ -148,6 +148,60 @@ class FlatIPIndex:
         formats.write_faiss_flat_ip(path, self.rows.float().cpu().numpy())
 
 
+def group_plan(labels: np.ndarray, n_groups: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """Host-side index plumbing for frb_group_mean_renorm: (order i64 [M], offsets i64 [G + 1]) with the samples of
+    each label in ascending sample order (what `embeddings[labels == label]` yields in the reference)."""
+    lab = np.asarray(labels).astype(np.int64).reshape(-1)
+    g = int(n_groups if n_groups is not None else (lab.max() + 1 if lab.size else 0))
+    if lab.size and (lab.min() < 0 or lab.max() >= g):
+        raise IndexError(f"label out of range 0..{g - 1}")      # the reference's prototypes[label] = ... raises the same way
+    order = np.argsort(lab, kind="stable").astype(np.int64)
+    offsets = np.zeros(g + 1, np.int64)
+    np.cumsum(np.bincount(lab, minlength=g), out=offsets[1:])
+    return order, offsets
+
+
+def compute_prototypes(embeddings: np.ndarray, labels: np.ndarray, output_path: str = None, device: Optional[str] = None
+                       ) -> np.ndarray:
+    """inference/extract_embeddings.py:555-592: prototype[label] = mean(embeddings[labels == label]) / (||mean|| + 1e-8),
+    num_classes = len(np.unique(labels)) rows.  The means and norms run on the GPU (frb_group_mean_renorm)."""
+    print("\n=== COMPUTING PROTOTYPES ===")
+    emb = np.ascontiguousarray(embeddings, np.float32)
+    num_classes = len(np.unique(labels))
+    order, offsets = group_plan(labels, num_classes)
+    dev = _match_device(device)
+    out, _ = ops.group_mean_renorm(_to_dev(emb, dev), torch.from_numpy(order).to(dev), torch.from_numpy(offsets).to(dev))
+    prototypes = out.cpu().numpy()
+    print(f"Computed {num_classes} prototypes")
+    if output_path:
+        np.save(output_path, prototypes)
+        print(f"Saved prototypes: {output_path}")
+    return prototypes
+
+
+def mean_embedding(embeddings: Sequence[np.ndarray], device: Optional[str] = None) -> np.ndarray:
+    """One identity's gallery row: mean of its embeddings, / (||mean|| + 1e-8) (extract_embeddings.py:758-760,
+    recognition_engine.py:413-414)."""
+    emb = np.ascontiguousarray(np.stack(embeddings), np.float32)
+    dev = _match_device(device)
+    order = torch.arange(emb.shape[0], dtype=torch.int64, device=dev)
+    offsets = torch.tensor([0, emb.shape[0]], dtype=torch.int64, device=dev)
+    out, _ = ops.group_mean_renorm(_to_dev(emb, dev), order, offsets)
+    return out[0].cpu().numpy()
+
+
+def build_db_from_embeddings(names: Sequence[str], embeddings: np.ndarray, owner: np.ndarray, device: Optional[str] = None
+                             ) -> Dict[str, np.ndarray]:
+    """The gallery dict build_db emits (extract_embeddings.py:808-831), from already-extracted embeddings:
+    `owner[i]` = index into `names` of sample i; identities with no sample are left out, as build_db skips them."""
+    emb = np.ascontiguousarray(embeddings, np.float32)
+    order, offsets = group_plan(owner, len(names))
+    dev = _match_device(device)
+    out, _ = ops.group_mean_renorm(_to_dev(emb, dev), torch.from_numpy(order).to(dev), torch.from_numpy(offsets).to(dev))
+    rows = out.cpu().numpy()
+    return {n: rows[i] for i, n in enumerate(names) if offsets[i + 1] > offsets[i]}
+
+
 def build_faiss_index(embeddings: np.ndarray, output_path: str = None, use_gpu: bool = True,
                       device: Optional[str] = None) -> FlatIPIndex:
     """inference/extract_embeddings.py:595-645: rows / (||row|| + 1e-8), IndexFlatIP(dim).add, optional write."""
@@ -328,8 +382,7 @@ class RecognitionEngine:
         if len(embeddings) == 0:
             print(f"Khong the extract embedding cho {name}")
             return False
-        mean_emb = np.mean(np.stack(embeddings), axis=0)
-        mean_emb = mean_emb / (np.linalg.norm(mean_emb) + 1e-8)
+        mean_emb = mean_embedding(embeddings, str(self.match_device))
         if self.db is None:
             self.db = {}
         self.db[name] = mean_emb

@@ -115,6 +115,16 @@ int frb_cosine_topk(const float *queries_dev, int64_t n_query, const void *galle
                     int score_mode, int qnorm_mode, int k, int64_t idx_base, float *out_scores_dev,
                     int64_t *out_idx_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* Gallery builder (K4): out[g] = mean(emb[order[offsets[g] .. offsets[g+1])]) / (||mean|| + 1e-8), float32 sums in
+ * the given order then a division by the count (numpy's mean(axis=0)); groups with no rows come out all-zero.
+ * emb f32 [M, dim]; order i64 [M] = sample indices grouped by identity; offsets i64 [n_groups + 1].
+ * out_f32 [n_groups, dim] and/or out_bf16 [n_groups, dim] (either may be NULL; the bf16 copy is the K1 gallery).
+ * Replaces: compute_prototypes (inference/extract_embeddings.py:573-584), the per-identity mean + renorm of
+ * extract_embedding_for_folder (:758-760) / build_db (:808-831) and RecognitionEngine.add_to_db
+ * (inference/recognition_engine.py:413-419). */
+int frb_group_mean_renorm(const float *emb_dev, const int64_t *order_dev, const int64_t *offsets_dev, int64_t n_groups,
+                          int dim, float *out_f32_dev, void *out_bf16_dev, void *stream);
+
 /* Merge R candidate lists per query (e.g. one per GPU after the all-gather, or one per
  * gallery chunk): cand_scores [R, n_query, k], cand_idx [R, n_query, k] -> best k.
  * largest != 0: descending score (cosine); largest == 0: ascending distance (LBPH).

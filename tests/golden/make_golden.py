@@ -11,6 +11,10 @@
   UNPINNED: cv2.face is not installed anywhere we can run), and chi-square distances computed
   by the REAL cv2.compareHist(HISTCMP_CHISQR_ALT) of the installed OpenCV core (pinned).
 
+* gallery_golden.npz — outputs of the REAL reference's gallery builders on seeded embeddings:
+  compute_prototypes (inference/extract_embeddings.py:555-592) and RecognitionEngine.add_to_db
+  (inference/recognition_engine.py:391-422, with extract_embedding stubbed to pass embeddings through).
+
 /root/reference does not exist on the GPU box; the tests read only the .npz files.
 """
 import os
@@ -126,6 +130,56 @@ def make_lbph():
     print("lbph_golden.npz:", {k: getattr(v, "shape", None) for k, v in out.items()})
 
 
+def make_gallery():
+    sys.path.insert(0, "/root/reference")
+    from inference.extract_embeddings import compute_prototypes          # the real reference
+    from inference.recognition_engine import RecognitionEngine
+
+    rng = np.random.default_rng(77)
+    D, C, M = 512, 37, 411
+    labels = rng.integers(0, C, M).astype(np.int64)
+    labels[:C] = np.arange(C)                                             # every class present (the reference indexes by label)
+    emb = unit(rng.standard_normal((M, D)) + 0.5 * rng.standard_normal((C, D))[labels])
+    protos = compute_prototypes(emb, labels)
+    eng = RecognitionEngine(model_path=None, db_path=None, use_face_detection=False)
+    eng.extract_embedding = lambda x: x                                   # "images" are already embeddings
+    groups = [emb[labels == c] for c in (0, 5, 36)]
+    for c, g in zip((0, 5, 36), groups):
+        assert eng.add_to_db(f"id_{c}", list(g))
+    assert eng.add_to_db("nobody", []) is False
+    out = dict(emb=emb, labels=labels, prototypes=protos,
+               add_names=np.array(list(eng.db.keys())), add_rows=np.stack([eng.db[k] for k in eng.db]),
+               add_classes=np.array([0, 5, 36]))
+    np.savez_compressed(os.path.join(HERE, "gallery_golden.npz"), **out)
+    print("gallery_golden.npz:", {k: getattr(v, "shape", None) for k, v in out.items()})
+
+
+def make_sweep():
+    """sweep_golden.npz — the REAL inference/evaluate.py threshold_sweep (:61-128) on seeded scores.  The module's
+    plotting imports (matplotlib, seaborn — not installed here) are stubbed; threshold_sweep itself is pure numpy."""
+    import json
+    import types
+    for name in ("matplotlib", "matplotlib.pyplot", "seaborn"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.path.insert(0, "/root/reference")
+    from inference.evaluate import threshold_sweep as ref_sweep
+    rng = np.random.default_rng(3)
+    n = 500
+    yt = rng.integers(0, 40, n)
+    yp = np.where(rng.random(n) < 0.8, yt, rng.integers(0, 40, n))
+    sim = np.clip(rng.normal(0.6, 0.2, n), 0, 1)
+    np.savez_compressed(os.path.join(HERE, "sweep_golden.npz"), sim=sim, y_true=yt, y_pred=yp,
+                        report=np.array(json.dumps(ref_sweep(sim, yt, yp))))
+    print("sweep_golden.npz written")
+
+
 if __name__ == "__main__":
-    make_lbph()
-    make_cosine()
+    which = sys.argv[1:] or ["lbph", "cosine", "gallery", "sweep"]
+    if "lbph" in which:
+        make_lbph()
+    if "cosine" in which:
+        make_cosine()
+    if "gallery" in which:
+        make_gallery()
+    if "sweep" in which:
+        make_sweep()

@@ -217,3 +217,48 @@ def test_full_size_1m_gallery_properties():
     s3, i3 = ops.cosine_topk(sub, gal16[:200_000].contiguous(), k, qnorm_mode=NV.FRB_QNORM_CLAMP)
     assert torch.allclose(s2, s3, atol=2e-6, rtol=0)
     assert bool(((i2 == i3) | ((s2 - s3).abs() <= 2e-6)).all())
+
+
+def test_gallery_builders_match_the_reference_outputs():
+    """K4 (frb_group_mean_renorm) behind compute_prototypes / add_to_db / build_db_from_embeddings vs the REAL
+    reference's outputs (tests/golden/gallery_golden.npz).  Tolerance 1e-6 absolute on unit-norm rows."""
+    import os
+    import facerecognition_b200 as F
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "gallery_golden.npz"))
+    emb, labels = g["emb"], g["labels"]
+    protos = F.compute_prototypes(emb, labels)
+    assert protos.dtype == np.float32 and protos.shape == g["prototypes"].shape
+    np.testing.assert_allclose(protos, g["prototypes"], rtol=0, atol=1e-6)
+    eng = F.RecognitionEngine(model_path=None, use_face_detection=False, embedder=lambda x: x)
+    for c in g["add_classes"]:
+        assert eng.add_to_db(f"id_{c}", list(emb[labels == c]))
+    assert eng.add_to_db("nobody", []) is False
+    assert list(eng.db.keys()) == list(g["add_names"])
+    np.testing.assert_allclose(np.stack([eng.db[k] for k in eng.db]), g["add_rows"], rtol=0, atol=1e-6)
+    names = [f"id_{c}" for c in range(40)]                     # 37 classes present, 3 identities without samples
+    db = F.build_db_from_embeddings(names, emb, labels)
+    assert list(db.keys()) == names[:37]
+    np.testing.assert_allclose(np.stack(list(db.values())), g["prototypes"], rtol=0, atol=1e-6)
+    # device-level: bf16 copy for the tensor-core gallery, empty groups all-zero
+    from facerecognition_b200 import ops
+    order, offsets = F.group_plan(labels, 40)
+    o32, o16 = ops.group_mean_renorm(torch.from_numpy(emb).cuda(), torch.from_numpy(order).cuda(),
+                                     torch.from_numpy(offsets).cuda(), want_bf16=True)
+    assert torch.equal(o16, o32.to(torch.bfloat16)) and float(o32[37:].abs().max()) == 0.0
+
+
+def test_topk_accuracy_matches_the_notebook_form():
+    """evaluation.topk_accuracy (fused K1) vs the notebooks' np.dot + argmax / argsort on the golden gallery."""
+    import os
+    from facerecognition_b200 import evaluation as EV
+    from oracle import cosine as OC
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "gallery_golden.npz"))
+    emb, labels, protos = g["emb"], g["labels"], g["prototypes"]
+    S = emb @ protos.T                                                   # evaluate_arcface_kaggle.ipynb:618
+    top1 = float((np.argmax(S, 1) == labels).mean())
+    top5 = float((np.argsort(S, 1)[:, -5:] == labels[:, None]).any(1).mean())   # :713
+    for bf16 in (False, True):
+        r = EV.topk_accuracy(emb, labels, protos, (1, 5), bf16=bf16)
+        assert r["top1_accuracy"] == pytest.approx(top1, abs=(0 if not bf16 else 2 / len(labels)))
+        assert r["top5_accuracy"] == pytest.approx(top5, abs=(0 if not bf16 else 2 / len(labels)))
+        np.testing.assert_allclose(r["similarities"], S.max(1), atol=1e-5 if not bf16 else 1e-3)

@@ -122,3 +122,28 @@ def test_gallery_dict_tracks_mutations():
     d.update(c=3); assert d.version > v; v = d.version
     d.pop("c"); assert d.version > v; v = d.version
     d.clear(); assert d.version > v and len(d) == 0
+
+
+def test_group_plan_orders_samples_by_label_then_index():
+    from facerecognition_b200.recognition_engine import group_plan
+    labels = np.array([2, 0, 2, 1, 0, 2])
+    order, offsets = group_plan(labels, 4)
+    assert order.tolist() == [1, 4, 3, 0, 2, 5] and offsets.tolist() == [0, 2, 3, 6, 6]
+    with pytest.raises(IndexError):
+        group_plan(np.array([0, 5]), 3)
+    order, offsets = group_plan(np.zeros(0, np.int64), 2)
+    assert order.size == 0 and offsets.tolist() == [0, 0, 0]
+
+
+def test_threshold_sweep_matches_the_real_reference():
+    """facerecognition_b200.evaluation.threshold_sweep vs the report of inference/evaluate.py:61-128 (sweep_golden.npz)."""
+    import json
+    from facerecognition_b200.evaluation import threshold_sweep
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sweep_golden.npz"))
+    ref = json.loads(str(g["report"]))
+    got = threshold_sweep(g["sim"], g["y_true"], g["y_pred"])
+    assert got["best_f1_threshold"] == ref["best_f1_threshold"] and got["best_accuracy_threshold"] == ref["best_accuracy_threshold"]
+    for a, b in zip(got["results"], ref["results"]):
+        assert a.keys() == b.keys()
+        for k in a:
+            assert a[k] == pytest.approx(b[k], abs=1e-12), k

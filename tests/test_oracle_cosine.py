@@ -78,3 +78,14 @@ def test_facenet_matcher_and_prototypes():
     np.testing.assert_allclose(P[1], O.mean_prototype(list(e[2:5])), atol=1e-7)
     s, i = O.batched_topk(e, P, 2)
     assert list(i[:, 0]) == list(lab)
+
+
+def test_oracle_prototypes_match_the_real_reference():
+    """oracle.cosine.compute_prototypes / mean_prototype vs outputs of the reference's compute_prototypes
+    (inference/extract_embeddings.py:555-592) and add_to_db (recognition_engine.py:391-422) in gallery_golden.npz."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "gallery_golden.npz"))
+    from oracle import cosine as OC
+    np.testing.assert_allclose(OC.compute_prototypes(g["emb"], g["labels"]), g["prototypes"], rtol=0, atol=1e-7)
+    for c, row in zip(g["add_classes"], g["add_rows"]):
+        np.testing.assert_allclose(OC.mean_prototype(list(g["emb"][g["labels"] == c])), row, rtol=0, atol=1e-7)
