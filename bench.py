@@ -259,6 +259,23 @@ def lbph_leg(torch, ops, NV, device, peaks):
                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                  "frac": gbs / peaks["hbm_gbs"], "traffic": ncu_traffic("chisq_kernel"),
                                  "note": "algorithmic bytes = 32768 B per (query, gallery row) pair: every query streams the gallery"}}
+    # front end: interleaved BGR video crops -> gray (3 B read + 1 B written per pixel)
+    n_fr = 32768
+    bgr = torch.randint(0, 256, (n_fr, 112, 112, 3), generator=gen, device=device, dtype=torch.uint8)
+    for _ in range(2):
+        gray = ops.bgr_to_gray(bgr)
+    NV.profile_enable(True)
+    NV.profile_read(NV.K_BGR2GRAY)
+    for _ in range(5):
+        gray = ops.bgr_to_gray(bgr)
+    ms, n = NV.profile_read(NV.K_BGR2GRAY)
+    NV.profile_enable(False)
+    gbs = n_fr * 112 * 112 * 4 / (ms / n * 1e-3) / 1e9
+    out["bgr2gray"] = {"frames_per_s": n_fr / (ms / n * 1e-3), "ms_per_launch": ms / n, "frames_per_launch": n_fr,
+                       "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                    "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                                    "note": "algorithmic bytes = 4 per pixel (3 read, 1 written)"}}
+    del bgr, gray
     # C5 shape on one GPU's share: 1024 frames, extract + chi-square NN against 125 000 histograms (1M / 8 GPUs)
     frames = faces[:1024].contiguous()
     gal5 = hist.view(torch.int16)[torch.randint(0, n_faces, (125_000,), generator=gen, device=device)].contiguous().view(torch.uint16)

@@ -43,6 +43,7 @@ SIGNATURES = {
     "frb_cosine_topk": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_int, c_int,
                                 c_int, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "frb_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "frb_bgr2gray_u8": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "frb_group_mean_renorm": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "frb_topk_merge_strided": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int, c_int, c_void_p,
                                        c_void_p, c_void_p]),
@@ -86,7 +87,7 @@ def call(fn: str, *args) -> None:
     check(fn, getattr(lib, fn)(*args))
 
 
-K_COSINE_TC, K_COSINE_SIMT, K_LBP_HIST, K_CHISQ = 0, 1, 2, 3
+K_COSINE_TC, K_COSINE_SIMT, K_LBP_HIST, K_CHISQ, K_BGR2GRAY = 0, 1, 2, 3, 4
 
 
 def profile_enable(on: bool) -> None:

@@ -131,6 +131,38 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const float *__rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// BGR -> gray, OpenCV's 8-bit fixed point (cv2.cvtColor COLOR_BGR2GRAY, 4.x): (3735 B + 19235 G + 9798 R + 2^14) >> 15.
+// HBM-bound: 3 bytes in, 1 byte out per pixel.  A thread converts 16 pixels: three 128-bit loads, one 128-bit store.
+__device__ __forceinline__ uint32_t gray_of(uint32_t b, uint32_t g, uint32_t r)
+{
+    return (b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15;
+}
+
+__global__ void __launch_bounds__(256) bgr2gray_kernel(const uint8_t *__restrict__ bgr, int64_t n_px, uint8_t *__restrict__ out, int vec_ok)
+{
+    const int64_t n_vec = vec_ok ? n_px / 16 : 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec; v += stride) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(bgr) + v * 3;
+        const uint4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+        const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {  // 4 pixels = 12 bytes = 3 words
+            const uint32_t w0 = w[3 * q], w1 = w[3 * q + 1], w2 = w[3 * q + 2];
+            const uint32_t g0 = gray_of(w0 & 0xFF, (w0 >> 8) & 0xFF, (w0 >> 16) & 0xFF);
+            const uint32_t g1 = gray_of(w0 >> 24, w1 & 0xFF, (w1 >> 8) & 0xFF);
+            const uint32_t g2 = gray_of((w1 >> 16) & 0xFF, w1 >> 24, w2 & 0xFF);
+            const uint32_t g3 = gray_of((w2 >> 8) & 0xFF, (w2 >> 16) & 0xFF, w2 >> 24);
+            o[q] = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+        }
+        reinterpret_cast<uint4 *>(out)[v] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    for (int64_t i = n_vec * 16 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += stride)
+        out[i] = (uint8_t)gray_of(__ldg(bgr + 3 * i), __ldg(bgr + 3 * i + 1), __ldg(bgr + 3 * i + 2));
+}
+
+// ---------------------------------------------------------------------------------------------
 // Gallery builder: out[g] = mean(rows of group g) / (||mean|| + 1e-8).  One CTA per group; thread t owns dims
 // t, t + 128, ...; rows are added in the order given (ascending sample index), in float32, then divided by the
 // count, as numpy's mean(axis=0) does; sum of squares by a block reduction.  Empty groups stay all-zero.
@@ -382,6 +414,22 @@ static int topk_merge_launch(const char *fn, const float *cs, const int64_t *ci,
     else
         topk_merge_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(cs, ci, s_stride, i_stride, n_lists, n_query, k, os, oi);
     FRB_LAUNCH_OK("topk_merge_kernel");
+    return FRB_OK;
+}
+
+int frb_bgr2gray_u8(const uint8_t *bgr, int64_t n_pixels, uint8_t *out, void *stream)
+{
+    FRB_CHECK_ARG(n_pixels >= 0, "frb_bgr2gray_u8: n_pixels=%lld", (long long)n_pixels);
+    if (n_pixels == 0) return FRB_OK;
+    FRB_CHECK_ARG(bgr && out, "frb_bgr2gray_u8: null pointer");
+    const int vec_ok = (((uintptr_t)bgr | (uintptr_t)out) & 15) == 0;
+    int64_t blocks = (n_pixels / 16 + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    ProfileScope prof(FRB_K_BGR2GRAY, (cudaStream_t)stream);
+    bgr2gray_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(bgr, n_pixels, out, vec_ok);
+    FRB_LAUNCH_OK("bgr2gray_kernel");
     return FRB_OK;
 }
 

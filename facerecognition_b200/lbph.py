@@ -170,6 +170,11 @@ class LBPHFaceRecognizer:
         q_hist, q_px = self.compute_histograms(images)
         return self._search(q_hist, q_px, k)
 
+    def predict_device_bgr(self, frames_bgr: torch.Tensor, k: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Video-batch front end: u8 CUDA [Q, H, W, 3] BGR crops -> gray on the device (frb_bgr2gray_u8, the
+        cv2.cvtColor step of web_app.py:475) -> predict_device."""
+        return self.predict_device(ops.bgr_to_gray(frames_bgr), k)
+
     def predict_batch(self, images) -> Tuple[np.ndarray, np.ndarray]:
         """Batched predict: (labels int32 [Q], distances float64 [Q]); (-1, DBL_MAX) where the model
         threshold rejects the best match (dist >= threshold), as StandardCollector does."""

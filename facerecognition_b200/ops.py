@@ -141,6 +141,16 @@ def topk_merge_packed(buf: torch.Tensor, n_query: int, k: int, largest: bool) ->
     return scores, idx
 
 
+def bgr_to_gray(frames: torch.Tensor) -> torch.Tensor:
+    """frb_bgr2gray_u8: u8 [..., 3] interleaved BGR -> u8 [...] gray, bit-exact with cv2.cvtColor(COLOR_BGR2GRAY)."""
+    dev = _require_cuda(frames)
+    assert frames.dtype == torch.uint8 and frames.dim() >= 2 and frames.shape[-1] == 3
+    out = torch.empty(frames.shape[:-1], dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.call("frb_bgr2gray_u8", _p(frames), _I64(out.numel()), _p(out), _stream(dev))
+    return out
+
+
 def lbp_codes(images: torch.Tensor, radius: int = 1, neighbors: int = 8) -> torch.Tensor:
     """frb_lbp_codes_u8: u8 [B, H, W] -> u8 [B, H-2, W-2] LBP codes (OpenCV elbp_ semantics)."""
     dev = _require_cuda(images)

@@ -74,7 +74,8 @@ typedef enum frb_kernel {
     FRB_K_COSINE_SIMT = 1, /* cosine_simt_kernel (fp32 FFMA similarity + top-k)    */
     FRB_K_LBP_HIST = 2,    /* lbp_hist_kernel                                       */
     FRB_K_CHISQ = 3,       /* chisq_kernel                                          */
-    FRB_K_COUNT = 4
+    FRB_K_BGR2GRAY = 4,    /* bgr2gray_kernel                                       */
+    FRB_K_COUNT = 5
 } frb_kernel;
 
 /* When enabled, every launch of the four hot kernels is bracketed by a CUDA event pair on the
@@ -139,6 +140,12 @@ int frb_topk_merge(const float *cand_scores_dev, const int64_t *cand_idx_dev, in
 int frb_topk_merge_strided(const float *cand_scores_dev, const int64_t *cand_idx_dev, int64_t score_list_stride,
                            int64_t idx_list_stride, int n_lists, int64_t n_query, int k, int largest,
                            float *out_scores_dev, int64_t *out_idx_dev, void *stream);
+
+/* BGR -> gray front end of the LBPH path: bgr u8 [n_pixels, 3] (interleaved, as cv2 frames) -> gray u8 [n_pixels],
+ * OpenCV's 8-bit fixed point (3735 B + 19235 G + 9798 R + 2^14) >> 15, bit-exact with cv2.cvtColor(COLOR_BGR2GRAY)
+ * of OpenCV 4.13 over all 2^24 colours.  Replaces the cv2.cvtColor calls that feed LBPH
+ * (models/lbphmodel/train_lbph_script.py:72, web_app.py:475,486). */
+int frb_bgr2gray_u8(const uint8_t *bgr_dev, int64_t n_pixels, uint8_t *out_gray_dev, void *stream);
 
 /* ---- LBPH path (K2, K3) ---------------------------------------------------------------- */
 

@@ -220,3 +220,28 @@ def test_baseline_config1_shape_train_predict_1k(oracle_lbph):
         j = int(np.argmin(ref))
         assert abs(confs[r] - ref[j]) <= REL * ref[j]
         assert labs[r] == labels[j] or abs(ref[j] - np.partition(ref, 1)[1]) <= REL * ref[j]
+
+
+def test_bgr2gray_is_bit_exact_with_cv2():
+    """frb_bgr2gray_u8 vs the REAL cv2.cvtColor(COLOR_BGR2GRAY) of the installed OpenCV core: a colour cube slab
+    (every B, G with 16 R values), random frames of ragged sizes, and the batched video front end."""
+    import cv2
+    from facerecognition_b200 import ops
+    b, g, r = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8),
+                          np.arange(0, 256, 16, dtype=np.uint8) + 7, indexing="ij")
+    cube = np.stack([b.ravel(), g.ravel(), r.ravel()], 1).reshape(1024, 1024, 3)
+    got = ops.bgr_to_gray(torch.from_numpy(cube).cuda()).cpu().numpy()
+    np.testing.assert_array_equal(got, cv2.cvtColor(cube, cv2.COLOR_BGR2GRAY))
+    rng = np.random.default_rng(4)
+    for shape in [(1, 1, 3), (3, 5, 3), (7, 112, 112, 3), (2, 101, 99, 3)]:
+        x = rng.integers(0, 256, shape, dtype=np.uint8)
+        if len(shape) == 4:
+            ref = np.stack([cv2.cvtColor(f, cv2.COLOR_BGR2GRAY) for f in x])
+        else:
+            ref = cv2.cvtColor(x, cv2.COLOR_BGR2GRAY)
+        np.testing.assert_array_equal(ops.bgr_to_gray(torch.from_numpy(x).cuda()).cpu().numpy(), ref)
+    # unaligned base pointer -> scalar path
+    x = rng.integers(0, 256, (64 * 3 + 1,), dtype=np.uint8)
+    t = torch.from_numpy(x).cuda()[1:].view(64, 3)
+    np.testing.assert_array_equal(ops.bgr_to_gray(t.contiguous()).cpu().numpy(),
+                                  cv2.cvtColor(x[1:].reshape(1, 64, 3), cv2.COLOR_BGR2GRAY)[0])
