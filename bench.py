@@ -166,7 +166,7 @@ def workload_config(world, n_gallery, n_query_total):
     return {"workload": "configs[2]: FaceNet 512-d cosine top-5, 1M-row bf16 gallery, 4096-query batch per GPU",
             "gallery_rows": n_gallery, "queries_per_step": n_query_total, "dim": DIM, "k": TOPK,
             "sharding": (f"gallery rows by identity over {world} ranks, batch = 4096 x {world} queries; "
-                         "1 NCCL all-gather of [Q,5] candidates + merge") if world > 1 else "none",
+                         "per-rank [Q,5] candidates exchanged once and merged on every rank") if world > 1 else "none",
             "l2": "flushed between timed steps (256 MiB memset outside the event bracket); shard >= L2"}
 
 
@@ -449,6 +449,9 @@ def main():
     }
     if strong:
         line["strong"] = strong
+    if world > 1:
+        line["config"]["exchange"] = ("one fused kernel over NVLink peer memory (frb_exchange_topk_merge: peer stores + flags + merge)"
+                                      if search._exchange is not None else "one NCCL all-gather of packed records + frb_topk_merge_strided")
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # bounded CPU sample: 256-query chunks of the same batch against the full gallery until ~12 s

@@ -17,6 +17,7 @@ FRB_F32, FRB_BF16 = 0, 1
 FRB_QNORM_NONE, FRB_QNORM_CLAMP, FRB_QNORM_EPS = 0, 1, 2
 FRB_SCORE_IP, FRB_SCORE_REF_COSINE = 0, 1
 FRB_MAX_K = 64
+FRB_EXCHANGE_MAX_WORLD, FRB_IPC_HANDLE_BYTES = 8, 64
 
 _STATUS_NAMES = {0: "FRB_OK", -1: "FRB_ERR_INVALID", -2: "FRB_ERR_UNSUPPORTED", -3: "FRB_ERR_CUDA",
                  -4: "FRB_ERR_WORKSPACE"}
@@ -47,6 +48,11 @@ SIGNATURES = {
     "frb_group_mean_renorm": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "frb_topk_merge_strided": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int, c_int, c_void_p,
                                        c_void_p, c_void_p]),
+    "frb_exchange_create": (c_int, [c_int, c_int, c_int64, c_int, c_void_p, c_void_p]),
+    "frb_exchange_open": (c_int, [c_void_p, c_void_p]),
+    "frb_exchange_destroy": (c_int, [c_void_p]),
+    "frb_exchange_topk_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "frb_exchange_emulate": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "frb_lbp_codes_u8": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "frb_lbp_hist_u8": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p]),

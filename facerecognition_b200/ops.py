@@ -7,7 +7,7 @@ docstring, and returns CUDA tensors.  No arithmetic is done in torch.
 from __future__ import annotations
 
 import ctypes
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 
@@ -149,6 +149,59 @@ def bgr_to_gray(frames: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(dev):
         N.call("frb_bgr2gray_u8", _p(frames), _I64(out.numel()), _p(out), _stream(dev))
     return out
+
+
+class Exchange:
+    """frb_exchange_*: this rank's peer-memory exchange buffer (see include/frb200.h).  `handle` is the 64-byte CUDA
+    IPC handle to all-gather; `open(handles)` maps the peers; `topk_merge` is the fused exchange + merge kernel."""
+
+    def __init__(self, world: int, rank: int, max_query: int, max_k: int, device: torch.device):
+        self.world, self.rank, self.max_query, self.max_k, self.device = world, rank, max_query, max_k, device
+        self._ctx = ctypes.c_void_p(0)
+        buf = (ctypes.c_ubyte * N.FRB_IPC_HANDLE_BYTES)()
+        with torch.cuda.device(device):
+            N.call("frb_exchange_create", world, rank, _I64(max_query), max_k, ctypes.byref(self._ctx), buf)
+        self.handle = bytes(buf)
+
+    def open(self, handles: bytes) -> None:
+        assert len(handles) == self.world * N.FRB_IPC_HANDLE_BYTES
+        with torch.cuda.device(self.device):
+            N.call("frb_exchange_open", self._ctx, ctypes.c_char_p(handles))
+
+    def topk_merge(self, scores: torch.Tensor, idx: torch.Tensor, largest: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+        dev = _require_cuda(scores, idx)
+        assert scores.dtype == torch.float32 and idx.dtype == torch.int64 and scores.shape == idx.shape and scores.dim() == 2
+        q, k = scores.shape
+        out_s = torch.empty_like(scores)
+        out_i = torch.empty_like(idx)
+        with torch.cuda.device(dev):
+            N.call("frb_exchange_topk_merge", self._ctx, _p(scores), _p(idx), _I64(q), k, 1 if largest else 0, _p(out_s), _p(out_i),
+                   _stream(dev))
+        return out_s, out_i
+
+    def close(self) -> None:
+        if self._ctx:
+            N.lib.frb_exchange_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def exchange_emulate(ranks: Sequence["Exchange"], scores: torch.Tensor, idx: torch.Tensor, largest: bool
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """frb_exchange_emulate: [R, Q, k] local lists -> [R, Q, k] merged lists, all ranks in one launch on one GPU."""
+    dev = _require_cuda(scores, idx)
+    r, q, k = scores.shape
+    assert len(ranks) == r and idx.shape == scores.shape
+    arr = (ctypes.c_void_p * r)(*[x._ctx for x in ranks])
+    out_s, out_i = torch.empty_like(scores), torch.empty_like(idx)
+    with torch.cuda.device(dev):
+        N.call("frb_exchange_emulate", arr, r, _p(scores), _p(idx), _I64(q), k, 1 if largest else 0, _p(out_s), _p(out_i), _stream(dev))
+    return out_s, out_i
 
 
 def lbp_codes(images: torch.Tensor, radius: int = 1, neighbors: int = 8) -> torch.Tensor:

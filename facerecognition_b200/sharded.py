@@ -2,9 +2,11 @@
 
 One process per GPU (torch.distributed, NCCL over NVLink).  Rank r owns gallery rows
 [shard_bounds(N, R, r)); queries are replicated; every rank runs the local fused search with
-idx_base = its first row, so candidates carry GLOBAL row ids; ONE all-gather of the packed [Q, k] (id, score)
-records follows and every rank merges the R lists in place with frb_topk_merge_strided (ties -> lowest global
-id, so the answer is identical for any R).  Nothing else crosses NVLink: shards are loaded once and never move.
+idx_base = its first row, so candidates carry GLOBAL row ids.  The exchange is ONE kernel over NVLink peer memory
+(frb_exchange_topk_merge: every CTA stores its queries' candidates into all ranks' buffers, flags them, waits for
+the same CTA of every rank and merges); where CUDA IPC is not available — and under gloo in the CPU tests — it is
+ONE all-gather of the packed [Q, k] (id, score) records followed by frb_topk_merge_strided.  Ties -> lowest
+global id, so the answer is identical for any R and for either transport.  Nothing else crosses NVLink: shards are loaded once and never move.
 
 `local_search` and `merge` are injectable so the host-side plumbing (bounds, id offsets, gather layout)
 can be exercised with the gloo backend on a CPU-only box; the product wiring below binds them to the
@@ -44,9 +46,51 @@ class ShardedSearch:
                  merge: Optional[Callable[[torch.Tensor, torch.Tensor, bool], Tuple[torch.Tensor, torch.Tensor]]],
                  largest: bool, group: Optional[dist.ProcessGroup] = None,
                  local_into: Optional[Callable[[torch.Tensor, int, torch.Tensor, torch.Tensor], None]] = None,
-                 merge_packed: Optional[Callable[[torch.Tensor, int, int, bool], Tuple[torch.Tensor, torch.Tensor]]] = None):
+                 merge_packed: Optional[Callable[[torch.Tensor, int, int, bool], Tuple[torch.Tensor, torch.Tensor]]] = None,
+                 peer_exchange: bool = False):
         self.local_search, self.merge, self.largest, self.group = local_search, merge, largest, group
         self.local_into, self.merge_packed = local_into, merge_packed
+        # peer_exchange: use the fused NVLink exchange + merge kernel (frb_exchange_topk_merge) instead of the
+        # all-gather; set up lazily, and only if every rank managed to map every peer's buffer (CUDA IPC)
+        self.peer_exchange, self._exchange, self._exchange_failed = peer_exchange, None, False
+
+    def _get_exchange(self, n_query: int, k: int, device: torch.device):
+        from . import _native as N
+        from . import ops
+        ex = self._exchange
+        if ex is not None and n_query <= ex.max_query and k <= ex.max_k:
+            return ex
+        if self._exchange_failed:
+            return None
+        world, rank = self.world(), dist.get_rank(self.group)
+        ok, new = 1, None
+        try:
+            new = ops.Exchange(world, rank, max(n_query, ex.max_query if ex else 0), max(k, ex.max_k if ex else 0), device)
+            mine = torch.tensor(list(new.handle), dtype=torch.uint8, device=device)
+        except N.FrbError:
+            ok, mine = 0, torch.zeros(N.FRB_IPC_HANDLE_BYTES, dtype=torch.uint8, device=device)
+        handles = torch.empty(world * N.FRB_IPC_HANDLE_BYTES, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(handles, mine, group=self.group)
+        if ok:
+            try:
+                new.open(bytes(handles.cpu().tolist()))
+            except N.FrbError:
+                ok = 0
+        agree = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=self.group)    # all ranks take the same path
+        if int(agree.item()) == 0:
+            self._exchange_failed = True
+            if new is not None:
+                new.close()
+            if rank == 0:
+                print("facerecognition_b200: peer-memory exchange unavailable (CUDA IPC), using the all-gather path")
+            return None
+        if ex is not None:
+            torch.cuda.synchronize(device)
+            dist.barrier(group=self.group)       # nobody is still reading the old buffers
+            ex.close()
+        self._exchange = new
+        return new
 
     def world(self) -> int:
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
@@ -56,6 +100,11 @@ class ShardedSearch:
         n_query = queries.shape[0]
         if world == 1:
             return self.local_search(queries, k)               # [Q, k] with global ids
+        if self.peer_exchange and queries.is_cuda:
+            ex = self._get_exchange(n_query, k, queries.device)
+            if ex is not None:
+                scores, idx = self.local_search(queries, k)
+                return ex.topk_merge(scores, idx, self.largest)   # ONE kernel: peer stores + flags + merge
         idx_bytes, rec, rec_pad = _record_layout(n_query, k)
         rank = dist.get_rank(self.group)
         gathered = torch.empty((world, rec_pad), dtype=torch.uint8, device=queries.device)
@@ -77,7 +126,7 @@ class ShardedSearch:
 
 
 def cosine_sharded(gallery_shard: torch.Tensor, row_offset: int, *, qnorm_mode: int = 0,
-                   group: Optional[dist.ProcessGroup] = None) -> ShardedSearch:
+                   group: Optional[dist.ProcessGroup] = None, peer_exchange: bool = True) -> ShardedSearch:
     """Product wiring for K1: `gallery_shard` = this rank's rows (fp32 or bf16, CUDA), `row_offset` = global id of row 0."""
     from . import _native as N
     from . import ops
@@ -89,15 +138,16 @@ def cosine_sharded(gallery_shard: torch.Tensor, row_offset: int, *, qnorm_mode: 
         ops.cosine_topk(q, gallery_shard, k, score_mode=N.FRB_SCORE_IP, qnorm_mode=qnorm_mode, idx_base=row_offset,
                         out=(scores, idx))
 
-    return ShardedSearch(local, ops.topk_merge, True, group, local_into=local_into, merge_packed=ops.topk_merge_packed)
+    return ShardedSearch(local, ops.topk_merge, True, group, local_into=local_into, merge_packed=ops.topk_merge_packed,
+                         peer_exchange=peer_exchange)
 
 
 def chisq_sharded(hist_shard: torch.Tensor, cell_px: int, row_offset: int, *, q_cell_px: Optional[int] = None,
-                  group: Optional[dist.ProcessGroup] = None) -> ShardedSearch:
+                  group: Optional[dist.ProcessGroup] = None, peer_exchange: bool = True) -> ShardedSearch:
     """Product wiring for K3: u16 histogram shard; queries are u16 histograms [Q, L]."""
     from . import ops
 
     def local(q_hist: torch.Tensor, k: int):
         return ops.chisq_topk(q_hist, q_cell_px or cell_px, hist_shard, cell_px, k, idx_base=row_offset)
 
-    return ShardedSearch(local, ops.topk_merge, False, group, merge_packed=ops.topk_merge_packed)
+    return ShardedSearch(local, ops.topk_merge, False, group, merge_packed=ops.topk_merge_packed, peer_exchange=peer_exchange)

@@ -147,6 +147,34 @@ int frb_topk_merge_strided(const float *cand_scores_dev, const int64_t *cand_idx
  * (models/lbphmodel/train_lbph_script.py:72, web_app.py:475,486). */
 int frb_bgr2gray_u8(const uint8_t *bgr_dev, int64_t n_pixels, uint8_t *out_gray_dev, void *stream);
 
+/* ---- cross-GPU exchange fused with the merge, over NVLink peer memory ------------------------------------- */
+/* One context per rank (process).  frb_exchange_create cudaMallocs this rank's buffer — `world` record slots of
+ * max_query x max_k candidates, double-buffered by step parity, plus one flag per (rank, 128-query CTA) — and
+ * returns its CUDA IPC handle (FRB_IPC_HANDLE_BYTES bytes).  The host all-gathers the handles (any transport) and
+ * passes all `world` of them, in rank order, to frb_exchange_open, which maps the peers' buffers.
+ * frb_exchange_topk_merge is then ONE kernel per step: each CTA stores its queries' local candidates into every
+ * rank's buffer (peer stores), release-stores the step's epoch into the peers' flags, acquire-waits for the same
+ * CTA of every rank, and merges (ties -> lowest global id).  All ranks must call it in lockstep (the epoch is a
+ * per-context call counter).  A rank that does not arrive within ~2 s traps the kernel.
+ * Replaces the all-gather + frb_topk_merge_strided pair of facerecognition_b200/sharded.py; no reference
+ * counterpart (the reference is single-device). */
+#define FRB_EXCHANGE_MAX_WORLD 8
+#define FRB_IPC_HANDLE_BYTES 64
+typedef struct frb_exchange frb_exchange;
+int frb_exchange_create(int world, int rank, int64_t max_query, int max_k, frb_exchange **out,
+                        unsigned char *ipc_handle_out);
+int frb_exchange_open(frb_exchange *ex, const unsigned char *ipc_handles /* world x FRB_IPC_HANDLE_BYTES */);
+int frb_exchange_destroy(frb_exchange *ex);
+int frb_exchange_topk_merge(frb_exchange *ex, const float *local_scores_dev, const int64_t *local_idx_dev,
+                            int64_t n_query, int k, int largest, float *out_scores_dev, int64_t *out_idx_dev,
+                            void *stream);
+/* Test hook: `world` contexts created in ONE process on one device act as the ranks of a single launch
+ * (local_* and out_* are [world, n_query, k]); exercises the store / flag / wait / merge protocol without
+ * a second GPU. */
+int frb_exchange_emulate(frb_exchange *const *ranks, int world, const float *local_scores_dev,
+                         const int64_t *local_idx_dev, int64_t n_query, int k, int largest, float *out_scores_dev,
+                         int64_t *out_idx_dev, void *stream);
+
 /* ---- LBPH path (K2, K3) ---------------------------------------------------------------- */
 
 /* LBP codes, OpenCV elbp_ semantics (radius 1, 8 neighbours, float32 bilinear diagonals,

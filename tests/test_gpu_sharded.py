@@ -56,3 +56,27 @@ def test_chisq_shards_merge_to_unsharded_result(R):
     md, mi = ops.topk_merge(torch.stack(cd).contiguous(), torch.stack(ci).contiguous(), largest=False)
     assert torch.equal(mi, full_i) and torch.equal(md, full_d)
     assert [int(x) for x in mi[0, :2]] == [3, N - 2] and md[0, 0].item() == 0.0
+
+
+@pytest.mark.parametrize("R,largest", [(2, True), (8, True), (3, False)])
+def test_peer_exchange_protocol_emulated_on_one_gpu(R, largest):
+    """frb_exchange_emulate: R rank contexts in one process, ONE launch with blockIdx.y = rank, runs the real
+    store / release-flag / acquire-wait / merge kernel; every emulated rank must end with the unsharded merge.
+    Two steps in a row exercise the epoch / parity double buffering, and a smaller second batch the re-layout."""
+    from facerecognition_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(R)
+    ranks = [ops.Exchange(R, r, 700, 5, torch.device("cuda")) for r in range(R)]
+    try:
+        for Q, k in [(700, 5), (333, 3), (700, 5)]:
+            s = torch.randn((R, Q, k), generator=gen, device="cuda")
+            s = torch.sort(s, dim=2, descending=largest).values
+            i = torch.randint(0, 10_000, (R, Q, k), generator=gen, device="cuda")
+            s[1, 0, 0] = s[0, 0, 0]                       # a tie across ranks: the lower id must win
+            i[R - 1, 5, k - 1] = -1                        # padding entry
+            want_s, want_i = ops.topk_merge(s.contiguous(), i.contiguous(), largest)
+            got_s, got_i = ops.exchange_emulate(ranks, s.contiguous(), i.contiguous(), largest)
+            for r in range(R):
+                assert torch.equal(got_i[r], want_i) and torch.equal(got_s[r], want_s)
+    finally:
+        for x in ranks:
+            x.close()
