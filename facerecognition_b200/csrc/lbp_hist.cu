@@ -98,6 +98,9 @@ __global__ void __launch_bounds__(256) lbp_codes_kernel(const uint8_t *__restric
 //     (0, 255, ...) of neighbouring cells fall into banks 4 apart; the write-out splits the halves and stores
 //     128 bits per cell.
 constexpr unsigned kLbpPairVec = 65;  // uint4 groups per cell pair: 256 counters + 16 bytes of bank skew
+#ifndef LBP_MIN_BLOCKS
+#define LBP_MIN_BLOCKS 3
+#endif
 constexpr int kLbpMaxThreads = 224;  // 7 warps: 8x8 grid on 112x112 = 208 work items; 3 CTAs/SM at <= 96 registers
 
 __device__ __forceinline__ uint32_t lbp_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -224,7 +227,7 @@ __device__ __forceinline__ void lbp_emit_row2(const LbpRow2 &top, const LbpRow2 
 }
 
 template <bool ALIGNED16>
-__global__ void __launch_bounds__(kLbpMaxThreads, 3) lbp_hist_kernel(const uint8_t *__restrict__ img, int64_t count, int rows,
+__global__ void __launch_bounds__(kLbpMaxThreads, LBP_MIN_BLOCKS) lbp_hist_kernel(const uint8_t *__restrict__ img, int64_t count, int rows,
                                                                      int cols, int grid_x, int grid_y, int img_smem_bytes,
                                                                      uint16_t *__restrict__ out)
 {
@@ -324,6 +327,148 @@ __global__ void __launch_bounds__(kLbpMaxThreads, 3) lbp_hist_kernel(const uint8
     }
 }
 
+// ---- pipelined variant (TMA-staged images): no block-wide barrier in steady state ---------------------------------
+// Warps 0..W-2 code images, the last warp is the writer.  Counters and image buffers are both double-buffered:
+//   full[b]  (TMA tx)        image n has landed in image buffer b = n & 1
+//   done[b]  (compute warps) every compute warp has finished coding image n into counter buffer b
+//   clean[b] (writer)        counter buffer b has been written out and cleared
+// A compute warp that finishes image n early goes straight on to image n + 1 (other buffers); it only waits for
+// things that happened a whole image ago (clean[b] of image n - 1's predecessor), so warp skew is absorbed instead of
+// being paid at a barrier.  The writer requests image n + 2 as soon as done[b] frees image buffer b.
+constexpr int kLbpPipeThreads = 256;
+
+// the writer warp waits for most of an image's coding time: back off so its polling does not take issue slots
+__device__ __forceinline__ void lbp_mbar_wait_relaxed(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(lbp_smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(256);
+    }
+}
+
+__device__ __forceinline__ void lbp_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(lbp_smem_u32(bar)) : "memory");
+}
+
+template <bool ALIGNED16>
+__global__ void __launch_bounds__(kLbpPipeThreads, 2) lbp_hist_pipe_kernel(const uint8_t *__restrict__ img, int64_t count, int rows,
+                                                                          int cols, int grid_x, int grid_y, int img_smem_bytes,
+                                                                          int hist_smem_bytes, uint16_t *__restrict__ out)
+{
+    // shared: [full[2], done[2], clean[2] mbarriers][image buffers 0, 1][counter buffers 0, 1]
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint64_t *s_full = reinterpret_cast<uint64_t *>(smem), *s_done = s_full + 2, *s_clean = s_full + 4;
+    uint8_t *s_img0 = smem + 64;
+    unsigned char *s_hist0 = smem + 64 + 2 * img_smem_bytes;
+
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned n_cwarps = (blockDim.x >> 5) - 1, n_cthreads = n_cwarps * 32;
+    const unsigned ocols = cols - 2, orows = rows - 2;
+    const unsigned gx = grid_x, gy = grid_y;
+    const unsigned cw = ocols / gx, ch = orows / gy;
+    const unsigned used_cols = cw * gx;
+    const unsigned strips = (used_cols + 1) >> 1;
+    const unsigned half = (gy + 1) >> 1;
+    const unsigned items = strips * half;
+    const unsigned pairs = half * gx;
+    const unsigned img_bytes = rows * cols;
+
+    for (unsigned w = tid; w < 2u * hist_smem_bytes / 16; w += blockDim.x) reinterpret_cast<uint4 *>(s_hist0)[w] = make_uint4(0, 0, 0, 0);
+    if (tid < 32) s_img0[(tid >> 4) * img_smem_bytes + img_smem_bytes - 16 + (tid & 15)] = 0;
+    if (tid == 0) {
+        for (int i = 0; i < 2; i++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lbp_smem_u32(&s_full[i])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lbp_smem_u32(&s_done[i])), "r"(n_cwarps));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lbp_smem_u32(&s_clean[i])));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == n_cwarps) {
+        // ---- writer / producer warp ---------------------------------------------------------------------------
+        if (lane == 0) {
+            for (int i = 0; i < 2; i++) {
+                const int64_t b = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
+                if (b < count) lbp_bulk_load(s_img0 + i * img_smem_bytes, img + b * img_bytes, img_bytes, &s_full[i]);
+            }
+        }
+        unsigned n = 0;
+        for (int64_t b = blockIdx.x; b < count; b += gridDim.x, n++) {
+            const unsigned buf = n & 1, par = (n >> 1) & 1;
+            lbp_mbar_wait_relaxed(&s_done[buf], par);  // image n is coded: its image buffer is free, its counters are final
+            const int64_t nxt = b + 2 * (int64_t)gridDim.x;
+            if (lane == 0 && nxt < count) lbp_bulk_load(s_img0 + buf * img_smem_bytes, img + nxt * img_bytes, img_bytes, &s_full[buf]);
+            uint4 *hist = reinterpret_cast<uint4 *>(s_hist0 + (size_t)buf * hist_smem_bytes);
+            uint4 *dst = reinterpret_cast<uint4 *>(out + b * (int64_t)gx * gy * 256);
+            for (unsigned w = lane; w < pairs * 32; w += 32) {
+                const unsigned pair = w >> 5, j = w & 31;
+                uint4 *grp = hist + pair * kLbpPairVec + 2 * j;
+                const uint4 u = grp[0], v = grp[1];
+                grp[0] = make_uint4(0, 0, 0, 0);
+                grp[1] = make_uint4(0, 0, 0, 0);
+                dst[pair * 32 + j] = make_uint4(__byte_perm(u.x, u.y, 0x5410), __byte_perm(u.z, u.w, 0x5410),
+                                                __byte_perm(v.x, v.y, 0x5410), __byte_perm(v.z, v.w, 0x5410));
+                if (pair + half * gx < gx * gy)
+                    dst[(pair + half * gx) * 32 + j] = make_uint4(__byte_perm(u.x, u.y, 0x7632), __byte_perm(u.z, u.w, 0x7632),
+                                                                   __byte_perm(v.x, v.y, 0x7632), __byte_perm(v.z, v.w, 0x7632));
+            }
+            __syncwarp();
+            if (lane == 0) lbp_mbar_arrive(&s_clean[buf]);
+        }
+        return;
+    }
+
+    // ---- compute warps ------------------------------------------------------------------------------------------
+    unsigned n = 0;
+    for (int64_t b = blockIdx.x; b < count; b += gridDim.x, n++) {
+        const unsigned buf = n & 1, par = (n >> 1) & 1;
+        const uint8_t *s_img = s_img0 + buf * img_smem_bytes;
+        const unsigned hist_addr = lbp_smem_u32(s_hist0 + (size_t)buf * hist_smem_bytes);
+        lbp_mbar_wait(&s_full[buf], par);
+        if (n >= 2) lbp_mbar_wait(&s_clean[buf], par ^ 1);  // image n - 2 (previous tenant of these counters) is written out
+
+        for (unsigned it = tid; it < items; it += n_cthreads) {
+            const unsigned band = it / strips, x0 = (it - band * strips) * 2;
+            const bool two = x0 + 1 < used_cols;
+            const bool lane_y = band + half < gy;
+            const unsigned cx0 = x0 / cw, cx1 = (x0 + 1) / cw;
+            LbpCells cells;
+            cells.pair_last[0] = hist_addr + (band * gx + cx0) * (kLbpPairVec * 16) + 1020;
+            cells.pair_last[1] = hist_addr + (two ? band * gx + cx1 : pairs) * (kLbpPairVec * 16) + 1020;
+            const uint8_t *p = s_img + band * ch * cols + x0;
+            const unsigned dy = lane_y ? half * ch * cols : 0;
+            LbpRow2 r[3];
+            lbp_load_row2<ALIGNED16>(r[0], p, p + dy);
+            lbp_load_row2<ALIGNED16>(r[1], p + cols, p + cols + dy);
+            p += 2 * cols;
+            for (unsigned y = 0; y < ch; y += 3) {
+#pragma unroll
+                for (int ph = 0; ph < 3; ph++) {
+                    if (y + ph < ch) {
+                        lbp_load_row2<ALIGNED16>(r[(ph + 2) % 3], p, p + dy);
+                        p += cols;
+                        lbp_emit_row2(r[ph % 3], r[(ph + 1) % 3], r[(ph + 2) % 3], cells);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) lbp_mbar_arrive(&s_done[buf]);
+    }
+}
+
 }  // namespace frb
 
 using namespace frb;
@@ -374,19 +519,48 @@ int frb_lbp_hist_u8(const uint8_t *images, int64_t count, int rows, int cols, in
     // +16: the right-most column pair reads up to 2 bytes past the image (zeroed, never used in a code it emits)
     const int img_smem = (int)align_up((size_t)rows * cols, 16) + 16;
     // counters: one u32 per (cell pair, bin), pairs = ceil(grid_y / 2) * grid_x, plus one scratch pair
-    const size_t smem = 16 + 2 * (size_t)img_smem + ((size_t)grid_x * ((grid_y + 1) / 2) + 1) * (kLbpPairVec * 16);
+    const size_t hist_bytes = ((size_t)grid_x * ((grid_y + 1) / 2) + 1) * (kLbpPairVec * 16);
+    const bool aligned16 = (cols % 2) == 0;
+    // one thread per (band pair, column pair) when that fits a CTA
+    const int items = ((cw * grid_x + 1) / 2) * ((grid_y + 1) / 2);
+    // images the TMA can fetch (16-byte aligned, a multiple of 16 bytes) take the pipelined kernel: double-buffered
+    // counters, a writer warp, no block-wide barrier
+    const bool bulk_ok = (((size_t)rows * cols) & 15) == 0 && ((uintptr_t)images & 15) == 0;
+    const size_t pipe_smem = 64 + 2 * (size_t)img_smem + 2 * hist_bytes;
+    if (bulk_ok && pipe_smem <= 113 * 1024) {
+        int threads = (items + 31) / 32 * 32 + 32;
+        if (threads > kLbpPipeThreads) threads = kLbpPipeThreads;
+        int per_sm = 1;
+        if (aligned16) {
+            FRB_CUDA_OK(cudaFuncSetAttribute(lbp_hist_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem));
+            FRB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbp_hist_pipe_kernel<true>, threads, pipe_smem));
+        } else {
+            FRB_CUDA_OK(cudaFuncSetAttribute(lbp_hist_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem));
+            FRB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbp_hist_pipe_kernel<false>, threads, pipe_smem));
+        }
+        if (per_sm < 1) per_sm = 1;
+        const int64_t cap = (int64_t)sm_count() * per_sm;
+        const int grid = (int)(count < cap ? count : cap);
+        {
+            ProfileScope prof(FRB_K_LBP_HIST, (cudaStream_t)stream);
+            if (aligned16)
+                lbp_hist_pipe_kernel<true><<<grid, threads, pipe_smem, (cudaStream_t)stream>>>(images, count, rows, cols, grid_x, grid_y, img_smem, (int)hist_bytes, out_hist);
+            else
+                lbp_hist_pipe_kernel<false><<<grid, threads, pipe_smem, (cudaStream_t)stream>>>(images, count, rows, cols, grid_x, grid_y, img_smem, (int)hist_bytes, out_hist);
+        }
+        FRB_LAUNCH_OK("lbp_hist_pipe_kernel");
+        return FRB_OK;
+    }
+    const size_t smem = 16 + 2 * (size_t)img_smem + hist_bytes;
     if (smem > 227 * 1024) {
         set_error("frb_lbp_hist_u8: image %dx%d with grid %dx%d needs %zu B of shared memory (> 227 KB)", rows, cols,
                   grid_x, grid_y, smem);
         return FRB_ERR_UNSUPPORTED;
     }
-    const bool aligned16 = (cols % 2) == 0;
     if (aligned16)
         FRB_CUDA_OK(cudaFuncSetAttribute(lbp_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else
         FRB_CUDA_OK(cudaFuncSetAttribute(lbp_hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // one thread per (band pair, column pair) when that fits a CTA
-    const int items = ((cw * grid_x + 1) / 2) * ((grid_y + 1) / 2);
     int threads = (items + 31) / 32 * 32;
     if (threads < 64) threads = 64;
     if (threads > kLbpMaxThreads) threads = kLbpMaxThreads;
