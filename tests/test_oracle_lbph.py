@@ -36,6 +36,20 @@ def test_compare_identities_used_by_the_kernel():
         ref = (t > c) | (np.abs((t - c).astype(np.float32)) < eps)
         thr = np.float32(1 - 2.0 ** -24) if e == 1 else c
         assert np.array_equal(ref, t >= thr)
+    # the packed kernel forms the threshold as fl(c - 2^-24) and takes bits from the SIGN of a subtraction:
+    # fl(c - 2^-24) is thr(c) for c >= 1 and negative for c = 0 (t >= 0 always), sign(t - thr) set <=> t < thr,
+    # and a product by +0-added FMA equals the rounded product for the non-negative operands involved
+    d24 = np.float32(2.0 ** -24)
+    for e in range(256):
+        c = np.float32(e)
+        thr = (c - d24).astype(np.float32)
+        assert thr == (np.float32(1 - 2.0 ** -24) if e == 1 else c) if e >= 1 else thr < 0
+        nthr = (d24 - c).astype(np.float32)                       # what the kernel holds: -(thr)
+        assert nthr == -thr
+        base = int(c.view(np.uint32))
+        near = np.array([base + d for d in range(-64, 65) if base + d >= 0], np.uint32).view(np.float32)
+        r = (near + nthr).astype(np.float32)
+        assert np.array_equal(np.signbit(r), near < thr)
     w2 = np.uint32(0x248D3132).view(np.float32)
     b, c, e = np.meshgrid(*(np.arange(256, dtype=np.float32),) * 3, indexing="ij")
     t = (b + (w2 * c).astype(np.float32)).astype(np.float32)
