@@ -93,7 +93,7 @@ def call(fn: str, *args) -> None:
     check(fn, getattr(lib, fn)(*args))
 
 
-K_COSINE_TC, K_COSINE_SIMT, K_LBP_HIST, K_CHISQ, K_BGR2GRAY = 0, 1, 2, 3, 4
+K_COSINE_TC, K_COSINE_SIMT, K_LBP_HIST, K_CHISQ, K_BGR2GRAY, K_COSINE_GEMV = 0, 1, 2, 3, 4, 5
 
 
 def profile_enable(on: bool) -> None:

@@ -1,7 +1,8 @@
-// cosine_api.cu — frb_cosine_topk: argument checks, workspace carving, kernel selection by gallery dtype.
+// cosine_api.cu — frb_cosine_topk: argument checks, workspace carving, kernel selection by shape and gallery dtype.
+//   few queries (<= 2 bf16, <= 16 fp32), dim a multiple of 256 <= 512 -> cosine_gemv.cu (HBM-bound row streaming)
 //   FRB_F32  gallery -> cosine_simt.cu (exact fp32 FFMA kernel)
 //   FRB_BF16 gallery -> cosine_tc.cu   (tcgen05 / TMEM / TMA kernel)
-// There is one kernel per dtype; nothing falls back to anything else.
+// One kernel per (shape class, dtype); nothing falls back to anything else.
 #include "frb_common.cuh"
 
 namespace frb {
@@ -14,6 +15,29 @@ size_t cosine_tc_workspace_bytes(int64_t n_query, int64_t n_gallery, int dim, in
 int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16, int64_t ng, int dim, int qnorm_mode,
                      int k, int64_t idx_base, float *out_scores, int64_t *out_idx, void *ws, size_t ws_bytes,
                      cudaStream_t st);
+
+bool gemv_applicable(int64_t n_query, int dim, int gallery_dtype);
+int64_t gemv_ctas(int64_t n_gallery, int64_t *rows_per_cta);
+int launch_cosine_gemv(const void *queries, int64_t nq, const void *gallery, int gallery_dtype, int64_t ng, int dim, const float *q_norms,
+                       const float *g_norms, int score_mode, int k, int64_t idx_base, float *cs, int64_t *ci, int *cnt, int64_t rpc,
+                       int64_t ctas, cudaStream_t st);
+
+struct GemvPlan {
+    int64_t rows_per_cta, ctas;
+    size_t q_bytes, cnt_bytes, idx_bytes, score_bytes;
+};
+
+static GemvPlan gemv_plan(int64_t nq, int64_t ng, int dim, int k)
+{
+    GemvPlan p;
+    p.ctas = gemv_ctas(ng > 0 ? ng : 1, &p.rows_per_cta);
+    const size_t n = (size_t)p.ctas * (size_t)nq * (size_t)k;
+    p.q_bytes = align_up((size_t)nq * dim * sizeof(float), 256);  // fp32 or bf16 copy of the (normalised) queries
+    p.cnt_bytes = align_up((size_t)nq * sizeof(int), 256);
+    p.idx_bytes = align_up(n * sizeof(int64_t), 256);
+    p.score_bytes = align_up(n * sizeof(float), 256);
+    return p;
+}
 
 struct SimtPlan {
     int64_t tiles_per_chunk, chunks;
@@ -39,6 +63,10 @@ extern "C" {
 size_t frb_cosine_topk_workspace_bytes(int64_t n_query, int64_t n_gallery, int dim, int gallery_dtype, int k)
 {
     if (n_query <= 0 || dim <= 0 || k <= 0) return 0;
+    if (gemv_applicable(n_query, dim, gallery_dtype)) {
+        GemvPlan p = gemv_plan(n_query, n_gallery, dim, k);
+        return p.q_bytes + p.cnt_bytes + p.idx_bytes + p.score_bytes;
+    }
     if (gallery_dtype == FRB_BF16) return cosine_tc_workspace_bytes(n_query, n_gallery, dim, k);
     SimtPlan p = simt_plan(n_query, n_gallery, dim, k, true);
     return p.qn_bytes + p.idx_bytes + p.score_bytes;
@@ -72,12 +100,35 @@ int frb_cosine_topk(const float *queries, int64_t n_query, const void *gallery, 
         return FRB_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (gallery_dtype == FRB_BF16 && score_mode != FRB_SCORE_IP) {
+        set_error("frb_cosine_topk: bf16 galleries hold pre-normalised rows; only FRB_SCORE_IP is implemented");
+        return FRB_ERR_UNSUPPORTED;
+    }
+
+    if (gemv_applicable(n_query, dim, gallery_dtype)) {
+        GemvPlan p = gemv_plan(n_query, n_gallery, dim, k);
+        char *ws = (char *)workspace;
+        int *cnt = (int *)(ws + p.q_bytes);
+        int64_t *ci = (int64_t *)(ws + p.q_bytes + p.cnt_bytes);
+        float *cs = (float *)(ws + p.q_bytes + p.cnt_bytes + p.idx_bytes);
+        const void *q_use = queries;
+        if (gallery_dtype == FRB_BF16) {
+            // the same rounding the tcgen05 path applies: normalise in fp32, round to bf16
+            int rc = normalize_rows_impl(queries, n_query, dim, qnorm_mode, ws, FRB_BF16, nullptr, nullptr, st);
+            if (rc != FRB_OK) return rc;
+            q_use = ws;
+        } else if (qnorm_mode != FRB_QNORM_NONE) {
+            int rc = frb_normalize_rows(queries, n_query, dim, qnorm_mode, ws, FRB_F32, stream);
+            if (rc != FRB_OK) return rc;
+            q_use = ws;
+        }
+        int rc = launch_cosine_gemv(q_use, n_query, gallery, gallery_dtype, n_gallery, dim, q_norms, g_norms, score_mode, k, idx_base, cs, ci,
+                                    cnt, p.rows_per_cta, p.ctas, st);
+        if (rc != FRB_OK) return rc;
+        return topk_merge_compact(cs, ci, cnt, p.ctas * k, n_query, k, /*largest=*/1, out_scores, out_idx, st);
+    }
 
     if (gallery_dtype == FRB_BF16) {
-        if (score_mode != FRB_SCORE_IP) {
-            set_error("frb_cosine_topk: bf16 galleries hold pre-normalised rows; only FRB_SCORE_IP is implemented");
-            return FRB_ERR_UNSUPPORTED;
-        }
         return launch_cosine_tc(queries, n_query, gallery, n_gallery, dim, qnorm_mode, k, idx_base, out_scores, out_idx,
                                 workspace, workspace_bytes, st);
     }

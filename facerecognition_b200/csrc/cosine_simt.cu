@@ -142,7 +142,8 @@ int64_t simt_chunks(int64_t n_query, int64_t n_gallery, int64_t *tiles_per_chunk
     const int64_t q_tiles = (n_query + kBQ - 1) / kBQ;
     int64_t n_tiles = (n_gallery + kBN - 1) / kBN;
     if (n_tiles < 1) n_tiles = 1;
-    int64_t want = ((int64_t)sms * 2 + q_tiles - 1) / (q_tiles > 0 ? q_tiles : 1);
+    // ~4 CTAs per SM in total: small galleries (configs[1]: 79 tiles x 4 query tiles) then run one tile per CTA, 2-3 CTAs per SM
+    int64_t want = ((int64_t)sms * 4 + q_tiles - 1) / (q_tiles > 0 ? q_tiles : 1);
     if (want < 1) want = 1;
     if (want > n_tiles) want = n_tiles;
     if (want > 65535) want = 65535;

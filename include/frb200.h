@@ -75,7 +75,8 @@ typedef enum frb_kernel {
     FRB_K_LBP_HIST = 2,    /* lbp_hist_kernel                                       */
     FRB_K_CHISQ = 3,       /* chisq_kernel                                          */
     FRB_K_BGR2GRAY = 4,    /* bgr2gray_kernel                                       */
-    FRB_K_COUNT = 5
+    FRB_K_COSINE_GEMV = 5, /* cosine_gemv_kernel (1..4 queries, HBM-bound row streaming) */
+    FRB_K_COUNT = 6
 } frb_kernel;
 
 /* When enabled, every launch of the four hot kernels is bracketed by a CUDA event pair on the

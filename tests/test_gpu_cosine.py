@@ -42,7 +42,13 @@ def test_golden_reference_outputs_through_engine(cosine_golden):
     batched = eng.recognize_embeddings(g["a_queries"])
     for i, e in enumerate(g["a_queries"]):
         name, score, top = eng.recognize_with_db(e)
-        assert (name, score, top) == batched[i]
+        # one query runs the row-streaming kernel, the batch the tiled one: same answer up to fp32 summation order
+        bname, bscore, btop = batched[i]
+        assert abs(score - bscore) <= 2e-6 and len(top) == len(btop)
+        assert name == bname or abs(score - float(g["a_threshold"])) <= 2e-6
+        np.testing.assert_allclose([t[1] for t in top], [t[1] for t in btop], atol=2e-6, rtol=0)
+        if [t[0] for t in top] != [t[0] for t in btop]:      # names may swap only between scores that close
+            assert all(abs(a[1] - b[1]) <= 2e-6 for a, b in zip(top, btop))
         assert abs(score - g["a_best_scores"][i]) <= TOL_F32
         np.testing.assert_allclose([t[1] for t in top], g["a_top_scores"][i], atol=TOL_F32, rtol=0)
         ref_names = [str(x) for x in g["a_top_names"][i]]
@@ -262,3 +268,44 @@ def test_topk_accuracy_matches_the_notebook_form():
         assert r["top1_accuracy"] == pytest.approx(top1, abs=(0 if not bf16 else 2 / len(labels)))
         assert r["top5_accuracy"] == pytest.approx(top5, abs=(0 if not bf16 else 2 / len(labels)))
         np.testing.assert_allclose(r["similarities"], S.max(1), atol=1e-5 if not bf16 else 1e-3)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("Q", [1, 2, 3, 4])
+def test_small_batches_take_the_row_streaming_kernel_and_agree_with_the_batched_one(Q, dtype):
+    """Few queries go to cosine_gemv_kernel; the same queries inside a 64-query batch go to the tiled kernels.
+    Same operand rounding => same ids (ties included) and scores within fp32 summation-order noise."""
+    from facerecognition_b200 import ops, _native as NV
+    rng = np.random.default_rng(100 + Q)
+    N, k = 30_011, 7
+    gal = unit(rng.standard_normal((N, 512)))
+    gal[20_000] = gal[11]                                               # duplicate rows: lowest id first
+    q = gal[rng.integers(0, N, 64)] + 0.05 * rng.standard_normal((64, 512)).astype(np.float32)
+    q[0] = gal[11]
+    q *= rng.uniform(0.5, 3.0, (64, 1)).astype(np.float32)
+    if dtype == "bf16":
+        g = ops.normalize_rows(dev(gal), NV.FRB_QNORM_NONE, torch.bfloat16)
+        kw = dict(qnorm_mode=NV.FRB_QNORM_CLAMP)
+    else:
+        g = dev(gal)
+        kw = dict(qnorm_mode=NV.FRB_QNORM_EPS)
+    NV.profile_enable(True)
+    NV.profile_read(NV.K_COSINE_GEMV)
+    s1, i1 = ops.cosine_topk(dev(q[:Q]), g, k, idx_base=5, **kw)
+    _, launches = NV.profile_read(NV.K_COSINE_GEMV)
+    NV.profile_enable(False)
+    expect = 1 if (dtype == "f32" or Q <= 2) else 0     # bf16: the tcgen05 path wins from 3 queries up (cosine_gemv.cu)
+    assert launches == expect, "kernel selection by batch size changed"
+    s64, i64 = ops.cosine_topk(dev(q), g, k, idx_base=5, **kw)
+    assert torch.equal(i1, i64[:Q]) and float((s1 - s64[:Q]).abs().max()) <= 2e-6
+    assert [int(x) - 5 for x in i1[0, :2]] == [11, 20_000]
+    if dtype == "f32":                                                   # the reference's cosine rule with explicit norms
+        qn, gn = ops.row_norms(dev(q)), ops.row_norms(g)
+        r1 = ops.cosine_topk(dev(q[:Q]), g, k, score_mode=NV.FRB_SCORE_REF_COSINE, q_norms=qn[:Q].contiguous(), g_norms=gn)
+        r64 = ops.cosine_topk(dev(q), g, k, score_mode=NV.FRB_SCORE_REF_COSINE, q_norms=qn, g_norms=gn)
+        assert torch.equal(r1[1], r64[1][:Q]) and float((r1[0] - r64[0][:Q]).abs().max()) <= 2e-6
+    # fewer rows than k, and an empty gallery
+    s, i = ops.cosine_topk(dev(q[:Q]), g[:3].contiguous(), k, **kw)
+    assert bool((i[:, 3:] == -1).all()) and bool((i[:, :3] >= 0).all())
+    s, i = ops.cosine_topk(dev(q[:Q]), g[:0].contiguous(), k, **kw)
+    assert bool((i == -1).all())
