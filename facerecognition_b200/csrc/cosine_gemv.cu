@@ -19,7 +19,7 @@ namespace frb {
 constexpr int kGvThreads = 256, kGvWarps = kGvThreads / 32;
 constexpr int kGvMaxQ = 4;
 constexpr int kGvMaxPerLane = 16;  // dim <= 512
-constexpr int kGvUnroll = 4;       // rows in flight per warp
+constexpr int kGvUnroll = 4;       // rows in flight per warp (fp32: 8 KB); bf16 rows are half as long and take 8
 
 __device__ __forceinline__ float gv_ref_cosine(float dot, float na, float nb)  // cosine_similarity(), recognition_engine.py:52-63
 {
@@ -69,6 +69,7 @@ cosine_gemv_kernel(const GT *__restrict__ queries, const GT *__restrict__ galler
 {
     constexpr int V = GvGroup<GT>::kVals;
     constexpr int G = kGvMaxPerLane / V;  // 128-bit groups per lane per row at dim = 512
+    constexpr int U = kGvUnroll * V / 4;  // rows in flight per warp: the same 8 KB for either dtype
     extern __shared__ __align__(16) unsigned char gv_smem[];  // [warps][NQ][k] scores, then ids
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -100,17 +101,17 @@ cosine_gemv_kernel(const GT *__restrict__ queries, const GT *__restrict__ galler
 
     const uint4 *gal4 = reinterpret_cast<const uint4 *>(gallery);
     const int64_t vec_per_row = dim / V;
-    for (int64_t r0 = r_begin + warp * kGvUnroll; r0 < r_end; r0 += kGvWarps * kGvUnroll) {
-        uint4 w[kGvUnroll][G];
+    for (int64_t r0 = r_begin + warp * U; r0 < r_end; r0 += kGvWarps * U) {
+        uint4 w[U][G];
 #pragma unroll
-        for (int u = 0; u < kGvUnroll; u++)
+        for (int u = 0; u < U; u++)
 #pragma unroll
             for (int j = 0; j < G; j++) {
                 w[u][j] = make_uint4(0, 0, 0, 0);
                 if (j < groups && r0 + u < r_end) w[u][j] = gv_ld(gal4 + (r0 + u) * vec_per_row + lane + 32 * j);
             }
 #pragma unroll
-        for (int u = 0; u < kGvUnroll; u++) {
+        for (int u = 0; u < U; u++) {
             float acc[NQ];
 #pragma unroll
             for (int q = 0; q < NQ; q++) acc[q] = 0.f;
@@ -205,7 +206,7 @@ int64_t gemv_ctas(int64_t n_gallery, int64_t *rows_per_cta)
 {
     int sms = sm_count();
     if (sms <= 0) sms = 148;
-    const int64_t min_rows = kGvWarps * kGvUnroll;  // one round of every warp
+    const int64_t min_rows = kGvWarps * kGvUnroll * 2;  // one round of every warp (bf16 takes 8 rows per round)
     int64_t want = (int64_t)sms * 4;
     int64_t max_ctas = (n_gallery + min_rows - 1) / min_rows;
     if (max_ctas < 1) max_ctas = 1;
