@@ -206,7 +206,7 @@ def c4(n_total=100_000_000, n_query=4096, steps=5):
         search.search(qs, 5)
         lat[f"ms_q{nq}"], _ = device_ms(lambda: search.search(qs, 5), 3)
     emit({"config": f"configs[3]: {n_total}-embedding bf16 gallery sharded by identity over {WORLD} GPU(s), 4096-query batch, top-5, "
-                    "one NCCL all-gather + merge", "queries_per_s": n_query / (ms * 1e-3), "ms_per_step": ms,
+                    "candidates exchanged once (" + ("fused peer-memory kernel" if getattr(search, "_exchange", None) is not None else "NCCL all-gather") + ") + merge", "queries_per_s": n_query / (ms * 1e-3), "ms_per_step": ms,
           "rows_per_gpu": hi - lo, "shard_gb": (hi - lo) * 1024 / 1e9, "generate_s": t_gen,
           "roofline": {"bound": "tensor", "achieved": ach, "peak": PEAKS["bf16_tflops_sustained"], "unit": "TFLOP/s",
                        "frac": ach / PEAKS["bf16_tflops_sustained"], "frac_of_burst": ach / PEAKS["bf16_tflops"],
