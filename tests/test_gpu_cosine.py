@@ -309,3 +309,37 @@ def test_small_batches_take_the_row_streaming_kernel_and_agree_with_the_batched_
     assert bool((i[:, 3:] == -1).all()) and bool((i[:, :3] >= 0).all())
     s, i = ops.cosine_topk(dev(q[:Q]), g[:0].contiguous(), k, **kw)
     assert bool((i == -1).all())
+
+
+def test_entry_points_are_reentrant_from_python_threads():
+    """The reference's callers are Flask request threads and daemon threads (web_app.py:1028, database_builder.py:114):
+    concurrent calls on one engine / one recognizer must not interfere (per-call workspaces, thread-local error state)."""
+    import threading
+    import facerecognition_b200 as F
+    rng = np.random.default_rng(9)
+    gal = unit(rng.standard_normal((5000, 512)))
+    eng = F.RecognitionEngine(model_path=None, threshold=0.3, use_face_detection=False)
+    eng.db = {f"id_{i:05d}": g for i, g in enumerate(gal)}
+    faces = rng.integers(0, 256, (64, 100, 100), dtype=np.uint8)
+    model = F.train_lbph_model(list(faces), np.arange(64, dtype=np.int32))
+    errors = []
+
+    def worker(t):
+        try:
+            for j in range(25):
+                r = (t * 25 + j) % 5000
+                q = gal[r] + 0.01 * rng.standard_normal(512).astype(np.float32)
+                assert eng.recognize_with_db(q)[0] == f"id_{r:05d}"
+                got = eng.recognize_embeddings(np.stack([gal[r], gal[(r + 1) % 5000]]))
+                assert [g[0] for g in got] == [f"id_{r:05d}", f"id_{(r + 1) % 5000:05d}"]
+                lab, dist = model.predict(faces[(t + j) % 64])
+                assert lab == (t + j) % 64 and dist == 0.0
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors

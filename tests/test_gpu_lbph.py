@@ -245,3 +245,25 @@ def test_bgr2gray_is_bit_exact_with_cv2():
     t = torch.from_numpy(x).cuda()[1:].view(64, 3)
     np.testing.assert_array_equal(ops.bgr_to_gray(t.contiguous()).cpu().numpy(),
                                   cv2.cvtColor(x[1:].reshape(1, 64, 3), cv2.COLOR_BGR2GRAY)[0])
+
+
+@pytest.mark.parametrize("L", [256, 4096, 8960, 16384])
+def test_chisq_other_histogram_lengths_and_large_counts(oracle_lbph, L):
+    """K3 with other grids (hist_len 256 = 1x1, 4096 = 4x4, 8960 = 7x5, 16384 = 8x8): partial and full per-thread
+    coverage, same and different cell sizes, counts up to the u16 limit, tail rows (gallery not a multiple of 12)."""
+    from facerecognition_b200 import ops
+    rng = np.random.default_rng(L)
+    N, Q = 157, 5
+    gal = rng.integers(0, 60_000, (N, L)).astype(np.uint16)
+    gal[rng.random((N, L)) < 0.4] = 0                                   # empty bins on both sides
+    q = gal[rng.integers(0, N, Q)].copy()
+    q[1:] = np.where(rng.random((Q - 1, L)) < 0.1, rng.integers(0, 60_000, (Q - 1, L)), q[1:]).astype(np.uint16)
+    for q_px, g_px in [(30_000, 30_000), (144, 169)]:
+        ref = np.stack([oracle_lbph.c_chisq_scan_u16(gal, g_px, qq, q_px) for qq in q])
+        d = ops.chisq_dist(dev(q), q_px, dev(gal), g_px).cpu().numpy().astype(np.float64)
+        np.testing.assert_allclose(d, ref, rtol=REL, atol=0)
+        dist, idx = ops.chisq_topk(dev(q), q_px, dev(gal), g_px, k=3)
+        order = np.argsort(ref, axis=1, kind="stable")[:, :3]
+        np.testing.assert_allclose(dist.cpu().numpy(), np.take_along_axis(ref, order, 1), rtol=REL)
+        if q_px == g_px:
+            assert float(dist[0, 0]) == 0.0                             # q[0] is a gallery row: exactly zero
