@@ -11,7 +11,7 @@
 //   4. merges the R lists of its queries under the total order (key, then lowest global row).
 // Buffers are double-buffered by epoch parity: a rank can only be one step ahead of a peer (it had to see the
 // peer's flag of the previous step), and the peer's kernel of two steps ago has finished by then.
-// The spin is bounded (~2 s): a rank that never arrives traps the kernel instead of hanging the GPU.
+// The spin is bounded (~10 s): a rank that never arrives traps the kernel instead of hanging the GPU.
 //
 // Replaces: torch.distributed all_gather_into_tensor + frb_topk_merge_strided (facerecognition_b200/sharded.py),
 // which stay as the portable path (gloo tests, hosts without IPC).  There is no reference counterpart: the
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kExThreads) topk_exchange_merge_kernel(const f
         const unsigned *f = flags + ((size_t)parity * ex.world + threadIdx.x) * ex.max_ctas + blockIdx.x;
         const long long t0 = clock64();
         while (ld_acquire_sys(f) != ex.epoch) {
-            if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a rank never arrived
+            if (clock64() - t0 > 20000000000LL) __trap();  // ~10 s: a rank never arrived
         }
     }
     __syncthreads();

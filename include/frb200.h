@@ -156,7 +156,7 @@ int frb_bgr2gray_u8(const uint8_t *bgr_dev, int64_t n_pixels, uint8_t *out_gray_
  * frb_exchange_topk_merge is then ONE kernel per step: each CTA stores its queries' local candidates into every
  * rank's buffer (peer stores), release-stores the step's epoch into the peers' flags, acquire-waits for the same
  * CTA of every rank, and merges (ties -> lowest global id).  All ranks must call it in lockstep (the epoch is a
- * per-context call counter).  A rank that does not arrive within ~2 s traps the kernel.
+ * per-context call counter).  A rank that does not arrive within ~10 s traps the kernel.
  * Replaces the all-gather + frb_topk_merge_strided pair of facerecognition_b200/sharded.py; no reference
  * counterpart (the reference is single-device). */
 #define FRB_EXCHANGE_MAX_WORLD 8
