@@ -12,16 +12,15 @@
 //   * axis bits (n = 0,2,4,6): the weights degenerate to (1, ~6e-17, 0, 0), so bit = neighbour >= centre;
 //   * diagonal bits: for an integer centre c in 0..255, (t > c) || |t - c| < 2^-23  <=>  t >= thr(c) with
 //     thr(1) = 1 - 2^-24 and thr(c) = c otherwise (float spacing at c >= 2 is >= 2^-23).
-// The blend itself uses __fmul_rn / __fadd_rn (and their packed f32x2 forms) in OpenCV's left-to-right order;
-// this file is compiled with --fmad=false because nvcc DOES contract __fmul2_rn + __fadd2_rn into FFMA2
-// otherwise (seen in SASS), which would round once where OpenCV rounds twice.
+// The blend itself keeps OpenCV's left-to-right order with every product and sum rounded separately: scalar
+// __fmul_rn / __fadd_rn in the codes-only kernel; in the histogram kernels packed __fadd2_rn sums and products
+// formed as fma(a, b, +0) — ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (seen in SASS, also with
+// -fmad=false, which this file is compiled with anyway), which would round once where OpenCV rounds twice.
 //
-// Layout.  One CTA per image at a time (persistent, grid-stride).  The image is staged in shared
-// memory; warp w owns cell-row ("band") w: lanes walk down image columns with a rolling 3x3 window
-// (3 new pixels per code), and add into the band's cell histograms with shared-memory atomics.  A band's
-// histograms are touched by its warp only (warp-private), so the only block barriers are around staging
-// and write-out.  Counters are u16 pairs packed in u32 words in the final [cell][bin] order, so the
-// write-out is a straight 128-bit copy of 32 KB per image.
+// Kernels.  lbp_codes_kernel: codes only (parity checks).  lbp_hist_pipe_kernel: the fast path for images the
+// TMA can fetch — double-buffered images and counters, coding warps + one writer warp, mbarrier hand-offs, no
+// block-wide barrier.  lbp_hist_kernel: any other shape — same arithmetic, plain staging, two barriers per
+// image.  See the comment blocks above each for the work decomposition.
 #include "frb_common.cuh"
 
 namespace frb {
@@ -101,7 +100,7 @@ constexpr unsigned kLbpPairVec = 65;  // uint4 groups per cell pair: 256 counter
 #ifndef LBP_MIN_BLOCKS
 #define LBP_MIN_BLOCKS 3
 #endif
-constexpr int kLbpMaxThreads = 224;  // 7 warps: 8x8 grid on 112x112 = 208 work items; 3 CTAs/SM at <= 96 registers
+constexpr int kLbpMaxThreads = 224;  // 7 warps: 8x8 grid on 112x112 = 208 work items
 
 __device__ __forceinline__ uint32_t lbp_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void lbp_mbar_wait(uint64_t *bar, uint32_t parity)
