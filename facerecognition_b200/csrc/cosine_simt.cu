@@ -8,10 +8,11 @@
 // One CTA = (64-query tile, range of 128-row gallery tiles).  Register-tiled SGEMM: 256 threads as 16 x 16, each
 // thread TM x 8 accumulators (TM = 4; a 128-query TM = 8 tile measured no faster), packed FFMA2 with a scalar
 // broadcast operand, BK = 16, shared tiles double-buffered behind a two-slab-deep register prefetch (one barrier
-// per k-step; a whole slab of FMAs hides the global latency).  The score tile goes to shared memory only; thread q
-// then scans its query's 128 scores, applies the reference's score rule (frb_score) and updates a running best-k
-// list that persists across the CTA's gallery tiles.  Per-CTA lists go to the workspace and are merged by
-// topk_merge_kernel.
+// per k-step; a whole slab of FMAs hides the global latency).  The score tile goes to shared memory only; four threads
+// per query apply the reference's score rule (frb_score) in place and pre-filter the tile by its maximum, and the
+// query's owner thread walks the 128 scores only when that maximum beats the list: a running best-k
+// list that persists across the CTA's gallery tiles (four threads per query pre-filter each tile by its maximum).
+// Per-CTA lists go to the workspace and are merged by topk_merge_kernel.
 #include "frb_common.cuh"
 
 namespace frb {
@@ -48,11 +49,11 @@ __device__ __forceinline__ float ref_cosine(float dot, float na, float nb)
     return __fdiv_rn(dot, __fmul_rn(na, nb));
 }
 
-// shared memory (dynamic): As[2][kBK][BQ + 4], Bs[2][kBK][kBN + 4], St[BQ][kBN + 1]
+// shared memory (dynamic): As[2][kBK][BQ + 4], Bs[2][kBK][kBN + 4], St[BQ][kBN + 4]
 template <int TM>
 struct SimtSmem {
     static constexpr int BQ = 16 * TM;
-    static constexpr int kAs = kBK * (BQ + 4), kBs = kBK * (kBN + 4), kSt = BQ * (kBN + 1);
+    static constexpr int kAs = kBK * (BQ + 4), kBs = kBK * (kBN + 4), kSt = BQ * (kBN + 4);
     static constexpr size_t kBytes = (size_t)(2 * kAs + 2 * kBs + kSt) * sizeof(float);
 };
 
@@ -64,7 +65,7 @@ cosine_simt_kernel(const float *__restrict__ queries, int64_t n_query, const GT 
                    int64_t *__restrict__ cand_idx)
 {
     constexpr int BQ = 16 * TM;
-    constexpr int A_LD = BQ + 4, B_LD = kBN + 4, S_LD = kBN + 1;
+    constexpr int A_LD = BQ + 4, B_LD = kBN + 4, S_LD = kBN + 4;  // S_LD = 4 mod 32: the 4-threads-per-query scan is conflict-free
     constexpr int A_PER_THREAD = BQ * kBK / 4 / kSimtThreads;  // float4 loads per thread per k-slab: 1 (TM=4) or 2
     extern __shared__ __align__(16) float simt_smem[];
     float *As = simt_smem;                                  // [2][kBK][A_LD]
@@ -83,14 +84,17 @@ cosine_simt_kernel(const float *__restrict__ queries, int64_t n_query, const GT 
     // loader mapping: 4 threads per row cover 16 consecutive k (one float4 each); 64 rows per pass
     const int lr = tid >> 2, lk = (tid & 3) * 4;
 
+    // score scan: 4 threads per query (sq = query, seg = which interleaved quarter of the tile's 128 scores);
+    // thread seg == 0 owns the query's running best-k list
+    static_assert(BQ * 4 == kSimtThreads, "the scan maps 4 threads to each query of the tile");
+    const int sq = tid >> 2, seg = tid & 3;
+    const bool q_live = q0 + sq < n_query;
     float best_s[FRB_MAX_K];
     int64_t best_i[FRB_MAX_K];
     float kth = -INFINITY;
     float my_qn = 0.f;
-    if (tid < BQ) {
-        list_init<true>(best_s, best_i, k);
-        if (score_mode == FRB_SCORE_REF_COSINE && q0 + tid < n_query) my_qn = q_norms[q0 + tid];
-    }
+    if (seg == 0) list_init<true>(best_s, best_i, k);
+    if (score_mode == FRB_SCORE_REF_COSINE && q_live) my_qn = q_norms[q0 + sq];
 
     for (int64_t tile = tile_begin; tile < tile_end; tile++) {
         const int64_t n0 = tile * kBN;
@@ -171,18 +175,40 @@ cosine_simt_kernel(const float *__restrict__ queries, int64_t n_query, const GT 
             for (int j = 0; j < 8; j++)
                 St[((i >> 2) * 64 + ty * 4 + (i & 3)) * S_LD + (j >> 2) * 64 + tx * 4 + (j & 3)] = (j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x;
         __syncthreads();
-        if (tid < BQ && q0 + tid < n_query) {
+        {
+            // pass 1, all threads: apply the score rule in place and take the maximum of my 32 scores; the 4 threads
+            // of a query combine with two shuffles.  Only when that maximum beats the query's admission threshold
+            // (rare once the list has warmed up) does the owner walk the 128 scores in row order.
             const int lim = (int)((n_gallery - n0) < kBN ? (n_gallery - n0) : kBN);
-            for (int j = 0; j < lim; j++) {
-                float s = St[tid * S_LD + j];
-                if (score_mode == FRB_SCORE_REF_COSINE) s = ref_cosine(s, my_qn, __ldg(g_norms + n0 + j));
-                if (s > kth) kth = list_insert_stream<true>(best_s, best_i, k, s, idx_base + n0 + j);
+            float m = -INFINITY;
+            if (q_live) {
+#pragma unroll 8
+                for (int jj = 0; jj < kBN / 4; jj++) {
+                    const int j = jj * 4 + seg;
+                    if (j < lim) {
+                        float sc = St[sq * S_LD + j];
+                        if (score_mode == FRB_SCORE_REF_COSINE) {
+                            sc = ref_cosine(sc, my_qn, __ldg(g_norms + n0 + j));
+                            St[sq * S_LD + j] = sc;
+                        }
+                        m = fmaxf(m, sc);
+                    }
+                }
+            }
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            __syncwarp();  // the in-place rewrites of the other three threads are visible to the owner
+            if (seg == 0 && q_live && m > kth) {
+                for (int j = 0; j < lim; j++) {
+                    const float sc = St[sq * S_LD + j];
+                    if (sc > kth) kth = list_insert_stream<true>(best_s, best_i, k, sc, idx_base + n0 + j);
+                }
             }
         }
         __syncthreads();  // St and the tile buffers are rewritten by the next tile
     }
-    if (tid < BQ && q0 + tid < n_query) {
-        const int64_t o = (chunk * n_query + q0 + tid) * k;
+    if (seg == 0 && q_live) {
+        const int64_t o = (chunk * n_query + q0 + sq) * k;
         for (int j = 0; j < k; j++) {
             cand_scores[o + j] = best_s[j];
             cand_idx[o + j] = best_i[j];
