@@ -84,3 +84,28 @@ def test_cosine_random_shapes(dtype):
         np.testing.assert_allclose(s[:, :kk], want, atol=tol, rtol=0, err_msg=f"Q={Q} N={N} k={k}")
         picked = np.take_along_axis(ref, np.clip(i[:, :kk], 0, N - 1), 1)
         assert np.all(np.abs(picked - want) <= 2 * tol) and np.all(i[:, kk:] == -1) and np.all(i[:, :kk] >= 0)
+
+
+def test_cosine_other_embedding_widths():
+    """The reference's embeddings are 512-d, but nothing in the ABI fixes that: fp32 takes any multiple of 8, the
+    tensor-core path multiples of 64 up to 512 (anything else is refused, not silently mis-computed)."""
+    from facerecognition_b200 import ops, _native as NV
+    rng = np.random.default_rng(5)
+    for dtype, dims in (("f32", [8, 24, 200, 256, 384, 1024]), ("bf16", [64, 128, 256, 384])):
+        for D in dims:
+            for Q in (1, 3, 40):
+                N, k = 777, 4
+                gal = rng.standard_normal((N, D)).astype(np.float32)
+                gal /= np.linalg.norm(gal, axis=1, keepdims=True)
+                q = gal[rng.integers(0, N, Q)] + 0.05 * rng.standard_normal((Q, D)).astype(np.float32)
+                g = dev(gal) if dtype == "f32" else ops.normalize_rows(dev(gal), NV.FRB_QNORM_NONE, torch.bfloat16)
+                s, i = ops.cosine_topk(dev(q), g, k, qnorm_mode=NV.FRB_QNORM_CLAMP)
+                ref = OC.l2_normalize(q).astype(np.float64) @ gal.T.astype(np.float64)
+                want = -np.sort(-ref, axis=1)[:, :k]
+                # bf16: 1e-3 is the bar at the reference's 512-d; with fewer, larger components the rounding of a
+                # unit vector's entries averages out less (measured 1.2e-3 at 64-d)
+                tol = 1e-5 if dtype == "f32" else (1e-3 if D >= 256 else 3e-3)
+                np.testing.assert_allclose(s.cpu().numpy(), want, atol=tol, rtol=0, err_msg=f"{dtype} D={D} Q={Q}")
+    with pytest.raises(NV.FrbError):                       # 96 is not a multiple of 64: refused by the bf16 path
+        g = torch.zeros((10, 96), dtype=torch.bfloat16, device="cuda")
+        ops.cosine_topk(torch.zeros((40, 96), device="cuda"), g, 1)
