@@ -177,7 +177,16 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is one process that should use the whole host
+    cores = os.cpu_count() or 1
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(cores)
     import numpy as np
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
     rng = np.random.default_rng(1234)
     sample_q = 64
     gal = rng.standard_normal((N_GALLERY, DIM), dtype=np.float32)
@@ -190,7 +199,6 @@ def run_reference(args):
         s, i = cpu_topk_port(q, gal, TOPK)
     dt = time.perf_counter() - t0
     val = sample_q * args.steps / dt
-    cores = os.cpu_count()
     cfg = workload_config(world, N_GALLERY, N_QUERY * world)
     cfg["cpu_step"] = f"{sample_q}-query sample of the batch against the full 1M fp32 gallery"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "queries/s",
