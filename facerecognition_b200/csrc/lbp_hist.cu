@@ -97,9 +97,6 @@ __global__ void __launch_bounds__(256) lbp_codes_kernel(const uint8_t *__restric
 //     (0, 255, ...) of neighbouring cells fall into banks 4 apart; the write-out splits the halves and stores
 //     128 bits per cell.
 constexpr unsigned kLbpPairVec = 65;  // uint4 groups per cell pair: 256 counters + 16 bytes of bank skew
-#ifndef LBP_MIN_BLOCKS
-#define LBP_MIN_BLOCKS 3
-#endif
 constexpr int kLbpMaxThreads = 224;  // 7 warps: 8x8 grid on 112x112 = 208 work items
 
 __device__ __forceinline__ uint32_t lbp_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -226,7 +223,7 @@ __device__ __forceinline__ void lbp_emit_row2(const LbpRow2 &top, const LbpRow2 
 }
 
 template <bool ALIGNED16>
-__global__ void __launch_bounds__(kLbpMaxThreads, LBP_MIN_BLOCKS) lbp_hist_kernel(const uint8_t *__restrict__ img, int64_t count, int rows,
+__global__ void __launch_bounds__(kLbpMaxThreads, 3) lbp_hist_kernel(const uint8_t *__restrict__ img, int64_t count, int rows,
                                                                      int cols, int grid_x, int grid_y, int img_smem_bytes,
                                                                      uint16_t *__restrict__ out)
 {
