@@ -136,26 +136,28 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr)
 constexpr uint32_t kTcIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcBlockN >> 3) << 17) | ((uint32_t)(kTcBlockM >> 4) << 24);
 
 
-// ---- register-resident best-k list for k <= kTcRegK (the common top-1 / top-5 case) ---------------
-// s[] stays sorted descending over all kTcRegK slots; an element is admitted when it beats s[k-1]
+// ---- register-resident best-k list, RK = 8 / 16 / 32 / 64 slots (k <= RK; 8 covers the common top-1 / top-5) ---
+// s[] stays sorted descending over all RK slots; an element is admitted when it beats s[k-1]
 // (strictly, so an equal score with a later row stays behind), dropped into the last slot and bubbled
 // up with predicated swaps: no local memory, ~6 instructions per slot, executed only on admissions.
-constexpr int kTcRegK = 8;
+constexpr int kTcMaxRegK = 64;  // == FRB_MAX_K: every list fits the register file (the local-memory list, RK = 0, is kept as the generic form)
 
-__device__ __forceinline__ float reg_kth(const float (&s)[kTcRegK], int k)
+template <int RK>
+__device__ __forceinline__ float reg_kth(const float (&s)[RK], int k)
 {
     float r = s[0];
 #pragma unroll
-    for (int j = 1; j < kTcRegK; j++) r = (k == j + 1) ? s[j] : r;
+    for (int j = 1; j < RK; j++) r = (k == j + 1) ? s[j] : r;
     return r;
 }
 
-__device__ __forceinline__ void reg_insert(float (&s)[kTcRegK], int (&id)[kTcRegK], float v, int idx)
+template <int RK>
+__device__ __forceinline__ void reg_insert(float (&s)[RK], int (&id)[RK], float v, int idx)
 {
-    s[kTcRegK - 1] = v;
-    id[kTcRegK - 1] = idx;
+    s[RK - 1] = v;
+    id[RK - 1] = idx;
 #pragma unroll
-    for (int j = kTcRegK - 1; j > 0; --j) {
+    for (int j = RK - 1; j > 0; --j) {
         const bool sw = s[j] > s[j - 1];
         const float ts = s[j - 1];
         const int ti = id[j - 1];
@@ -235,7 +237,8 @@ struct TcParams {
     int64_t *cand_idx;
 };
 
-template <bool REG_LIST>
+// RK: slots of the register-resident list (8, 16, 32, 64), or 0 for the local-memory list
+template <int RK>
 __global__ void __launch_bounds__(kTcThreads, 1)
 cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
                  const __grid_constant__ CUtensorMap tmap_pf, const TcParams p)
@@ -354,10 +357,12 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const int row = ew * 32 + lane;                // query row inside the tile == TMEM lane
         int acc = 0;
         uint32_t acc_phase = 0;
-        // REG_LIST: k <= 8, list in registers with 32-bit row offsets relative to the unit's first row;
+        // REG_LIST: k <= RK, list in registers with 32-bit row offsets relative to the unit's first row;
         // otherwise a local-memory list (k up to FRB_MAX_K), touched only on admissions.
-        float rs[kTcRegK];
-        int ri[kTcRegK];
+        constexpr bool REG_LIST = RK > 0;
+        constexpr int RS = REG_LIST ? RK : 1;
+        float rs[RS];
+        int ri[RS];
         float best_s[REG_LIST ? 1 : FRB_MAX_K];
         int64_t best_i[REG_LIST ? 1 : FRB_MAX_K];
         for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -367,7 +372,7 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const int64_t unit_n0 = t0 * kTcBlockN;
             if (REG_LIST) {
 #pragma unroll
-                for (int j = 0; j < kTcRegK; j++) { rs[j] = -INFINITY; ri[j] = -1; }
+                for (int j = 0; j < RS; j++) { rs[j] = -INFINITY; ri[j] = -1; }
             } else {
                 list_init<true>(best_s, best_i, p.k);
             }
@@ -404,8 +409,8 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             const float x = select32(v, j);
                             if (x > adm) {
                                 if (REG_LIST) {
-                                    reg_insert(rs, ri, x, col0 + c0 + j);
-                                    kth = reg_kth(rs, p.k);
+                                    reg_insert<RS>(rs, ri, x, col0 + c0 + j);
+                                    kth = reg_kth<RS>(rs, p.k);
                                 } else {
                                     kth = list_insert_stream<true>(best_s, best_i, p.k, x, p.idx_base + n0 + c0 + j);
                                 }
@@ -434,7 +439,7 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 int nv = 0;
                 if (REG_LIST) {
 #pragma unroll
-                    for (int j = 0; j < kTcRegK; j++) nv += (j < p.k && ri[j] >= 0) ? 1 : 0;
+                    for (int j = 0; j < RS; j++) nv += (j < p.k && ri[j] >= 0) ? 1 : 0;
                 } else {
                     for (int j = 0; j < p.k; j++) nv += best_i[j] >= 0 ? 1 : 0;
                 }
@@ -442,7 +447,7 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     const int64_t o = q * p.cand_cap + atomicAdd(p.cand_cnt + q, nv);
                     if (REG_LIST) {
 #pragma unroll
-                        for (int j = 0; j < kTcRegK; j++)
+                        for (int j = 0; j < RS; j++)
                             if (j < nv) {
                                 p.cand_scores[o + j] = rs[j];
                                 p.cand_idx[o + j] = p.idx_base + unit_n0 + ri[j];
@@ -637,19 +642,18 @@ int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16,
     p.cand_scores = cs;
     p.cand_idx = ci;
     const size_t smem = 1024 + a_bytes + (size_t)stages * kTcBBytesPerStage + sizeof(TcBarriers);
-    const bool reg_list = k <= kTcRegK;
+    const int variant = k <= 8 ? 0 : (k <= 16 ? 1 : (k <= 32 ? 2 : (k <= kTcMaxRegK ? 3 : 4)));  // register list of 8 / 16 / 32 / 64 slots, else local memory
+    typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
+    const TcKernel kernels[5] = {cosine_tc_kernel<8>, cosine_tc_kernel<16>, cosine_tc_kernel<32>, cosine_tc_kernel<64>, cosine_tc_kernel<0>};
+    const TcKernel kernel = kernels[variant];
     {
         // opt in to >48 KB dynamic shared memory once per (device, kernel variant, size)
-        static thread_local int attr_dev[2] = {-1, -1};
-        static thread_local size_t attr_smem[2] = {0, 0};
-        const int v = reg_list ? 1 : 0;
-        if (attr_dev[v] != dev || attr_smem[v] < smem) {
-            if (reg_list)
-                FRB_CUDA_OK(cudaFuncSetAttribute(cosine_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            else
-                FRB_CUDA_OK(cudaFuncSetAttribute(cosine_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_dev[v] = dev;
-            attr_smem[v] = smem;
+        static thread_local int attr_dev[5] = {-1, -1, -1, -1, -1};
+        static thread_local size_t attr_smem[5] = {0, 0, 0, 0, 0};
+        if (attr_dev[variant] != dev || attr_smem[variant] < smem) {
+            FRB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_dev[variant] = dev;
+            attr_smem[variant] = smem;
         }
     }
     const int sms = sm_count();
@@ -664,10 +668,7 @@ int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16,
         const int64_t n_units = pl.n_qtiles * ps.n_groups;
         const int grid = (int)(n_units < sms ? n_units : sms);
         ProfileScope prof(FRB_K_COSINE_TC, st);
-        if (reg_list)
-            cosine_tc_kernel<true><<<grid, kTcThreads, smem, st>>>(tq, tg, tpf, p);
-        else
-            cosine_tc_kernel<false><<<grid, kTcThreads, smem, st>>>(tq, tg, tpf, p);
+        kernel<<<grid, kTcThreads, smem, st>>>(tq, tg, tpf, p);
         FRB_LAUNCH_OK("cosine_tc_kernel");
     }
     return topk_merge_compact(cs, ci, cnt, p.cand_cap, nq, k, /*largest=*/1, out_scores, out_idx, st);

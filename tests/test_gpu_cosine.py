@@ -136,7 +136,7 @@ def bf16_round(x):
 
 
 @pytest.mark.parametrize("Q,N,k", [(1, 1, 1), (5, 255, 5), (128, 256, 5), (129, 257, 5), (300, 5000, 5), (64, 70000, 1),
-                                   (1000, 33333, 16)])
+                                   (1000, 33333, 16), (200, 20000, 9), (150, 9000, 33), (140, 30000, 64)])
 def test_bf16_tensor_core_kernel_vs_oracle(Q, N, k):
     from facerecognition_b200 import ops, _native as NV
     rng = np.random.default_rng(Q + N)
