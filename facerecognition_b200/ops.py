@@ -87,6 +87,45 @@ def cosine_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, *, score_m
     return scores, idx
 
 
+# >= |exact score - bf16 first-pass score| for ANY pair: bf16 keeps 8 significant bits (unit roundoff 2^-8), so rounding
+# two unit vectors moves their inner product by at most 2 * 2^-8 + 2^-16 = 0.00783 (Cauchy-Schwarz), and
+# cosine_similarity()'s raw-dot branch (both norms within 1e-3 of 1) differs from the true cosine by at most 0.002
+REFINE_EPS = 0.0105
+# measured (profiles/run_refine.py): 4096 q x 1M rows 12.7 ms vs 131.7 ms for the fp32 tiled kernel, but 256 q x 1M
+# 17.9 ms vs 8.0 ms (a 64-slot list has to warm up in every (query tile, gallery group) unit): large batches only
+REFINE_MIN_QUERIES = 1024
+REFINE_MIN_ROWS = 65536
+
+
+def refine_list_length(k: int) -> int:
+    """Candidates fetched by the first pass for a final top-k (0: k too large for a provable margin)."""
+    return N.FRB_MAX_K if k <= 16 else 0   # the longest list the kernels keep: the widest provable margin
+
+
+def cosine_topk_refined(queries: torch.Tensor, gallery: torch.Tensor, gallery_bf16_unit: torch.Tensor, k: int, *,
+                        score_mode: int = N.FRB_SCORE_REF_COSINE, q_norms: Optional[torch.Tensor] = None,
+                        g_norms: Optional[torch.Tensor] = None, idx_base: int = 0
+                        ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Exact fp32 top-k through the tensor cores, for the reference's cosine rule (FRB_SCORE_REF_COSINE; or inner
+    products of unit-norm queries against unit-norm gallery rows, which rank like the cosine): bf16 first pass
+    (frb_cosine_topk on `gallery_bf16_unit`, the unit-norm bf16 copy of `gallery`) -> frb_cosine_rescore_topk.
+    Returns (scores, idx, fail_count int32 [1]); when fail_count != 0 some list could not be proven complete and the
+    caller must use `cosine_topk` on the fp32 gallery."""
+    dev = _require_cuda(queries, gallery, gallery_bf16_unit, q_norms, g_norms)
+    kp = refine_list_length(k)
+    assert kp > 0 and gallery.dtype == torch.float32 and gallery_bf16_unit.dtype == torch.bfloat16
+    assert gallery.shape == gallery_bf16_unit.shape
+    q, d, n = queries.shape[0], queries.shape[1], gallery.shape[0]
+    approx, cand = cosine_topk(queries, gallery_bf16_unit, kp, qnorm_mode=N.FRB_QNORM_CLAMP)
+    scores = torch.empty((q, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((q, k), dtype=torch.int64, device=dev)
+    fail = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        N.call("frb_cosine_rescore_topk", _p(queries), _I64(q), _p(gallery), _I64(n), d, _p(q_norms), _p(g_norms), score_mode,
+               _p(cand), _p(approx), kp, k, ctypes.c_float(REFINE_EPS), _I64(idx_base), _p(scores), _p(idx), _p(fail), _stream(dev))
+    return scores, idx, fail
+
+
 def topk_merge(cand_scores: torch.Tensor, cand_idx: torch.Tensor, largest: bool) -> Tuple[torch.Tensor, torch.Tensor]:
     """frb_topk_merge: [R, Q, k] candidate lists -> best [Q, k] (ties -> lowest idx; idx < 0 is padding)."""
     dev = _require_cuda(cand_scores, cand_idx)

@@ -102,6 +102,13 @@ class DeviceGallery:
         self.rows = _to_dev(mat, device)
         self.norms = ops.row_norms(self.rows) if len(self.names) else torch.zeros(0, device=device)
         self._unit_rows = None
+        self._unit_bf16 = None
+
+    def unit_rows_bf16(self) -> torch.Tensor:
+        """Unit-norm bf16 copy of the rows: the tensor-core first pass of ops.cosine_topk_refined."""
+        if self._unit_bf16 is None:
+            self._unit_bf16 = ops.normalize_rows(self.rows, N.FRB_QNORM_CLAMP, torch.bfloat16)
+        return self._unit_bf16
 
     def unit_rows(self) -> torch.Tensor:
         """rows / (||row|| + 1e-8) — web_app.py:549 normalises every db row this way."""
@@ -295,7 +302,17 @@ class RecognitionEngine:
         """(scores [Q, k], rows [Q, k]) on the host for Q query embeddings under the reference's cosine rule."""
         g = self.gallery()
         q = _to_dev(np.asarray(emb).astype(np.float32).reshape(-1, g.dim), self.match_device)
-        s, i = ops.cosine_topk(q, g.rows, k, score_mode=N.FRB_SCORE_REF_COSINE, q_norms=ops.row_norms(q), g_norms=g.norms)
+        qn = ops.row_norms(q)
+        if (q.shape[0] >= ops.REFINE_MIN_QUERIES and len(g.names) >= ops.REFINE_MIN_ROWS and ops.refine_list_length(k)
+                and g.dim % 64 == 0 and g.dim <= 512):
+            # large batches against large galleries: bf16 tensor-core first pass + exact fp32 re-score of 64 candidates
+            # per query, each list proven complete; any query without a provable margin sends the batch to the exact kernel
+            s, i, fail = ops.cosine_topk_refined(q, g.rows, g.unit_rows_bf16(), k, score_mode=N.FRB_SCORE_REF_COSINE,
+                                                 q_norms=qn, g_norms=g.norms)
+            s, i, fail = s.cpu().numpy(), i.cpu().numpy(), int(fail.cpu().item())
+            if fail == 0:
+                return s, i, g.names
+        s, i = ops.cosine_topk(q, g.rows, k, score_mode=N.FRB_SCORE_REF_COSINE, q_norms=qn, g_norms=g.norms)
         return s.cpu().numpy(), i.cpu().numpy(), g.names
 
     def _format_db_result(self, scores, rows, names):

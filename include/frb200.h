@@ -117,6 +117,21 @@ int frb_cosine_topk(const float *queries_dev, int64_t n_query, const void *galle
                     int score_mode, int qnorm_mode, int k, int64_t idx_base, float *out_scores_dev,
                     int64_t *out_idx_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* Exact fp32 top-k from a tensor-core first pass.  cand_idx / cand_approx [n_query, kp] are the (local row, score) lists
+ * frb_cosine_topk returned for a unit-norm bf16 copy of the gallery with kp > k.  Each listed row is re-scored in fp32
+ * under score_mode (queries as that rule takes them: normalised rows for FRB_SCORE_IP, raw rows + norms for
+ * FRB_SCORE_REF_COSINE), the best k are written (ties -> lowest row, ids + idx_base), and *fail_count_dev is
+ * incremented for every query whose list could not be PROVEN complete: min first-pass score + eps must be below the
+ * k-th exact score, eps >= the worst |exact - first pass| (0.0105 covers two bf16 roundings of unit vectors,
+ * 2 * 2^-8, and cosine_similarity()'s raw-dot branch, 0.002).  A caller that reads a non-zero count reruns
+ * frb_cosine_topk on the fp32 gallery.  Same result as recognize_with_db / np.dot + argsort
+ * (inference/recognition_engine.py:277-289, notebooks/evaluate_arcface_kaggle.ipynb:618,713), reached through tcgen05. */
+int frb_cosine_rescore_topk(const float *queries_dev, int64_t n_query, const float *gallery_f32_dev, int64_t n_gallery,
+                            int dim, const float *q_norms_dev, const float *g_norms_dev, int score_mode,
+                            const int64_t *cand_idx_dev, const float *cand_approx_dev, int kp, int k, float eps,
+                            int64_t idx_base, float *out_scores_dev, int64_t *out_idx_dev, int *fail_count_dev,
+                            void *stream);
+
 /* Gallery builder (K4): out[g] = mean(emb[order[offsets[g] .. offsets[g+1])]) / (||mean|| + 1e-8), float32 sums in
  * the given order then a division by the count (numpy's mean(axis=0)); groups with no rows come out all-zero.
  * emb f32 [M, dim]; order i64 [M] = sample indices grouped by identity; offsets i64 [n_groups + 1].

@@ -343,3 +343,53 @@ def test_entry_points_are_reentrant_from_python_threads():
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("N,Q,k", [(10_000, 256, 5), (3000, 40, 1), (70_000, 333, 16)])
+def test_tensor_core_first_pass_plus_exact_rescore_equals_the_exact_kernel(N, Q, k):
+    """ops.cosine_topk_refined (bf16 tcgen05 first pass, 64 candidates, exact fp32 re-score, completeness proof) must
+    return exactly what the fp32 kernel returns whenever it reports fail_count == 0; (10000, 256, 5) is configs[1]."""
+    from facerecognition_b200 import ops, _native as NV
+    rng = np.random.default_rng(N + Q)
+    gal = unit(rng.standard_normal((N, 512)))
+    gal[5] *= 1.0004                                     # cosine_similarity()'s raw-dot window
+    gal[6] *= 1.7                                        # division branch
+    gal[N - 1] = gal[7]                                  # duplicate rows: lowest id first
+    q = gal[rng.integers(0, N, Q)] + 0.03 * rng.standard_normal((Q, 512)).astype(np.float32)
+    q[0] = gal[7]
+    q[1] *= 2.5
+    g = dev(gal)
+    g16 = ops.normalize_rows(g, NV.FRB_QNORM_CLAMP, torch.bfloat16)
+    qn, gn = ops.row_norms(dev(q)), ops.row_norms(g)
+    want_s, want_i = ops.cosine_topk(dev(q), g, k, score_mode=NV.FRB_SCORE_REF_COSINE, q_norms=qn, g_norms=gn)
+    s, i, fail = ops.cosine_topk_refined(dev(q), g, g16, k, score_mode=NV.FRB_SCORE_REF_COSINE, q_norms=qn, g_norms=gn)
+    assert int(fail.item()) == 0, "planted queries over a random gallery leave a wide margin"
+    assert float((s - want_s).abs().max()) <= 2e-6
+    mism = (i != want_i)
+    assert bool((((s - want_s).abs() <= 2e-6) | ~mism).all())          # ids may differ only between scores that close
+    assert int(i[0, 0]) == 7 and (k == 1 or int(i[0, 1]) == N - 1)
+    # a query with no margin (all scores zero) must be reported, not silently answered
+    z = torch.zeros((17, 512), device="cuda")
+    _, _, fail = ops.cosine_topk_refined(z, g, g16, k, score_mode=NV.FRB_SCORE_REF_COSINE, q_norms=ops.row_norms(z), g_norms=gn)
+    assert int(fail.item()) == 17
+
+
+def test_engine_batches_on_a_large_gallery_use_the_first_pass_and_agree_with_single_queries():
+    """RecognitionEngine.recognize_embeddings with >= 1024 queries over a 70k-identity dict DB takes the tensor-core
+    first pass + exact re-score; each answer must equal the single-query (row-streaming, exact) answer."""
+    import facerecognition_b200 as F
+    from facerecognition_b200 import ops
+    rng = np.random.default_rng(1)
+    n, nq = 70_000, 1100
+    assert nq >= ops.REFINE_MIN_QUERIES and n >= ops.REFINE_MIN_ROWS
+    gal = unit(rng.standard_normal((n, 512)))
+    eng = F.RecognitionEngine(model_path=None, threshold=0.4, use_face_detection=False)
+    eng.db = {f"id_{i:06d}": g for i, g in enumerate(gal)}
+    src = rng.integers(0, n, nq)
+    q = gal[src] + 0.03 * rng.standard_normal((nq, 512)).astype(np.float32)
+    batched = eng.recognize_embeddings(q)
+    assert all(b[0] == f"id_{s:06d}" for b, s in zip(batched, src))
+    for j in (0, 7, nq - 1):
+        name, score, top = eng.recognize_with_db(q[j])
+        assert batched[j][0] == name == f"id_{src[j]:06d}" and abs(batched[j][1] - score) <= 2e-6
+        assert [t[0] for t in batched[j][2]] == [t[0] for t in top]
