@@ -560,8 +560,15 @@ static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
     } else {
         pl.warm = TcPass{0, 0, 1, 0, 0};
     }
-    // main: ~16 units per CTA for balance; a unit's gallery group is shared (through L2) by all query tiles
-    int64_t want_groups = ((int64_t)sms * 16 + pl.n_qtiles - 1) / pl.n_qtiles;
+    // main: a unit's gallery group is shared (through L2) by all query tiles.  Up to 16 units per CTA for balance, but a
+    // unit should span ~16 gallery tiles or more: every unit reloads its 128 KB query tile and refills the MMA /
+    // TMEM pipeline, which dominated small batches when units were 2 tiles long (256 queries x 1M rows).
+    const int64_t main_tiles = pl.n_tiles - warm_tiles;
+    const int64_t tiles_per_cta = (main_tiles * pl.n_qtiles + sms - 1) / sms;
+    int64_t units_per_cta = (tiles_per_cta + 8) / 16;
+    if (units_per_cta < 1) units_per_cta = 1;
+    if (units_per_cta > 16) units_per_cta = 16;
+    int64_t want_groups = ((int64_t)sms * units_per_cta + pl.n_qtiles - 1) / pl.n_qtiles;
     if (want_groups > 1024) want_groups = 1024;
     tc_split(warm_tiles, pl.n_tiles, want_groups, pl.warm.n_groups, &pl.main);
     pl.n_groups = pl.warm.n_groups + pl.main.n_groups;
