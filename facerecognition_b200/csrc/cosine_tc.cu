@@ -37,7 +37,12 @@ constexpr int kTcMaxKBlocks = 8;  // dim <= 512
 constexpr uint32_t kTcABytesPerKb = kTcBlockM * kTcBlockK * 2;  // 16 KB
 constexpr uint32_t kTcBBytesPerStage = kTcBlockN * kTcBlockK * 2;  // 32 KB
 constexpr int kTcMaxStages = 8;
-constexpr int kTcPrefetchDist = 6;  // gallery tiles (256 rows = 256 KB) kept ahead of the TMA loads in L2
+constexpr int kTcPrefetchDist = 6;  // gallery tiles (256 rows = 256 KB) kept ahead of the TMA loads in L2, at most
+// L2 the prefetched tiles of all concurrently walked gallery groups may occupy.  With few query tiles per group the
+// grid walks many groups at once (148 of them for <= 128 queries): 6 tiles ahead in each is 227 MB, which evicts lines
+// before their demand load arrives -- measured 1.78x the gallery in DRAM reads and 3.9 TB/s instead of 6.1 TB/s
+// (profiles/r1_tc_prefetch_sweep.txt).  The distance shrinks to fit this budget; 0 turns the prefetch off.
+constexpr size_t kTcPrefetchL2Budget = 8u << 20;
 constexpr size_t kTcSmemLimit = 227 * 1024;
 
 struct TcBarriers {
@@ -640,8 +645,7 @@ int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16,
     p.stages = stages;
     p.n_qtiles = pl.n_qtiles;
     p.k = k;
-    p.prefetch_dist = kTcPrefetchDist;
-    if (const char *e = getenv("FRB_TC_PREFETCH_DIST")) p.prefetch_dist = atoi(e);  // tuning knob for experiments
+    const char *pf_env = getenv("FRB_TC_PREFETCH_DIST");  // tuning knob for experiments
     p.idx_base = idx_base;
     p.thr = thr;
     p.cand_cnt = cnt;
@@ -674,6 +678,12 @@ int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16,
         p.tile_end = ng > 0 ? ps.tile_end : ps.tile_begin;  // empty gallery: units run with no tiles and emit empty lists
         const int64_t n_units = pl.n_qtiles * ps.n_groups;
         const int grid = (int)(n_units < sms ? n_units : sms);
+        {
+            const size_t tile_bytes = (size_t)kTcBlockN * (size_t)p.k_blocks * kTcBlockK * 2;
+            const size_t groups_in_flight = (size_t)((grid + pl.n_qtiles - 1) / pl.n_qtiles);
+            const size_t fit = kTcPrefetchL2Budget / (groups_in_flight * tile_bytes);
+            p.prefetch_dist = pf_env ? atoi(pf_env) : (int)(fit < (size_t)kTcPrefetchDist ? fit : (size_t)kTcPrefetchDist);
+        }
         ProfileScope prof(FRB_K_COSINE_TC, st);
         kernel<<<grid, kTcThreads, smem, st>>>(tq, tg, tpf, p);
         FRB_LAUNCH_OK("cosine_tc_kernel");
