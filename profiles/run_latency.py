@@ -20,4 +20,16 @@ for name, gal, bytes_per_row in (("bf16", gal16, 1024), ("fp32", gal32, 2048)):
             b.record()
         torch.cuda.synchronize()
         ms = sorted(a.elapsed_time(b) for a, b in ev)[len(ev) // 2]
-        print(f"{name} gallery {n} rows, {nq} queries: {ms:.3f} ms  ({n * bytes_per_row / ms / 1e6:.0f} GB/s of gallery)  top1 ok={bool((i[:, 0] == torch.arange(nq, device='cuda')).all())}")
+        # the same step recorded into a CUDA graph (every entry point only enqueues on the caller's stream)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            gs, gi = ops.cosine_topk(q, gal, 5, qnorm_mode=NV.FRB_QNORM_CLAMP)
+        for a, b in ev:
+            flush.zero_()
+            a.record()
+            graph.replay()
+            b.record()
+        torch.cuda.synchronize()
+        gms = sorted(a.elapsed_time(b) for a, b in ev)[len(ev) // 2]
+        assert torch.equal(gi, i) and torch.equal(gs, s)
+        print(f"{name} gallery {n} rows, {nq} queries: {ms:.3f} ms  ({n * bytes_per_row / ms / 1e6:.0f} GB/s of gallery)  as a graph: {gms:.3f} ms ({n * bytes_per_row / gms / 1e6:.0f} GB/s)  top1 ok={bool((i[:, 0] == torch.arange(nq, device='cuda')).all())}")
