@@ -270,34 +270,49 @@ int normalize_rows_impl(const float *x, int64_t rows, int dim, int mode, void *o
 }
 
 // Compact candidate merge: query q owns cnt[q] unordered (score, row) candidates at cand[q * cap ...].
-// One warp per query: lanes take candidates round-robin into private sorted lists, then k rounds of a
-// warp-wide arg-best over the lane heads.  Total order (key, then lowest row) => order-independent result.
+// Lanes take candidates round-robin into private sorted lists (loads issued four at a time so their latencies
+// overlap), then k rounds of a warp-wide arg-best over the lane heads.  Total order (key, then lowest row) =>
+// order-independent result.  WQ = 1: one warp per query, 8 queries per CTA (large batches).  WQ = 8: one CTA per
+// query, each warp reduces an eighth of the candidates into shared memory and warp 0 merges the eight lists --
+// for a handful of queries with thousands of candidates each (the row-streaming kernel leaves k per CTA: 2895 for
+// one query, which took one warp 119 us of dependent L2 round trips).
 template <bool LARGEST>
-__global__ void __launch_bounds__(256) topk_merge_compact_kernel(const float *__restrict__ cs, const int64_t *__restrict__ ci,
-                                                                 const int *__restrict__ cnt, int64_t cap, int64_t n_query,
-                                                                 int k, float *__restrict__ os, int64_t *__restrict__ oi)
+__device__ __forceinline__ void merge_insert(float *s, int64_t *id, int k, float v, int64_t idx)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (q >= n_query) return;
-    int64_t n = cnt[q];
-    if (n > cap) n = cap;
-    float s[FRB_MAX_K];
-    int64_t id[FRB_MAX_K];
-    list_init<LARGEST>(s, id, k);
-    for (int64_t i = lane; i < n; i += 32) {
-        const float v = cs[q * cap + i];
-        const int64_t idx = ci[q * cap + i];
-        if (idx < 0 || !better<LARGEST>(v, idx, s[k - 1], id[k - 1])) continue;
-        int p = k - 1;
-        while (p > 0 && better<LARGEST>(v, idx, s[p - 1], id[p - 1])) {
-            s[p] = s[p - 1];
-            id[p] = id[p - 1];
-            --p;
-        }
-        s[p] = v;
-        id[p] = idx;
+    if (idx < 0 || !better<LARGEST>(v, idx, s[k - 1], id[k - 1])) return;
+    int p = k - 1;
+    while (p > 0 && better<LARGEST>(v, idx, s[p - 1], id[p - 1])) {
+        s[p] = s[p - 1];
+        id[p] = id[p - 1];
+        --p;
     }
+    s[p] = v;
+    id[p] = idx;
+}
+
+template <bool LARGEST>
+__device__ __forceinline__ void merge_scan(float *s, int64_t *id, int k, const float *cs, const int64_t *ci, int64_t first,
+                                           int64_t n, int64_t step)
+{
+    int64_t i = first;
+    for (; i + 3 * step < n; i += 4 * step) {
+        float v[4];
+        int64_t x[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            v[u] = cs[i + u * step];
+            x[u] = ci[i + u * step];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) merge_insert<LARGEST>(s, id, k, v[u], x[u]);
+    }
+    for (; i < n; i += step) merge_insert<LARGEST>(s, id, k, cs[i], ci[i]);
+}
+
+// k rounds of warp arg-best over the lanes' sorted lists; lane 0 stores round r through (os, oi)
+template <bool LARGEST>
+__device__ __forceinline__ void merge_extract(const float *s, const int64_t *id, int k, int lane, float *os, int64_t *oi)
+{
     int head = 0;
     for (int r = 0; r < k; r++) {
         float v = head < k ? s[head] : worst_value<LARGEST>();
@@ -311,8 +326,38 @@ __global__ void __launch_bounds__(256) topk_merge_compact_kernel(const float *__
         }
         if (idx >= 0 && mine == idx) head++;
         if (lane == 0) {
-            os[q * k + r] = idx >= 0 ? v : worst_value<LARGEST>();
-            oi[q * k + r] = idx;
+            os[r] = idx >= 0 ? v : worst_value<LARGEST>();
+            oi[r] = idx;
+        }
+    }
+}
+
+template <bool LARGEST, int WQ>
+__global__ void __launch_bounds__(256) topk_merge_compact_kernel(const float *__restrict__ cs, const int64_t *__restrict__ ci,
+                                                                 const int *__restrict__ cnt, int64_t cap, int64_t n_query,
+                                                                 int k, float *__restrict__ os, int64_t *__restrict__ oi)
+{
+    __shared__ float sh_s[WQ > 1 ? WQ * FRB_MAX_K : 1];
+    __shared__ int64_t sh_i[WQ > 1 ? WQ * FRB_MAX_K : 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t q = WQ > 1 ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (q >= n_query) return;   // WQ > 1: uniform over the CTA
+    int64_t n = cnt[q];
+    if (n > cap) n = cap;
+    float s[FRB_MAX_K];
+    int64_t id[FRB_MAX_K];
+    list_init<LARGEST>(s, id, k);
+    if (WQ == 1) {
+        merge_scan<LARGEST>(s, id, k, cs + q * cap, ci + q * cap, lane, n, 32);
+        merge_extract<LARGEST>(s, id, k, lane, os + q * k, oi + q * k);
+    } else {
+        merge_scan<LARGEST>(s, id, k, cs + q * cap, ci + q * cap, threadIdx.x, n, 32 * WQ);
+        merge_extract<LARGEST>(s, id, k, lane, sh_s + warp * k, sh_i + warp * k);
+        __syncthreads();
+        if (warp == 0) {
+            list_init<LARGEST>(s, id, k);
+            merge_scan<LARGEST>(s, id, k, sh_s, sh_i, lane, (int64_t)WQ * k, 32);
+            merge_extract<LARGEST>(s, id, k, lane, os + q * k, oi + q * k);
         }
     }
 }
@@ -321,11 +366,19 @@ int topk_merge_compact(const float *cs, const int64_t *ci, const int *cnt, int64
                        float *os, int64_t *oi, cudaStream_t st)
 {
     if (n_query == 0) return FRB_OK;
-    const int grid = (int)((n_query + 7) / 8);
-    if (largest)
-        topk_merge_compact_kernel<true><<<grid, 256, 0, st>>>(cs, ci, cnt, cap, n_query, k, os, oi);
-    else
-        topk_merge_compact_kernel<false><<<grid, 256, 0, st>>>(cs, ci, cnt, cap, n_query, k, os, oi);
+    // a CTA per query while that still leaves SMs idle and the lists are long enough to split eight ways
+    if (n_query <= sm_count() && cap >= 512) {
+        if (largest)
+            topk_merge_compact_kernel<true, 8><<<(int)n_query, 256, 0, st>>>(cs, ci, cnt, cap, n_query, k, os, oi);
+        else
+            topk_merge_compact_kernel<false, 8><<<(int)n_query, 256, 0, st>>>(cs, ci, cnt, cap, n_query, k, os, oi);
+    } else {
+        const int grid = (int)((n_query + 7) / 8);
+        if (largest)
+            topk_merge_compact_kernel<true, 1><<<grid, 256, 0, st>>>(cs, ci, cnt, cap, n_query, k, os, oi);
+        else
+            topk_merge_compact_kernel<false, 1><<<grid, 256, 0, st>>>(cs, ci, cnt, cap, n_query, k, os, oi);
+    }
     FRB_LAUNCH_OK("topk_merge_compact_kernel");
     return FRB_OK;
 }
