@@ -290,23 +290,43 @@ __device__ __forceinline__ void merge_insert(float *s, int64_t *id, int k, float
     id[p] = idx;
 }
 
-template <bool LARGEST>
-__device__ __forceinline__ void merge_scan(float *s, int64_t *id, int k, const float *cs, const int64_t *ci, int64_t first,
-                                           int64_t n, int64_t step)
+// candidate i of a query: compact layout (contiguous) or n_lists sorted lists of k, `stride` elements apart
+struct CompactCands {
+    const float *s;
+    const int64_t *x;
+    __device__ __forceinline__ void get(int64_t i, float &v, int64_t &idx) const { v = s[i]; idx = x[i]; }
+};
+struct ListCands {
+    const float *s;
+    const int64_t *x;
+    int64_t s_stride, i_stride;
+    int k;
+    __device__ __forceinline__ void get(int64_t i, float &v, int64_t &idx) const
+    {
+        const int64_t l = i / k, j = i - l * k;
+        v = s[l * s_stride + j];
+        idx = x[l * i_stride + j];
+    }
+};
+
+template <bool LARGEST, class Cands>
+__device__ __forceinline__ void merge_scan(float *s, int64_t *id, int k, const Cands &c, int64_t first, int64_t n, int64_t step)
 {
     int64_t i = first;
     for (; i + 3 * step < n; i += 4 * step) {
         float v[4];
         int64_t x[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            v[u] = cs[i + u * step];
-            x[u] = ci[i + u * step];
-        }
+        for (int u = 0; u < 4; u++) c.get(i + u * step, v[u], x[u]);
 #pragma unroll
         for (int u = 0; u < 4; u++) merge_insert<LARGEST>(s, id, k, v[u], x[u]);
     }
-    for (; i < n; i += step) merge_insert<LARGEST>(s, id, k, cs[i], ci[i]);
+    for (; i < n; i += step) {
+        float v;
+        int64_t x;
+        c.get(i, v, x);
+        merge_insert<LARGEST>(s, id, k, v, x);
+    }
 }
 
 // k rounds of warp arg-best over the lanes' sorted lists; lane 0 stores round r through (os, oi)
@@ -332,34 +352,56 @@ __device__ __forceinline__ void merge_extract(const float *s, const int64_t *id,
     }
 }
 
+// shared by the two layouts: this warp's (WQ = 1) or this CTA's (WQ = 8) query q with n candidates
+template <bool LARGEST, int WQ, class Cands>
+__device__ __forceinline__ void merge_query(const Cands &c, int64_t n, int k, float *os, int64_t *oi)
+{
+    __shared__ float sh_s[WQ > 1 ? WQ * FRB_MAX_K : 1];
+    __shared__ int64_t sh_i[WQ > 1 ? WQ * FRB_MAX_K : 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float s[FRB_MAX_K];
+    int64_t id[FRB_MAX_K];
+    list_init<LARGEST>(s, id, k);
+    if (WQ == 1) {
+        merge_scan<LARGEST>(s, id, k, c, lane, n, 32);
+        merge_extract<LARGEST>(s, id, k, lane, os, oi);
+    } else {
+        merge_scan<LARGEST>(s, id, k, c, threadIdx.x, n, 32 * WQ);
+        merge_extract<LARGEST>(s, id, k, lane, sh_s + warp * k, sh_i + warp * k);
+        __syncthreads();
+        if (warp == 0) {
+            list_init<LARGEST>(s, id, k);
+            const CompactCands mine = {sh_s, sh_i};
+            merge_scan<LARGEST>(s, id, k, mine, lane, (int64_t)WQ * k, 32);
+            merge_extract<LARGEST>(s, id, k, lane, os, oi);
+        }
+    }
+}
+
 template <bool LARGEST, int WQ>
 __global__ void __launch_bounds__(256) topk_merge_compact_kernel(const float *__restrict__ cs, const int64_t *__restrict__ ci,
                                                                  const int *__restrict__ cnt, int64_t cap, int64_t n_query,
                                                                  int k, float *__restrict__ os, int64_t *__restrict__ oi)
 {
-    __shared__ float sh_s[WQ > 1 ? WQ * FRB_MAX_K : 1];
-    __shared__ int64_t sh_i[WQ > 1 ? WQ * FRB_MAX_K : 1];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t q = WQ > 1 ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    const int64_t q = WQ > 1 ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= n_query) return;   // WQ > 1: uniform over the CTA
     int64_t n = cnt[q];
     if (n > cap) n = cap;
-    float s[FRB_MAX_K];
-    int64_t id[FRB_MAX_K];
-    list_init<LARGEST>(s, id, k);
-    if (WQ == 1) {
-        merge_scan<LARGEST>(s, id, k, cs + q * cap, ci + q * cap, lane, n, 32);
-        merge_extract<LARGEST>(s, id, k, lane, os + q * k, oi + q * k);
-    } else {
-        merge_scan<LARGEST>(s, id, k, cs + q * cap, ci + q * cap, threadIdx.x, n, 32 * WQ);
-        merge_extract<LARGEST>(s, id, k, lane, sh_s + warp * k, sh_i + warp * k);
-        __syncthreads();
-        if (warp == 0) {
-            list_init<LARGEST>(s, id, k);
-            merge_scan<LARGEST>(s, id, k, sh_s, sh_i, lane, (int64_t)WQ * k, 32);
-            merge_extract<LARGEST>(s, id, k, lane, os + q * k, oi + q * k);
-        }
-    }
+    const CompactCands c = {cs + q * cap, ci + q * cap};
+    merge_query<LARGEST, WQ>(c, n, k, os + q * k, oi + q * k);
+}
+
+// the strided-list layout ([n_lists] x [n_query, k], lists s_stride / i_stride elements apart) with many lists:
+// same warp / CTA per query scheme instead of topk_merge_kernel's one thread per query
+template <bool LARGEST, int WQ>
+__global__ void __launch_bounds__(256) topk_merge_lists_kernel(const float *__restrict__ cs, const int64_t *__restrict__ ci,
+                                                               int64_t s_stride, int64_t i_stride, int n_lists, int64_t n_query,
+                                                               int k, float *__restrict__ os, int64_t *__restrict__ oi)
+{
+    const int64_t q = WQ > 1 ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= n_query) return;
+    const ListCands c = {cs + q * k, ci + q * k, s_stride, i_stride, k};
+    merge_query<LARGEST, WQ>(c, (int64_t)n_lists * k, k, os + q * k, oi + q * k);
 }
 
 int topk_merge_compact(const float *cs, const int64_t *ci, const int *cnt, int64_t cap, int64_t n_query, int k, int largest,
@@ -461,11 +503,28 @@ static int topk_merge_launch(const char *fn, const float *cs, const int64_t *ci,
     FRB_CHECK_ARG(cs && ci && os && oi, "%s: null pointer", fn);
     FRB_CHECK_ARG(s_stride >= n_query * k && i_stride >= n_query * k, "%s: list strides %lld / %lld < n_query * k", fn,
                   (long long)s_stride, (long long)i_stride);
-    int grid = (int)((n_query + 127) / 128);
-    if (largest)
-        topk_merge_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(cs, ci, s_stride, i_stride, n_lists, n_query, k, os, oi);
-    else
-        topk_merge_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(cs, ci, s_stride, i_stride, n_lists, n_query, k, os, oi);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t cands = (int64_t)n_lists * k;
+    if (cands >= 512 && n_query <= sm_count()) {
+        // few queries, long candidate sets: a CTA per query
+        if (largest)
+            topk_merge_lists_kernel<true, 8><<<(int)n_query, 256, 0, st>>>(cs, ci, s_stride, i_stride, n_lists, n_query, k, os, oi);
+        else
+            topk_merge_lists_kernel<false, 8><<<(int)n_query, 256, 0, st>>>(cs, ci, s_stride, i_stride, n_lists, n_query, k, os, oi);
+    } else if (cands >= 32 && n_query <= (int64_t)sm_count() * 64) {
+        // a warp per query while one thread per query would leave most of the GPU idle walking its lists
+        const int grid = (int)((n_query + 7) / 8);
+        if (largest)
+            topk_merge_lists_kernel<true, 1><<<grid, 256, 0, st>>>(cs, ci, s_stride, i_stride, n_lists, n_query, k, os, oi);
+        else
+            topk_merge_lists_kernel<false, 1><<<grid, 256, 0, st>>>(cs, ci, s_stride, i_stride, n_lists, n_query, k, os, oi);
+    } else {
+        const int grid = (int)((n_query + 127) / 128);
+        if (largest)
+            topk_merge_kernel<true><<<grid, 128, 0, st>>>(cs, ci, s_stride, i_stride, n_lists, n_query, k, os, oi);
+        else
+            topk_merge_kernel<false><<<grid, 128, 0, st>>>(cs, ci, s_stride, i_stride, n_lists, n_query, k, os, oi);
+    }
     FRB_LAUNCH_OK("topk_merge_kernel");
     return FRB_OK;
 }
