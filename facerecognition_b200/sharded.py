@@ -151,3 +151,71 @@ def chisq_sharded(hist_shard: torch.Tensor, cell_px: int, row_offset: int, *, q_
         return ops.chisq_topk(q_hist, q_cell_px or cell_px, hist_shard, cell_px, k, idx_base=row_offset)
 
     return ShardedSearch(local, ops.topk_merge, False, group, merge_packed=ops.topk_merge_packed, peer_exchange=peer_exchange)
+
+
+class HostBatchPipeline:
+    """Double-buffered host -> GPU -> host ingestion around a (sharded) search, for throughput serving.
+
+    A synchronous call pays, every batch, an H2D copy of the queries, the search, and a D2H copy of the answers one
+    after the other.  Here the copies of batch i + 1 / i - 1 ride the two copy engines while batch i is searched:
+    `submit()` enqueues H2D on a copy stream, the search (and, with several ranks, the all-gather that replicates
+    this rank's slice of the batch) on the CALLER's stream, the D2H on a second copy stream, and returns a ticket;
+    `result(ticket)` blocks until that batch's answers are in pinned host memory.  All searches stay on one stream
+    in submission order, so the cross-rank exchange kernels never overlap one another.
+
+    queries per batch: `n_query` rows of `dim` fp32 for the whole job; this rank uploads rows [q0, q1) (its slice of
+    the batch; the whole batch on one GPU) and downloads the answers of the same rows.
+    """
+
+    def __init__(self, search: Callable[[torch.Tensor, int], Tuple[torch.Tensor, torch.Tensor]], n_query: int, dim: int,
+                 k: int, device: torch.device, *, rows: Optional[Tuple[int, int]] = None, depth: int = 2,
+                 group: Optional[dist.ProcessGroup] = None):
+        if device.type != "cuda":
+            raise RuntimeError("HostBatchPipeline needs a CUDA device: there is no CPU implementation in this package")
+        self.search, self.k, self.device, self.depth, self.group = search, k, device, depth, group
+        self.q0, self.q1 = rows if rows is not None else (0, n_query)
+        self.whole = (self.q0, self.q1) == (0, n_query)
+        n_mine = self.q1 - self.q0
+        self.copy_in, self.copy_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
+        self.stage = [torch.empty((n_query, dim), dtype=torch.float32, device=device) for _ in range(depth)]
+        self.out_s = [torch.empty((n_mine, k), dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.out_i = [torch.empty((n_mine, k), dtype=torch.int64).pin_memory() for _ in range(depth)]
+        self.h2d_done = [torch.cuda.Event() for _ in range(depth)]
+        self.searched = [torch.cuda.Event() for _ in range(depth)]
+        self.d2h_done = [torch.cuda.Event() for _ in range(depth)]
+        self.busy = [False] * depth
+        self.n = 0
+
+    def submit(self, q_host: torch.Tensor) -> int:
+        """q_host: this rank's rows of the batch, pinned fp32 [q1 - q0, dim].  Returns the ticket for result()."""
+        slot = self.n % self.depth
+        self.n += 1
+        if self.busy[slot]:
+            raise RuntimeError("HostBatchPipeline: result() of the batch submitted `depth` calls ago has not been taken")
+        main = torch.cuda.current_stream(self.device)
+        stage = self.stage[slot]
+        with torch.cuda.stream(self.copy_in):
+            self.copy_in.wait_event(self.searched[slot])        # the search that last read this staging buffer is done
+            stage[self.q0:self.q1].copy_(q_host, non_blocking=True)
+            self.h2d_done[slot].record(self.copy_in)
+        main.wait_event(self.h2d_done[slot])
+        if not self.whole:
+            dist.all_gather_into_tensor(stage, stage[self.q0:self.q1], group=self.group)
+        s, i = self.search(stage, self.k)
+        self.searched[slot].record(main)
+        with torch.cuda.stream(self.copy_out):
+            self.copy_out.wait_event(self.searched[slot])
+            self.out_s[slot].copy_(s[self.q0:self.q1], non_blocking=True)
+            self.out_i[slot].copy_(i[self.q0:self.q1], non_blocking=True)
+            self.d2h_done[slot].record(self.copy_out)
+        s.record_stream(self.copy_out)
+        i.record_stream(self.copy_out)
+        self.busy[slot] = True
+        return slot
+
+    def result(self, ticket: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(scores fp32 [q1 - q0, k], ids int64 [q1 - q0, k]) in pinned host memory; valid until the slot is reused,
+        i.e. until `depth` more submit() calls."""
+        self.d2h_done[ticket].synchronize()
+        self.busy[ticket] = False
+        return self.out_s[ticket], self.out_i[ticket]

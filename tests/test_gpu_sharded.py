@@ -80,3 +80,31 @@ def test_peer_exchange_protocol_emulated_on_one_gpu(R, largest):
     finally:
         for x in ranks:
             x.close()
+
+
+def test_host_batch_pipeline_matches_blocking_calls():
+    """sharded.HostBatchPipeline (two batches in flight, copies on side streams) returns, batch by batch, exactly
+    what a blocking search of the same host batch returns — including when the staging slots are reused."""
+    from facerecognition_b200 import ops, _native as NV
+    from facerecognition_b200.sharded import HostBatchPipeline, cosine_sharded
+    g = torch.Generator(device="cuda").manual_seed(3)
+    gal = ops.normalize_rows(torch.randn((50_000, 512), generator=g, device="cuda"), NV.FRB_QNORM_CLAMP, torch.bfloat16)
+    search = cosine_sharded(gal, 0, qnorm_mode=NV.FRB_QNORM_CLAMP)
+    batches = [(gal[torch.randint(0, 50_000, (300,), generator=g, device="cuda")].float()
+                + 0.02 * torch.randn((300, 512), generator=g, device="cuda")).cpu().pin_memory() for _ in range(7)]
+    pipe = HostBatchPipeline(search.search, 300, 512, 5, torch.device("cuda", 0))
+    got, tickets = [], []
+    for b in batches:
+        tickets.append(pipe.submit(b))
+        if len(tickets) == pipe.depth:
+            s, i = pipe.result(tickets.pop(0))
+            got.append((s.clone(), i.clone()))
+    for t in tickets:
+        s, i = pipe.result(t)
+        got.append((s.clone(), i.clone()))
+    assert len(got) == len(batches)
+    for b, (s, i) in zip(batches, got):
+        rs, ri = search.search(b.cuda(), 5)
+        assert torch.equal(i, ri.cpu()) and torch.equal(s, rs.cpu())
+    with pytest.raises(RuntimeError):
+        pipe.submit(batches[0]); pipe.submit(batches[1]); pipe.submit(batches[2])   # third without taking a result
