@@ -53,12 +53,14 @@ def measured_peaks():
 
 
 def ncu_traffic(kernel):
-    """DRAM bytes per step of `kernel` from the committed `ncu --set full` capture (profiles/ncu_traffic.json), or None."""
+    """{"traffic": DRAM bytes (read + written) of `kernel` over the launches `achieved` is computed on, "traffic_detail": ...}
+    from the committed `ncu --set full` capture (profiles/ncu_traffic.json); traffic None if there is no capture."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
-        return json.load(open(p))[kernel]
+        d = json.load(open(p))[kernel]
+        return {"traffic": d["bytes_per_step"], "traffic_detail": d}
     except Exception:
-        return None
+        return {"traffic": None}
 
 
 class ClockSampler:
@@ -246,7 +248,7 @@ def lbph_leg(torch, ops, NV, device, peaks):
     out["extract"] = {"faces_per_s": n_faces / (per * 1e-3), "ms_per_launch": per, "faces_per_launch": n_faces,
                       "faces": "112x112 u8: 1/3 noise + 255 stripe, 1/3 blurred noise, 1/3 flat patches",
                       "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                   "frac": gbs / peaks["hbm_gbs"], "traffic": ncu_traffic("lbp_hist_kernel"),
+                                   "frac": gbs / peaks["hbm_gbs"], **ncu_traffic("lbp_hist_kernel"),
                                    "note": "algorithmic bytes = 112*112 + 32768 per face; the kernel is issue-bound (DESIGN.md §3)"}}
     # K3: 64 query histograms against a 100k-row u16 gallery (3.3 GB), each query streams the gallery
     n_gal, n_q = 100_000, 64
@@ -265,7 +267,7 @@ def lbph_leg(torch, ops, NV, device, peaks):
     out["match"] = {"pairs_per_s": pairs / (per * 1e-3), "predicts_per_s_at_100k_gallery": n_q / (per * 1e-3), "ms_per_launch": per,
                     "queries": n_q, "gallery_rows": n_gal,
                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                 "frac": gbs / peaks["hbm_gbs"], "traffic": ncu_traffic("chisq_kernel"),
+                                 "frac": gbs / peaks["hbm_gbs"], **ncu_traffic("chisq_kernel"),
                                  "note": "algorithmic bytes = 32768 B per (query, gallery row) pair: every query streams the gallery"}}
     # front end: interleaved BGR video crops -> gray (3 B read + 1 B written per pixel)
     n_fr = 32768
@@ -458,7 +460,7 @@ def main():
     okt = torch.tensor([1 if ok else 0], device=device)
     if world > 1:
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-    traffic = ncu_traffic("cosine_tc_kernel") if world == 1 and n_gallery == N_GALLERY and q_per_gpu == N_QUERY else None
+    traffic = ncu_traffic("cosine_tc_kernel") if world == 1 and n_gallery == N_GALLERY and q_per_gpu == N_QUERY else {"traffic": None}
     # denominator: the timed steps follow >= 1 s of back-to-back steps; when the clock samples show the power cap
     # holding the SM clock down (median under load below 90 % of the maximum) the kernel ran in cuBLAS's "sustained"
     # regime, otherwise in its "burst" regime (B200_PROFILING.md)
@@ -479,7 +481,7 @@ def main():
                         "the other); blocking_call_value: one batch at a time, host waits for each"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "cosine_tc_kernel", "ms_per_step_in_kernel": kernel_ms_per_step,
+                     **traffic, "kernel": "cosine_tc_kernel", "ms_per_step_in_kernel": kernel_ms_per_step,
                      "launches_timed": k_n, "launches_per_step": tc_per_step, "flops_per_step": flops_per_step,
                      "frac_of_burst": achieved / peaks["bf16_tflops"], "frac_of_sustained": achieved / peaks["bf16_tflops_sustained"],
                      "peak_source": peaks["source"] + (", bf16 SUSTAINED figure: the timed steps ran power-capped (median SM clock < 90 % of max, see clocks) after >= 1 s of load"
