@@ -286,6 +286,24 @@ def lbph_leg(torch, ops, NV, device, peaks):
                                     "frac": gbs / peaks["hbm_gbs"], "traffic": None,
                                     "note": "algorithmic bytes = 4 per pixel (3 read, 1 written)"}}
     del bgr, gray
+    # front end in front of that: camera-sized BGR frames -> cv2.resize(frame, (112, 112)) + BGR2GRAY in one kernel
+    n_fr, sh, sw = 8192, 180, 240
+    big = torch.randint(0, 256, (n_fr, sh, sw, 3), generator=gen, device=device, dtype=torch.uint8)
+    for _ in range(2):
+        small = ops.resize_linear(big, (112, 112), to_gray=True)
+    NV.profile_enable(True)
+    NV.profile_read(NV.K_RESIZE)
+    for _ in range(5):
+        small = ops.resize_linear(big, (112, 112), to_gray=True)
+    ms, n = NV.profile_read(NV.K_RESIZE)
+    NV.profile_enable(False)
+    gbs = n_fr * (sh * sw * 3 + 112 * 112) / (ms / n * 1e-3) / 1e9
+    out["resize_gray"] = {"frames_per_s": n_fr / (ms / n * 1e-3), "ms_per_launch": ms / n, "frames_per_launch": n_fr,
+                          "frame": f"{sh}x{sw}x3 -> 112x112 gray",
+                          "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                       "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                                       "note": "algorithmic bytes = the whole source frame read once + the gray crop written"}}
+    del big, small
     # C5 shape on one GPU's share: 1024 frames, extract + chi-square NN against 125 000 histograms (1M / 8 GPUs)
     frames = faces[:1024].contiguous()
     gal5 = hist.view(torch.int16)[torch.randint(0, n_faces, (125_000,), generator=gen, device=device)].contiguous().view(torch.uint16)

@@ -47,6 +47,7 @@ SIGNATURES = {
                                         c_int, c_int, c_float, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "frb_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "frb_bgr2gray_u8": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "frb_resize_linear_u8": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "frb_group_mean_renorm": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "frb_topk_merge_strided": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int, c_int, c_void_p,
                                        c_void_p, c_void_p]),
@@ -95,7 +96,7 @@ def call(fn: str, *args) -> None:
     check(fn, getattr(lib, fn)(*args))
 
 
-K_COSINE_TC, K_COSINE_SIMT, K_LBP_HIST, K_CHISQ, K_BGR2GRAY, K_COSINE_GEMV = 0, 1, 2, 3, 4, 5
+K_COSINE_TC, K_COSINE_SIMT, K_LBP_HIST, K_CHISQ, K_BGR2GRAY, K_COSINE_GEMV, K_RESIZE = 0, 1, 2, 3, 4, 5, 6
 
 
 def profile_enable(on: bool) -> None:

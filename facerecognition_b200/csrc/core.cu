@@ -215,6 +215,88 @@ __global__ void __launch_bounds__(kGroupThreads) group_mean_renorm_kernel(const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// cv2.resize(src, (dst_cols, dst_rows)) with the default INTER_LINEAR on 8-bit images, bit-exact with OpenCV 4.x's
+// fixed-point path (imgproc/src/resize.cpp: resizeGeneric_Invoker / HResizeLinear / VResizeLinear<uchar,...>):
+//   coordinate  f = (float)((d + 0.5) * scale - 0.5), scale = 1 / (dst / src) in double; s = floor(f); f -= s
+//   weights     short(cvRound((1 - f) * 2048)), short(cvRound(f * 2048))   (round half to even)
+//   columns     s < 0 -> (s, f) = (0, 0);  s >= src - 1 -> (src - 1, 0)   (weights clamped)
+//   rows        weights kept, ROW INDICES clamped to [0, src - 1]          (so a border row is blended with itself)
+//   horizontal  r = p[s] * a0 + p[s + 1] * a1                               (int32, 11 fractional bits)
+//   vertical    ((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2
+// and, when both axes shrink by exactly 2, OpenCV switches INTER_LINEAR to the INTER_AREA fast path:
+// (p00 + p01 + p10 + p11 + 2) >> 2.  Pinned against the real cv2.resize (tests/test_oracle_lbph.py, oracle/resize.py).
+// GRAY additionally applies cvtColor(BGR2GRAY) to the resized pixel, so the resized colour image never reaches HBM.
+struct ResizeTap {
+    int ofs;         // first source row / column (not clamped for rows)
+    short w0, w1;    // 11-bit fixed-point weights
+};
+
+__device__ __forceinline__ ResizeTap resize_tap(int d, double scale, int src, bool clamp_weights)
+{
+    // every step individually rounded, as the host code of OpenCV does it (no fused multiply-add)
+    float f = __double2float_rn(__dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5));
+    int s = (int)floorf(f);
+    f = __fsub_rn(f, (float)s);
+    if (clamp_weights) {
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= src - 1) { s = src - 1; f = 0.f; }
+    }
+    ResizeTap t;
+    t.ofs = s;
+    t.w0 = (short)__float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+    t.w1 = (short)__float2int_rn(__fmul_rn(f, 2048.f));
+    return t;
+}
+
+template <int C, bool GRAY>
+__global__ void __launch_bounds__(256) resize_linear_kernel(const uint8_t *__restrict__ src, int64_t count, int src_rows, int src_cols,
+                                                            uint8_t *__restrict__ dst, int dst_rows, int dst_cols, double scale_x,
+                                                            double scale_y, int area2)
+{
+    extern __shared__ __align__(8) unsigned char resize_smem[];
+    ResizeTap *tx = reinterpret_cast<ResizeTap *>(resize_smem), *ty = tx + dst_cols;
+    if (!area2) {
+        for (int d = threadIdx.x; d < dst_cols; d += blockDim.x) tx[d] = resize_tap(d, scale_x, src_cols, true);
+        for (int d = threadIdx.x; d < dst_rows; d += blockDim.x) ty[d] = resize_tap(d, scale_y, src_rows, false);
+    }
+    __syncthreads();
+    const int64_t px_per_img = (int64_t)dst_rows * dst_cols;
+    const int64_t total = count * px_per_img;
+    const int64_t src_img = (int64_t)src_rows * src_cols * C;
+    constexpr int OC = GRAY ? 1 : C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / px_per_img;
+        const int r = (int)(i - b * px_per_img);
+        const int dy = r / dst_cols, dx = r - dy * dst_cols;
+        const uint8_t *img = src + b * src_img;
+        uint32_t v[C];
+        if (area2) {
+            const uint8_t *p0 = img + ((int64_t)(2 * dy) * src_cols + 2 * dx) * C, *p1 = p0 + (int64_t)src_cols * C;
+#pragma unroll
+            for (int c = 0; c < C; c++) v[c] = (__ldg(p0 + c) + __ldg(p0 + C + c) + __ldg(p1 + c) + __ldg(p1 + C + c) + 2u) >> 2;
+        } else {
+            const ResizeTap ax = tx[dx], ay = ty[dy];
+            const int x0 = ax.ofs, x1 = min(x0 + 1, src_cols - 1);
+            const int y0 = min(max(ay.ofs, 0), src_rows - 1), y1 = min(max(ay.ofs + 1, 0), src_rows - 1);
+            const uint8_t *r0 = img + (int64_t)y0 * src_cols * C, *r1 = img + (int64_t)y1 * src_cols * C;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const int h0 = (int)__ldg(r0 + (int64_t)x0 * C + c) * ax.w0 + (int)__ldg(r0 + (int64_t)x1 * C + c) * ax.w1;
+                const int h1 = (int)__ldg(r1 + (int64_t)x0 * C + c) * ax.w0 + (int)__ldg(r1 + (int64_t)x1 * C + c) * ax.w1;
+                const int o = (((ay.w0 * (h0 >> 4)) >> 16) + ((ay.w1 * (h1 >> 4)) >> 16) + 2) >> 2;
+                v[c] = (uint32_t)min(max(o, 0), 255);
+            }
+        }
+        if (GRAY) {
+            dst[i] = (uint8_t)gray_of(v[0], v[C > 1 ? 1 : 0], v[C > 2 ? 2 : 0]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; c++) dst[i * OC + c] = (uint8_t)v[c];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // One thread per query merges n_lists sorted candidate lists of length k (k <= FRB_MAX_K).
 template <bool LARGEST>
 __global__ void __launch_bounds__(128) topk_merge_kernel(const float *__restrict__ cs, const int64_t *__restrict__ ci,
@@ -542,6 +624,38 @@ int frb_bgr2gray_u8(const uint8_t *bgr, int64_t n_pixels, uint8_t *out, void *st
     ProfileScope prof(FRB_K_BGR2GRAY, (cudaStream_t)stream);
     bgr2gray_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(bgr, n_pixels, out, vec_ok);
     FRB_LAUNCH_OK("bgr2gray_kernel");
+    return FRB_OK;
+}
+
+int frb_resize_linear_u8(const uint8_t *src, int64_t count, int src_rows, int src_cols, int channels, uint8_t *dst,
+                         int dst_rows, int dst_cols, int to_gray, void *stream)
+{
+    FRB_CHECK_ARG(count >= 0 && src_rows >= 1 && src_cols >= 1 && dst_rows >= 1 && dst_cols >= 1,
+                  "frb_resize_linear_u8: count=%lld src=%dx%d dst=%dx%d", (long long)count, src_rows, src_cols, dst_rows, dst_cols);
+    FRB_CHECK_ARG(channels == 1 || channels == 3, "frb_resize_linear_u8: channels=%d (1 or 3)", channels);
+    FRB_CHECK_ARG(!to_gray || channels == 3, "frb_resize_linear_u8: to_gray needs 3 (BGR) channels");
+    if (dst_rows > 8192 || dst_cols > 8192) {
+        set_error("frb_resize_linear_u8: destination %dx%d larger than 8192 per side", dst_rows, dst_cols);
+        return FRB_ERR_UNSUPPORTED;
+    }
+    if (count == 0) return FRB_OK;
+    FRB_CHECK_ARG(src && dst, "frb_resize_linear_u8: null pointer");
+    // cv::resize: inv_scale = dsize / ssize; hal::resize: scale = 1. / inv_scale (both double)
+    const double scale_x = 1.0 / ((double)dst_cols / (double)src_cols), scale_y = 1.0 / ((double)dst_rows / (double)src_rows);
+    const int area2 = src_cols == 2 * dst_cols && src_rows == 2 * dst_rows;
+    const int64_t total = count * (int64_t)dst_rows * dst_cols;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    const size_t smem = (size_t)(dst_rows + dst_cols) * sizeof(ResizeTap);
+    cudaStream_t st = (cudaStream_t)stream;
+    typedef void (*Kernel)(const uint8_t *, int64_t, int, int, uint8_t *, int, int, double, double, int);
+    const Kernel kernel = channels == 1 ? resize_linear_kernel<1, false>
+                                        : (to_gray ? resize_linear_kernel<3, true> : resize_linear_kernel<3, false>);
+    if (smem > 48 * 1024) FRB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfileScope prof(FRB_K_RESIZE, st);
+    kernel<<<(unsigned)blocks, 256, smem, st>>>(src, count, src_rows, src_cols, dst, dst_rows, dst_cols, scale_x, scale_y, area2);
+    FRB_LAUNCH_OK("resize_linear_kernel");
     return FRB_OK;
 }
 

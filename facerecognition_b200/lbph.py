@@ -175,6 +175,13 @@ class LBPHFaceRecognizer:
         cv2.cvtColor step of web_app.py:475) -> predict_device."""
         return self.predict_device(ops.bgr_to_gray(frames_bgr), k)
 
+    def predict_device_frames(self, frames_bgr: torch.Tensor, target_size: Tuple[int, int] = (100, 100), k: int = 1
+                              ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The whole no-detector front end of web_app.py:484-486 / train_lbph_script.py:69-72 on the device:
+        u8 CUDA [Q, H, W, 3] BGR frames of any size -> cv2.resize(frame, target_size) + BGR2GRAY in one kernel
+        (frb_resize_linear_u8, to_gray) -> predict_device.  target_size = (cols, rows) as in cv2."""
+        return self.predict_device(preprocess_frames_device(frames_bgr, target_size), k)
+
     def predict_batch(self, images) -> Tuple[np.ndarray, np.ndarray]:
         """Batched predict: (labels int32 [Q], distances float64 [Q]); (-1, DBL_MAX) where the model
         threshold rejects the best match (dist >= threshold), as StandardCollector does."""
@@ -247,6 +254,14 @@ def LBPHFaceRecognizer_create(radius: int = 1, neighbors: int = 8, grid_x: int =
 
 
 # ---- mirrors of the reference's wrappers ------------------------------------------------------------
+def preprocess_frames_device(frames_bgr: torch.Tensor, target_size: Tuple[int, int] = (100, 100), grayscale: bool = True
+                             ) -> torch.Tensor:
+    """Batched `_preprocess_image_for_lbph(..., detector=None)` (train_lbph_script.py:49-76) on the device: every frame
+    of u8 CUDA [B, H, W, 3] goes through cv2.resize(image, target_size) and, if `grayscale`, cv2.cvtColor(BGR2GRAY),
+    bit for bit (fused: the resized colour frame is never written).  Returns u8 [B, rows, cols] or [B, rows, cols, 3]."""
+    return ops.resize_linear(frames_bgr, target_size, to_gray=grayscale)
+
+
 def train_lbph_model(faces, labels, radius=1, neighbors=8, grid_x=8, grid_y=8):
     """models/lbphmodel/train_lbph.py:4-36 — same signature, returns a trained recognizer."""
     model = LBPHFaceRecognizer_create(radius=radius, neighbors=neighbors, grid_x=grid_x, grid_y=grid_y)

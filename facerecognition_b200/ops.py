@@ -190,6 +190,22 @@ def bgr_to_gray(frames: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def resize_linear(frames: torch.Tensor, dsize: Tuple[int, int], to_gray: bool = False) -> torch.Tensor:
+    """frb_resize_linear_u8: u8 [B, H, W] or [B, H, W, 3] -> u8 [B, rows, cols(, 3)], bit-exact with
+    cv2.resize(img, dsize) (default INTER_LINEAR); dsize = (cols, rows) as in cv2.  to_gray=True (BGR input) also
+    applies cv2.cvtColor(COLOR_BGR2GRAY) to the resized pixels and returns u8 [B, rows, cols]."""
+    dev = _require_cuda(frames)
+    assert frames.dtype == torch.uint8 and frames.dim() in (3, 4) and frames.is_contiguous()
+    ch = 1 if frames.dim() == 3 else int(frames.shape[3])
+    cols, rows = int(dsize[0]), int(dsize[1])
+    shape = (frames.shape[0], rows, cols) if (ch == 1 or to_gray) else (frames.shape[0], rows, cols, ch)
+    out = torch.empty(shape, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.call("frb_resize_linear_u8", _p(frames), _I64(frames.shape[0]), int(frames.shape[1]), int(frames.shape[2]), ch,
+               _p(out), rows, cols, int(bool(to_gray)), _stream(dev))
+    return out
+
+
 class Exchange:
     """frb_exchange_*: this rank's peer-memory exchange buffer (see include/frb200.h).  `handle` is the 64-byte CUDA
     IPC handle to all-gather; `open(handles)` maps the peers; `topk_merge` is the fused exchange + merge kernel."""

@@ -76,7 +76,8 @@ typedef enum frb_kernel {
     FRB_K_CHISQ = 3,       /* chisq_kernel                                          */
     FRB_K_BGR2GRAY = 4,    /* bgr2gray_kernel                                       */
     FRB_K_COSINE_GEMV = 5, /* cosine_gemv_kernel (1..4 queries, HBM-bound row streaming) */
-    FRB_K_COUNT = 6
+    FRB_K_RESIZE = 6,      /* resize_linear_kernel (cv2.resize INTER_LINEAR, optionally fused with BGR2GRAY) */
+    FRB_K_COUNT = 7
 } frb_kernel;
 
 /* When enabled, every launch of the four hot kernels is bracketed by a CUDA event pair on the
@@ -162,6 +163,16 @@ int frb_topk_merge_strided(const float *cand_scores_dev, const int64_t *cand_idx
  * of OpenCV 4.13 over all 2^24 colours.  Replaces the cv2.cvtColor calls that feed LBPH
  * (models/lbphmodel/train_lbph_script.py:72, web_app.py:475,486). */
 int frb_bgr2gray_u8(const uint8_t *bgr_dev, int64_t n_pixels, uint8_t *out_gray_dev, void *stream);
+
+/* Resize front end of the LBPH path: src u8 [count, src_rows, src_cols, channels] (channels 1 or 3, interleaved) ->
+ * dst u8 [count, dst_rows, dst_cols, channels], bit-exact with cv2.resize(img, (dst_cols, dst_rows)) at its default
+ * INTER_LINEAR (OpenCV 4.x 11-bit fixed point, including its switch to the 2x2 INTER_AREA average when both axes
+ * halve exactly).  to_gray = 1 (channels must be 3) fuses cv2.cvtColor(..., COLOR_BGR2GRAY) behind it and writes
+ * dst u8 [count, dst_rows, dst_cols]: the resized colour image never reaches memory.  Replaces
+ * `cv2.resize(image, target_size)` + `cv2.cvtColor` in _preprocess_image_for_lbph
+ * (models/lbphmodel/train_lbph_script.py:67-72) and web_app.py:472-475,484-486; destination sides <= 8192. */
+int frb_resize_linear_u8(const uint8_t *src_dev, int64_t count, int src_rows, int src_cols, int channels,
+                         uint8_t *dst_dev, int dst_rows, int dst_cols, int to_gray, void *stream);
 
 /* ---- cross-GPU exchange fused with the merge, over NVLink peer memory ------------------------------------- */
 /* One context per rank (process).  frb_exchange_create cudaMallocs this rank's buffer — `world` record slots of

@@ -267,3 +267,52 @@ def test_chisq_other_histogram_lengths_and_large_counts(oracle_lbph, L):
         np.testing.assert_allclose(dist.cpu().numpy(), np.take_along_axis(ref, order, 1), rtol=REL)
         if q_px == g_px:
             assert float(dist[0, 0]) == 0.0                             # q[0] is a gallery row: exactly zero
+
+
+def test_resize_front_end_is_bit_exact_with_cv2():
+    """frb_resize_linear_u8 vs the REAL cv2.resize (default INTER_LINEAR) / cv2.cvtColor of the installed OpenCV core
+    and vs oracle/resize.py: batches, 1 and 3 channels, up- and down-scaling, the exact-halving (INTER_AREA) case,
+    1-pixel sides, and the fused resize + BGR2GRAY of _preprocess_image_for_lbph (train_lbph_script.py:67-72)."""
+    import cv2
+    from facerecognition_b200 import ops
+    from oracle import resize as OR
+    rng = np.random.default_rng(314)
+    cases = [(480, 640, 100, 100), (250, 250, 112, 112), (50, 40, 100, 100), (200, 200, 100, 100), (224, 224, 112, 112),
+             (100, 100, 100, 100), (37, 53, 112, 112), (720, 1280, 112, 112), (1, 1, 7, 5), (9, 1, 4, 6), (1, 13, 3, 40),
+             (2, 2, 1, 1), (64, 48, 32, 24), (31, 29, 300, 517)]
+    cases += [tuple(int(v) for v in rng.integers(1, 260, 4)) for _ in range(25)]
+    for sh, sw, dh, dw in cases:
+        n = 3
+        for ch in (1, 3):
+            imgs = rng.integers(0, 256, (n, sh, sw, ch) if ch == 3 else (n, sh, sw), dtype=np.uint8)
+            if (sh + sw) % 3 == 0:
+                imgs[1] = (imgs[1] // 64) * 85          # flat patches
+            got = ops.resize_linear(torch.from_numpy(imgs).cuda(), (dw, dh)).cpu().numpy()
+            for b in range(n):
+                ref = cv2.resize(imgs[b], (dw, dh)).reshape(got[b].shape)
+                np.testing.assert_array_equal(got[b], ref, err_msg=f"{sh}x{sw} -> {dh}x{dw}, {ch} ch")
+                np.testing.assert_array_equal(got[b], OR.resize_linear_u8(imgs[b], dw, dh).reshape(got[b].shape))
+            if ch == 3:
+                gray = ops.resize_linear(torch.from_numpy(imgs).cuda(), (dw, dh), to_gray=True).cpu().numpy()
+                for b in range(n):
+                    want = cv2.cvtColor(cv2.resize(imgs[b], (dw, dh)).reshape(dh, dw, 3), cv2.COLOR_BGR2GRAY)
+                    np.testing.assert_array_equal(gray[b], want, err_msg=f"fused gray {sh}x{sw} -> {dh}x{dw}")
+
+
+def test_predict_device_frames_equals_the_host_preprocessing(oracle_lbph):
+    """Frames of another size -> device resize + gray -> LBPH predict == cv2.resize + cv2.cvtColor on the host, then
+    predict (the reference's no-detector path, web_app.py:484-486 + :587)."""
+    import cv2
+    from facerecognition_b200.lbph import LBPHFaceRecognizer_create, preprocess_frames_device
+    rng = np.random.default_rng(8)
+    frames = rng.integers(0, 256, (12, 180, 240, 3), dtype=np.uint8)
+    host = [cv2.cvtColor(cv2.resize(f, (100, 100)), cv2.COLOR_BGR2GRAY) for f in frames]
+    dev_frames = torch.from_numpy(frames).cuda()
+    np.testing.assert_array_equal(preprocess_frames_device(dev_frames, (100, 100)).cpu().numpy(), np.stack(host))
+    model = LBPHFaceRecognizer_create()
+    model.train(host[:8], np.arange(8, dtype=np.int32))
+    dist, idx = model.predict_device_frames(dev_frames, (100, 100))
+    for j in range(12):
+        lab, conf = model.predict(host[j])
+        assert int(model.getLabels()[int(idx[j, 0])]) == lab and float(dist[j, 0]) == pytest.approx(conf, rel=1e-6, abs=1e-12)
+    assert (dist[:8, 0] == 0).all()

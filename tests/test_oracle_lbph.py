@@ -117,3 +117,31 @@ def test_predict_semantics(oracle_lbph, lbph_golden):
     m2.threshold = np.finfo(np.float64).max
     m2.update([faces[6]], np.array([11], np.int32))
     assert m2.predict(faces[6]) == (11, 0.0) and m2.hists.shape[0] == 4
+
+
+def test_resize_restatement_is_bit_exact_with_the_installed_cv2():
+    """oracle/resize.py vs the REAL cv2.resize (default INTER_LINEAR) and cv2.cvtColor of the installed OpenCV core:
+    up- and down-scaling, 1 and 3 channels, the exact-halving case (cv2 reroutes it to the INTER_AREA average),
+    1-pixel sides, and the reference's two target sizes from camera-like frames.  This pins the oracle."""
+    import cv2
+    from oracle import resize as OR
+    rng = np.random.default_rng(99)
+    cases = [(480, 640, 100, 100), (250, 250, 112, 112), (50, 40, 100, 100), (200, 200, 100, 100), (224, 224, 112, 112),
+             (100, 100, 100, 100), (37, 53, 112, 112), (720, 1280, 112, 112), (101, 99, 100, 100), (1, 1, 7, 5), (9, 1, 4, 6),
+             (1, 13, 3, 40), (2, 2, 1, 1), (300, 200, 100, 100), (64, 48, 32, 24)]
+    cases += [tuple(int(v) for v in rng.integers(1, 320, 4)) for _ in range(60)]
+    for sh, sw, dh, dw in cases:
+        for ch in (1, 3):
+            img = rng.integers(0, 256, (sh, sw, ch) if ch == 3 else (sh, sw), dtype=np.uint8)
+            ref = cv2.resize(img, (dw, dh))
+            got = OR.resize_linear_u8(img, dw, dh)
+            assert np.array_equal(got.reshape(ref.shape), ref), (sh, sw, dh, dw, ch)
+            if ch == 3:
+                want = cv2.cvtColor(ref.reshape(dh, dw, 3), cv2.COLOR_BGR2GRAY)
+                assert np.array_equal(OR.preprocess_for_lbph(img, (dw, dh)), want), (sh, sw, dh, dw)
+    # smooth images (long runs of equal weights) and saturated ones
+    ramp = np.add.outer(np.arange(240), np.arange(320)).astype(np.uint8)
+    for dsize in [(100, 100), (112, 112), (333, 17)]:
+        assert np.array_equal(OR.resize_linear_u8(ramp, *dsize), cv2.resize(ramp, dsize))
+        full = np.full((77, 91, 3), 255, np.uint8)
+        assert np.array_equal(OR.resize_linear_u8(full, *dsize), cv2.resize(full, dsize))
