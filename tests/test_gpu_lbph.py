@@ -299,6 +299,26 @@ def test_resize_front_end_is_bit_exact_with_cv2():
                     np.testing.assert_array_equal(gray[b], want, err_msg=f"fused gray {sh}x{sw} -> {dh}x{dw}")
 
 
+def test_resize_front_end_unaligned_batch_and_last_pixels():
+    """A batch that starts at an odd address (byte-load path) and the last pixels of the last image (the word-load
+    path must not read past the buffer) give the same bytes as cv2."""
+    import cv2
+    from facerecognition_b200 import ops
+    rng = np.random.default_rng(5)
+    for off in (0, 1, 2, 3):
+        n, sh, sw = 2, 33, 47
+        flat = torch.from_numpy(rng.integers(0, 256, off + n * sh * sw * 3, dtype=np.uint8)).cuda()
+        frames = flat[off:].view(n, sh, sw, 3)
+        host = frames.cpu().numpy()
+        for dsize in [(20, 15), (47, 33), (60, 70), (46, 32)]:
+            got = ops.resize_linear(frames, dsize).cpu().numpy()
+            gray = ops.resize_linear(frames, dsize, to_gray=True).cpu().numpy()
+            for b in range(n):
+                ref = cv2.resize(host[b], dsize)
+                np.testing.assert_array_equal(got[b], ref, err_msg=f"offset {off} dsize {dsize}")
+                np.testing.assert_array_equal(gray[b], cv2.cvtColor(ref, cv2.COLOR_BGR2GRAY))
+
+
 def test_predict_device_frames_equals_the_host_preprocessing(oracle_lbph):
     """Frames of another size -> device resize + gray -> LBPH predict == cv2.resize + cv2.cvtColor on the host, then
     predict (the reference's no-detector path, web_app.py:484-486 + :587)."""
