@@ -250,32 +250,79 @@ __device__ __forceinline__ ResizeTap resize_tap(int d, double scale, int src, bo
 
 // Work unit = (image, block of `rows_per_unit` destination rows); a CTA walks the unit's pixels 256 at a time, so
 // consecutive lanes write consecutive bytes and read neighbouring source pixels (L1 serves the overlap of the taps).
-// Byte loads on purpose: fetching each row's two taps as three aligned words + funnel shifts was measured slower
-// (0.64 vs 0.56 ms for 8192 frames of 180x240 -> 112x112) -- the kernel is bound by issue slots, not by the
-// load/store unit.
+// The tables hold everything that depends on one coordinate only (clamped byte offsets of both taps, weights), the
+// loop body is loads + the fixed-point blend; two pixels per thread per trip keep 24 loads in flight.
+// No clamp to [0, 255] is needed: weights are >= 0 and each pair sums to <= 2049, so the result is <= 255.
+// Byte loads on purpose: fetching each row's two taps as three aligned words + funnel shifts was measured slower.
+struct ResizeColTap {
+    int x0, x1;      // byte offsets of the two taps within a source row
+    short w0, w1;
+    int pad;
+};
+struct ResizeRowTap {
+    int y0, y1;      // byte offsets of the two source rows within the image (row index clamped)
+    short w0, w1;
+    int pad;
+};
+
+template <int C, bool GRAY>
+__device__ __forceinline__ void resize_pixel(const uint8_t *__restrict__ img, const ResizeColTap ax, const ResizeRowTap ay,
+                                             uint8_t *__restrict__ out)
+{
+    const uint8_t *p00 = img + ay.y0 + ax.x0, *p01 = img + ay.y0 + ax.x1, *p10 = img + ay.y1 + ax.x0, *p11 = img + ay.y1 + ax.x1;
+    uint32_t v[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const int h0 = (int)__ldg(p00 + c) * ax.w0 + (int)__ldg(p01 + c) * ax.w1;
+        const int h1 = (int)__ldg(p10 + c) * ax.w0 + (int)__ldg(p11 + c) * ax.w1;
+        v[c] = (uint32_t)((((ay.w0 * (h0 >> 4)) >> 16) + ((ay.w1 * (h1 >> 4)) >> 16) + 2) >> 2);
+    }
+    if (GRAY) {
+        out[0] = (uint8_t)gray_of(v[0], v[C > 1 ? 1 : 0], v[C > 2 ? 2 : 0]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; c++) out[c] = (uint8_t)v[c];
+    }
+}
+
 template <int C, bool GRAY>
 __global__ void __launch_bounds__(256) resize_linear_kernel(const uint8_t *__restrict__ src, int64_t count, int src_rows, int src_cols,
                                                             uint8_t *__restrict__ dst, int dst_rows, int dst_cols, double scale_x,
                                                             double scale_y, int area2, int rows_per_unit)
 {
-    extern __shared__ __align__(8) unsigned char resize_smem[];
-    ResizeTap *tx = reinterpret_cast<ResizeTap *>(resize_smem), *ty = tx + dst_cols;
+    extern __shared__ __align__(16) unsigned char resize_smem[];
+    ResizeColTap *tx = reinterpret_cast<ResizeColTap *>(resize_smem);
+    ResizeRowTap *ty = reinterpret_cast<ResizeRowTap *>(tx + dst_cols);
+    const int row_bytes = src_cols * C;
     if (!area2) {
         for (int d = threadIdx.x; d < dst_cols; d += blockDim.x) {
-            ResizeTap t = resize_tap(d, scale_x, src_cols, true);
-            t.ofs *= C;                                             // byte offset of the left tap within a row
-            tx[d] = t;
+            const ResizeTap t = resize_tap(d, scale_x, src_cols, true);
+            ResizeColTap o;
+            o.x0 = t.ofs * C;
+            o.x1 = min(t.ofs + 1, src_cols - 1) * C;
+            o.w0 = t.w0;
+            o.w1 = t.w1;
+            o.pad = 0;
+            tx[d] = o;
         }
-        for (int d = threadIdx.x; d < dst_rows; d += blockDim.x) ty[d] = resize_tap(d, scale_y, src_rows, false);
+        for (int d = threadIdx.x; d < dst_rows; d += blockDim.x) {
+            const ResizeTap t = resize_tap(d, scale_y, src_rows, false);
+            ResizeRowTap o;
+            o.y0 = min(max(t.ofs, 0), src_rows - 1) * row_bytes;
+            o.y1 = min(max(t.ofs + 1, 0), src_rows - 1) * row_bytes;
+            o.w0 = t.w0;
+            o.w1 = t.w1;
+            o.pad = 0;
+            ty[d] = o;
+        }
     }
     __syncthreads();
     constexpr int OC = GRAY ? 1 : C;
     const int unit_blocks = (dst_rows + rows_per_unit - 1) / rows_per_unit;
     const int64_t units = count * unit_blocks;
-    const int64_t src_img = (int64_t)src_rows * src_cols * C, dst_img = (int64_t)dst_rows * dst_cols * OC;
-    const int row_bytes = src_cols * C;
-    const int last_col = (src_cols - 1) * C;
-    const int step_y = (int)blockDim.x / dst_cols, step_x = (int)blockDim.x - step_y * dst_cols;
+    const int64_t src_img = (int64_t)src_rows * row_bytes, dst_img = (int64_t)dst_rows * dst_cols * OC;
+    const int nthr = (int)blockDim.x;
+    const int step_y = nthr / dst_cols, step_x = nthr - step_y * dst_cols;
     for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
         const int64_t b = u / unit_blocks;
         const int dy0 = (int)(u - b * unit_blocks) * rows_per_unit;
@@ -283,35 +330,37 @@ __global__ void __launch_bounds__(256) resize_linear_kernel(const uint8_t *__res
         const uint8_t *img = src + b * src_img;
         uint8_t *out = dst + b * dst_img + (int64_t)dy0 * dst_cols * OC;
         int dy = dy0 + (int)threadIdx.x / dst_cols, dx = (int)threadIdx.x % dst_cols;
-        for (int r = threadIdx.x; r < n; r += blockDim.x) {
-            uint32_t v[C];
-            if (area2) {
+        if (area2) {
+            for (int r = threadIdx.x; r < n; r += nthr) {
                 const uint8_t *p0 = img + (int64_t)(2 * dy) * row_bytes + 2 * dx * C, *p1 = p0 + row_bytes;
+                uint32_t v[C];
 #pragma unroll
                 for (int c = 0; c < C; c++) v[c] = (__ldg(p0 + c) + __ldg(p0 + C + c) + __ldg(p1 + c) + __ldg(p1 + C + c) + 2u) >> 2;
-            } else {
-                const ResizeTap ax = tx[dx], ay = ty[dy];
-                const int x0 = ax.ofs, x1 = min(x0 + C, last_col);
-                const int y0 = min(max(ay.ofs, 0), src_rows - 1), y1 = min(max(ay.ofs + 1, 0), src_rows - 1);
-                const uint8_t *r0 = img + (int64_t)y0 * row_bytes, *r1 = img + (int64_t)y1 * row_bytes;
+                if (GRAY) {
+                    out[r] = (uint8_t)gray_of(v[0], v[C > 1 ? 1 : 0], v[C > 2 ? 2 : 0]);
+                } else {
 #pragma unroll
-                for (int c = 0; c < C; c++) {
-                    const int h0 = (int)__ldg(r0 + x0 + c) * ax.w0 + (int)__ldg(r0 + x1 + c) * ax.w1;
-                    const int h1 = (int)__ldg(r1 + x0 + c) * ax.w0 + (int)__ldg(r1 + x1 + c) * ax.w1;
-                    const int o = (((ay.w0 * (h0 >> 4)) >> 16) + ((ay.w1 * (h1 >> 4)) >> 16) + 2) >> 2;
-                    v[c] = (uint32_t)min(max(o, 0), 255);
+                    for (int c = 0; c < C; c++) out[r * OC + c] = (uint8_t)v[c];
                 }
+                dx += step_x;
+                dy += step_y;
+                if (dx >= dst_cols) { dx -= dst_cols; dy++; }
             }
-            if (GRAY) {
-                out[r] = (uint8_t)gray_of(v[0], v[C > 1 ? 1 : 0], v[C > 2 ? 2 : 0]);
-            } else {
-#pragma unroll
-                for (int c = 0; c < C; c++) out[r * OC + c] = (uint8_t)v[c];
-            }
-            dx += step_x;
-            dy += step_y;
+            continue;
+        }
+        int r = threadIdx.x;
+        for (; r + nthr < n; r += 2 * nthr) {   // two pixels per trip: r and r + nthr
+            int dx2 = dx + step_x, dy2 = dy + step_y;
+            if (dx2 >= dst_cols) { dx2 -= dst_cols; dy2++; }
+            const ResizeColTap ax = tx[dx], bx = tx[dx2];
+            const ResizeRowTap ay = ty[dy], by = ty[dy2];
+            resize_pixel<C, GRAY>(img, ax, ay, out + (int64_t)r * OC);
+            resize_pixel<C, GRAY>(img, bx, by, out + (int64_t)(r + nthr) * OC);
+            dx = dx2 + step_x;
+            dy = dy2 + step_y;
             if (dx >= dst_cols) { dx -= dst_cols; dy++; }
         }
+        if (r < n) resize_pixel<C, GRAY>(img, tx[dx], ty[dy], out + (int64_t)r * OC);
     }
 }
 
@@ -671,7 +720,7 @@ int frb_resize_linear_u8(const uint8_t *src, int64_t count, int src_rows, int sr
     if (rpu < min_rows) rpu = min_rows;
     if (rpu > dst_rows) rpu = dst_rows;
     const int64_t units = count * ((dst_rows + rpu - 1) / rpu);
-    const size_t smem = (size_t)(dst_rows + dst_cols) * sizeof(ResizeTap);
+    const size_t smem = (size_t)dst_cols * sizeof(ResizeColTap) + (size_t)dst_rows * sizeof(ResizeRowTap);
     cudaStream_t st = (cudaStream_t)stream;
     typedef void (*Kernel)(const uint8_t *, int64_t, int, int, uint8_t *, int, int, double, double, int, int);
     const Kernel kernel = channels == 1 ? resize_linear_kernel<1, false>
