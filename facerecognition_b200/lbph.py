@@ -191,13 +191,16 @@ class LBPHFaceRecognizer:
             faces = [_as_gray_u8(f) for f in images]
             if self.size == 0:
                 raise LBPHError("This LBPH model is not computed yet. Did you call the train method?")
-            dist = torch.empty((len(faces), 1), dtype=torch.float32, device=self.device)
-            idx = torch.empty((len(faces), 1), dtype=torch.int64, device=self.device)
-            for pos, hist, px in self._hist_by_shape(faces):
-                d, i = self._search(hist, px, 1)
-                p = torch.tensor(pos, dtype=torch.int64, device=self.device)
-                dist[p], idx[p] = d, i
-        d = dist[:, 0].double().cpu().numpy()
+            parts = [(pos,) + self._search(hist, px, 1) for pos, hist, px in self._hist_by_shape(faces)]
+            if len(parts) == 1:                      # one image shape (the usual case): results are already in order
+                _, dist, idx = parts[0]
+            else:
+                dist = torch.empty((len(faces), 1), dtype=torch.float32, device=self.device)
+                idx = torch.empty((len(faces), 1), dtype=torch.int64, device=self.device)
+                for pos, d, i in parts:
+                    p = torch.tensor(pos, dtype=torch.int64, device=self.device)
+                    dist[p], idx[p] = d, i
+        d = dist[:, 0].cpu().numpy().astype(np.float64)      # float32 -> float64 is exact wherever it is done
         i = idx[:, 0].cpu().numpy()
         ok = (i >= 0) & (d < self._threshold)
         labels = np.where(ok, self._labels[np.clip(i, 0, max(self.size - 1, 0))], -1).astype(np.int32)

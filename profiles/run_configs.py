@@ -80,10 +80,13 @@ def c1():
     single = [model.predict(f) for f in faces[:200]]                      # the reference's call pattern: one image per call
     t_single = (time.perf_counter() - t0) / 200
     model.predict_batch(face_list[:64])                                   # first use of the batched kernel variant loads it
-    t0 = time.perf_counter()
-    lab_b, dist_b = model.predict_batch(face_list)
-    lab_f, dist_f = model.predict_batch([f for f in fresh])
-    t_batch = time.perf_counter() - t0
+    t_reps = []
+    for _ in range(5):                                                    # median of 5: a 20 ms host-driven burst is at the mercy of clock ramps
+        t0 = time.perf_counter()
+        lab_b, dist_b = model.predict_batch(face_list)
+        lab_f, dist_f = model.predict_batch([f for f in fresh])
+        t_reps.append(time.perf_counter() - t0)
+    t_batch = sorted(t_reps)[2]
     ok = bool((dist_b == 0.0).all()) and all(d == 0.0 for _, d in single)   # every training face matches itself at distance 0
     # CPU: the oracle's C restatement of OpenCV LBPH (1 thread, as cv2.face runs): extract all, then predict a sample
     t0 = time.perf_counter()

@@ -334,5 +334,5 @@ def test_predict_device_frames_equals_the_host_preprocessing(oracle_lbph):
     dist, idx = model.predict_device_frames(dev_frames, (100, 100))
     for j in range(12):
         lab, conf = model.predict(host[j])
-        assert int(model.getLabels()[int(idx[j, 0])]) == lab and float(dist[j, 0]) == pytest.approx(conf, rel=1e-6, abs=1e-12)
+        assert int(model.getLabels()[int(idx[j, 0]), 0]) == lab and float(dist[j, 0]) == pytest.approx(conf, rel=1e-6, abs=1e-12)
     assert (dist[:8, 0] == 0).all()
