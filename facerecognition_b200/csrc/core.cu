@@ -702,8 +702,8 @@ int frb_resize_linear_u8(const uint8_t *src, int64_t count, int src_rows, int sr
                   "frb_resize_linear_u8: count=%lld src=%dx%d dst=%dx%d", (long long)count, src_rows, src_cols, dst_rows, dst_cols);
     FRB_CHECK_ARG(channels == 1 || channels == 3, "frb_resize_linear_u8: channels=%d (1 or 3)", channels);
     FRB_CHECK_ARG(!to_gray || channels == 3, "frb_resize_linear_u8: to_gray needs 3 (BGR) channels");
-    if (dst_rows > 8192 || dst_cols > 8192) {
-        set_error("frb_resize_linear_u8: destination %dx%d larger than 8192 per side", dst_rows, dst_cols);
+    if (dst_rows > 4096 || dst_cols > 4096) {   // the two tap tables (16 B per destination row / column) live in shared memory
+        set_error("frb_resize_linear_u8: destination %dx%d larger than 4096 per side", dst_rows, dst_cols);
         return FRB_ERR_UNSUPPORTED;
     }
     if (count == 0) return FRB_OK;

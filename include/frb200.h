@@ -170,7 +170,7 @@ int frb_bgr2gray_u8(const uint8_t *bgr_dev, int64_t n_pixels, uint8_t *out_gray_
  * halve exactly).  to_gray = 1 (channels must be 3) fuses cv2.cvtColor(..., COLOR_BGR2GRAY) behind it and writes
  * dst u8 [count, dst_rows, dst_cols]: the resized colour image never reaches memory.  Replaces
  * `cv2.resize(image, target_size)` + `cv2.cvtColor` in _preprocess_image_for_lbph
- * (models/lbphmodel/train_lbph_script.py:67-72) and web_app.py:472-475,484-486; destination sides <= 8192. */
+ * (models/lbphmodel/train_lbph_script.py:67-72) and web_app.py:472-475,484-486; destination sides <= 4096. */
 int frb_resize_linear_u8(const uint8_t *src_dev, int64_t count, int src_rows, int src_cols, int channels,
                          uint8_t *dst_dev, int dst_rows, int dst_cols, int to_gray, void *stream);
 

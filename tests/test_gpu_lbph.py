@@ -319,6 +319,20 @@ def test_resize_front_end_unaligned_batch_and_last_pixels():
                 np.testing.assert_array_equal(gray[b], cv2.cvtColor(ref, cv2.COLOR_BGR2GRAY))
 
 
+def test_resize_front_end_large_destination_and_limits():
+    """An up-scale whose tap tables need more than 48 KB of shared memory (opt-in path), and the documented limit."""
+    import cv2
+    from facerecognition_b200 import ops, _native as NV
+    rng = np.random.default_rng(6)
+    img = rng.integers(0, 256, (1, 40, 30, 3), dtype=np.uint8)
+    got = ops.resize_linear(torch.from_numpy(img).cuda(), (3000, 1000)).cpu().numpy()
+    np.testing.assert_array_equal(got[0], cv2.resize(img[0], (3000, 1000)))
+    with pytest.raises(NV.FrbError):
+        ops.resize_linear(torch.from_numpy(img).cuda(), (4097, 10))
+    with pytest.raises(NV.FrbError):
+        ops.resize_linear(torch.from_numpy(img[..., :2].copy()).cuda(), (10, 10))     # 2 channels
+
+
 def test_predict_device_frames_equals_the_host_preprocessing(oracle_lbph):
     """Frames of another size -> device resize + gray -> LBPH predict == cv2.resize + cv2.cvtColor on the host, then
     predict (the reference's no-detector path, web_app.py:484-486 + :587)."""
