@@ -63,6 +63,9 @@ SIGNATURES = {
     "frb_chisq_topk": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_void_p,
                                c_void_p, c_void_p, c_size_t, c_void_p]),
     "frb_chisq_dist": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "frb_chisq_topk_g8": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_void_p,
+                                  c_void_p, c_void_p, c_size_t, c_void_p]),
+    "frb_chisq_dist_g8": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
 }
 
 

@@ -77,12 +77,19 @@ __device__ __forceinline__ float chi_rcp(float x)
     return r;
 }
 
-// Four bins: gallery words wa (bins 0,1) and wb (bins 2,3).  INTQ: qa/qb = -(2^23 + c), ta/tb = max(2c, 2^-40);
-// otherwise qa/qb = -c~ and ta/tb = max(c~, 2^-40) with c~ the query count rescaled to the gallery's cell size.
-template <bool INTQ>
-__device__ __forceinline__ float2 chi_quad(uint32_t wa, uint32_t wb, float2 qa, float2 ta, float2 qb, float2 tb, float2 acc)
+// the four u8 counts of a word as 2^23 + count: bins (0, 1) and (2, 3)
+__device__ __forceinline__ void chi_magic8(uint32_t w, float2 &ga, float2 &gb)
 {
-    float2 ga = chi_magic(wa), gb = chi_magic(wb);
+    ga = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)), __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541)));
+    gb = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)), __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543)));
+}
+
+// Four bins with gallery counts ga (bins 0,1) and gb (bins 2,3) given as 2^23 + count.  INTQ: qa/qb = -(2^23 + c),
+// ta/tb = max(2c, 2^-40); otherwise qa/qb = -c~ and ta/tb = max(c~, 2^-40) with c~ the query count rescaled to the
+// gallery's cell size.
+template <bool INTQ>
+__device__ __forceinline__ float2 chi_quad_core(float2 ga, float2 gb, float2 qa, float2 ta, float2 qb, float2 tb, float2 acc)
+{
     float2 da, db, sa, sb;
     if (INTQ) {
         da = __fadd2_rn(ga, qa);
@@ -103,16 +110,31 @@ __device__ __forceinline__ float2 chi_quad(uint32_t wa, uint32_t wb, float2 qa, 
     const float2 r = make_float2(chi_rcp(prod.x), chi_rcp(prod.y));
     return __ffma2_rn(u, r, acc);
 }
+// u16 gallery: words wa (bins 0,1) and wb (bins 2,3)
+template <bool INTQ>
+__device__ __forceinline__ float2 chi_quad(uint32_t wa, uint32_t wb, float2 qa, float2 ta, float2 qb, float2 tb, float2 acc)
+{
+    return chi_quad_core<INTQ>(chi_magic(wa), chi_magic(wb), qa, ta, qb, tb, acc);
+}
+// u8 gallery: one word holds the four bins
+template <bool INTQ>
+__device__ __forceinline__ float2 chi_quad8(uint32_t w, float2 qa, float2 ta, float2 qb, float2 tb, float2 acc)
+{
+    float2 ga, gb;
+    chi_magic8(w, ga, gb);
+    return chi_quad_core<INTQ>(ga, gb, qa, ta, qb, tb, acc);
+}
 
 // ---- twelve rows = two trips round the 6-slot ring, so slots and mbarrier parities are compile-time constants -----
 // Row i of the block (i = 0..11) lives in slot i % 6 during ring phase (i / 6) & 1.  While row i is consumed, warp i
 // requests row i + 4 (slot (i + 4) % 6) once every warp has released that slot's previous tenant (row i - 2).
 // GUARD: the block may run past the chunk's last row (tail block only).  FULL: every thread owns CHUNKS full groups.
-template <int CHUNKS, bool INTQ, bool FULL, bool GUARD>
+// G8: the gallery holds u8 counts (16 bins per 128-bit group, E = 8 bin pairs) instead of u16 (8 bins, E = 4).
+template <int CHUNKS, bool INTQ, bool FULL, bool GUARD, bool G8>
 __device__ __forceinline__ void chi_block12(const unsigned char *ring, uint64_t *s_full, uint64_t *s_empty, uint32_t row_bytes,
-                                            const uint16_t *__restrict__ gal_chunk, int hist_len, int64_t it0, int64_t n_rows,
-                                            const float2 (&qd)[CHUNKS][4], const float2 (&qs)[CHUNKS][4], const bool (&live)[CHUNKS],
-                                            float (*part)[kChiWarps + 1], int part_row0)
+                                            const unsigned char *__restrict__ gal_chunk, int64_t it0, int64_t n_rows,
+                                            const float2 (&qd)[CHUNKS][G8 ? 8 : 4], const float2 (&qs)[CHUNKS][G8 ? 8 : 4],
+                                            const bool (&live)[CHUNKS], float (*part)[kChiWarps + 1], int part_row0)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
@@ -129,7 +151,7 @@ __device__ __forceinline__ void chi_block12(const unsigned char *ring, uint64_t 
                     const int ns = j % 6;
                     const uint32_t par = (j < 6 || j >= 12) ? 1u : 0u;   // parity of the phase that released the slot
                     if (j >= 6 || it0 > 0) chi_mbar_wait(&s_empty[ns], par);
-                    chi_bulk_load(const_cast<unsigned char *>(ring) + (size_t)ns * row_bytes, gal_chunk + (it0 + j) * hist_len,
+                    chi_bulk_load(const_cast<unsigned char *>(ring) + (size_t)ns * row_bytes, gal_chunk + (it0 + j) * (int64_t)row_bytes,
                                   row_bytes, &s_full[ns]);
                 }
             }
@@ -150,8 +172,15 @@ __device__ __forceinline__ void chi_block12(const unsigned char *ring, uint64_t 
             float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
             for (int jj = 0; jj < CHUNKS; jj++) {
-                acc = chi_quad<INTQ>(w[jj].x, w[jj].y, qd[jj][0], qs[jj][0], qd[jj][1], qs[jj][1], acc);
-                acc = chi_quad<INTQ>(w[jj].z, w[jj].w, qd[jj][2], qs[jj][2], qd[jj][3], qs[jj][3], acc);
+                if (G8) {
+                    acc = chi_quad8<INTQ>(w[jj].x, qd[jj][0], qs[jj][0], qd[jj][1], qs[jj][1], acc);
+                    acc = chi_quad8<INTQ>(w[jj].y, qd[jj][2], qs[jj][2], qd[jj][3], qs[jj][3], acc);
+                    acc = chi_quad8<INTQ>(w[jj].z, qd[jj][G8 ? 4 : 0], qs[jj][G8 ? 4 : 0], qd[jj][G8 ? 5 : 1], qs[jj][G8 ? 5 : 1], acc);
+                    acc = chi_quad8<INTQ>(w[jj].w, qd[jj][G8 ? 6 : 2], qs[jj][G8 ? 6 : 2], qd[jj][G8 ? 7 : 3], qs[jj][G8 ? 7 : 3], acc);
+                } else {
+                    acc = chi_quad<INTQ>(w[jj].x, w[jj].y, qd[jj][0], qs[jj][0], qd[jj][1], qs[jj][1], acc);
+                    acc = chi_quad<INTQ>(w[jj].z, w[jj].w, qd[jj][2], qs[jj][2], qd[jj][3], qs[jj][3], acc);
+                }
             }
             p[r] = acc.x + acc.y;
         }
@@ -171,10 +200,11 @@ __device__ __forceinline__ void chi_block12(const unsigned char *ring, uint64_t 
     }
 }
 
-// CHUNKS: 128-bit groups per thread per row (hist_len <= CHUNKS * 4096).  WRITE_ALL: emit every distance.
-template <int CHUNKS, bool WRITE_ALL, bool INTQ, bool FULL>
+// CHUNKS: 128-bit groups per thread per row (hist_len <= CHUNKS * 4096 for a u16 gallery, CHUNKS * 8192 for u8).
+// WRITE_ALL: emit every distance.  G8: gallery of u8 counts (cell_px <= 255): half the bytes per row, same arithmetic.
+template <int CHUNKS, bool WRITE_ALL, bool INTQ, bool FULL, bool G8>
 __global__ void __launch_bounds__(kChiBlock, 1)
-chisq_kernel(const uint16_t *__restrict__ qhist, int64_t n_query, float q_scale, const uint16_t *__restrict__ gallery,
+chisq_kernel(const uint16_t *__restrict__ qhist, int64_t n_query, float q_scale, const void *__restrict__ gallery_v,
              int64_t n_gallery, int hist_len, float out_scale, int64_t rows_per_chunk, int k, int64_t idx_base,
              float *__restrict__ cand_dist, int64_t *__restrict__ cand_idx, float *__restrict__ all_dist)
 {
@@ -191,9 +221,10 @@ chisq_kernel(const uint16_t *__restrict__ qhist, int64_t n_query, float q_scale,
     int64_t row_end = row_begin + rows_per_chunk;
     if (row_end > n_gallery) row_end = n_gallery;
     const int64_t n_rows = row_end - row_begin;
-    const int vec_per_row = hist_len >> 3;  // uint4 per row
-    const uint32_t row_bytes = (uint32_t)hist_len * 2u;
-    const uint16_t *gal_chunk = gallery + row_begin * hist_len;
+    constexpr int E = G8 ? 8 : 4;                          // bin pairs per 128-bit gallery group
+    const int vec_per_row = hist_len >> (G8 ? 4 : 3);      // uint4 per gallery row
+    const uint32_t row_bytes = (uint32_t)hist_len * (G8 ? 1u : 2u);
+    const unsigned char *gal_chunk = reinterpret_cast<const unsigned char *>(gallery_v) + row_begin * (int64_t)row_bytes;
 
     if (tid == 0) {
         for (int i = 0; i < kChiSlots; i++) {
@@ -206,22 +237,30 @@ chisq_kernel(const uint16_t *__restrict__ qhist, int64_t n_query, float q_scale,
     // the first four rows are requested up front; after that warp i of a 12-row block requests row i + 4
     if (tid == 0) {
         for (int64_t i = 0; i < 4 && i < n_rows; i++)
-            chi_bulk_load(chi_smem + (size_t)i * row_bytes, gal_chunk + i * hist_len, row_bytes, &s_full[i]);
+            chi_bulk_load(chi_smem + (size_t)i * row_bytes, gal_chunk + i * (int64_t)row_bytes, row_bytes, &s_full[i]);
     }
 
     // ---- query bins -> registers ------------------------------------------------------------------------------
-    float2 qd[CHUNKS][4], qs[CHUNKS][4];
+    // (the query is always u16, as K2 writes it; a u8 gallery group of 16 bins takes two 128-bit query loads)
+    float2 qd[CHUNKS][E], qs[CHUNKS][E];
     bool live[CHUNKS];
     const float tiny = __uint_as_float(0x2B800000u);  // 2^-40
 #pragma unroll
     for (int j = 0; j < CHUNKS; j++) {
         const int v = j * kChiThreads + tid;
         live[j] = FULL || v < vec_per_row;
-        uint4 w = make_uint4(0, 0, 0, 0);
-        if (live[j]) w = __ldg(reinterpret_cast<const uint4 *>(qhist + q * hist_len) + v);
-        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+        uint32_t ww[E];
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
+        for (int h = 0; h < E / 4; h++) {
+            uint4 w = make_uint4(0, 0, 0, 0);
+            if (live[j]) w = __ldg(reinterpret_cast<const uint4 *>(qhist + q * hist_len) + v * (E / 4) + h);
+            ww[4 * h] = w.x;
+            ww[4 * h + 1] = w.y;
+            ww[4 * h + 2] = w.z;
+            ww[4 * h + 3] = w.w;
+        }
+#pragma unroll
+        for (int e = 0; e < E; e++) {
             const float c0 = (float)(ww[e] & 0xFFFFu), c1 = (float)(ww[e] >> 16);
             if (INTQ) {
                 qd[j][e] = make_float2(-(c0 + 8388608.0f), -(c1 + 8388608.0f));
@@ -246,11 +285,11 @@ chisq_kernel(const uint16_t *__restrict__ qhist, int64_t n_query, float q_scale,
         for (int h = 0; h < 2; h++) {
             const int64_t b0 = it0 + h * 12;
             if (b0 + 12 <= n_rows)
-                chi_block12<CHUNKS, INTQ, FULL, false>(chi_smem, s_full, s_empty, row_bytes, gal_chunk, hist_len, b0, n_rows, qd, qs,
-                                                       live, s_part[buf], h * 12);
+                chi_block12<CHUNKS, INTQ, FULL, false, G8>(chi_smem, s_full, s_empty, row_bytes, gal_chunk, b0, n_rows, qd, qs, live,
+                                                           s_part[buf], h * 12);
             else if (b0 < n_rows)
-                chi_block12<CHUNKS, INTQ, FULL, true>(chi_smem, s_full, s_empty, row_bytes, gal_chunk, hist_len, b0, n_rows, qd, qs,
-                                                      live, s_part[buf], h * 12);
+                chi_block12<CHUNKS, INTQ, FULL, true, G8>(chi_smem, s_full, s_empty, row_bytes, gal_chunk, b0, n_rows, qd, qs, live,
+                                                          s_part[buf], h * 12);
         }
         __syncthreads();
         if (warp == 0) {
@@ -307,8 +346,8 @@ static int64_t chi_chunks(int64_t n_query, int64_t n_gallery, int64_t *rows_per_
     return chunks < 1 ? 1 : chunks;
 }
 
-template <int CHUNKS, bool WRITE_ALL, bool INTQ, bool FULL>
-static int launch_chisq_t(dim3 grid, size_t smem, const uint16_t *qh, int64_t nq, float q_scale, const uint16_t *gal, int64_t ng,
+template <int CHUNKS, bool WRITE_ALL, bool INTQ, bool FULL, bool G8>
+static int launch_chisq_t(dim3 grid, size_t smem, const uint16_t *qh, int64_t nq, float q_scale, const void *gal, int64_t ng,
                           int L, float out_scale, int64_t rpc, int k, int64_t idx_base, float *cd, int64_t *ci, float *all,
                           cudaStream_t st)
 {
@@ -317,50 +356,68 @@ static int launch_chisq_t(dim3 grid, size_t smem, const uint16_t *qh, int64_t nq
     int dev = 0;
     FRB_CUDA_OK(cudaGetDevice(&dev));
     if (attr_dev != dev || attr_smem < smem) {
-        FRB_CUDA_OK(cudaFuncSetAttribute(chisq_kernel<CHUNKS, WRITE_ALL, INTQ, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem));
+        FRB_CUDA_OK(cudaFuncSetAttribute(chisq_kernel<CHUNKS, WRITE_ALL, INTQ, FULL, G8>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_dev = dev;
         attr_smem = smem;
     }
     ProfileScope prof(FRB_K_CHISQ, st);
-    chisq_kernel<CHUNKS, WRITE_ALL, INTQ, FULL><<<grid, kChiBlock, smem, st>>>(qh, nq, q_scale, gal, ng, L, out_scale, rpc, k,
-                                                                              idx_base, cd, ci, all);
+    chisq_kernel<CHUNKS, WRITE_ALL, INTQ, FULL, G8><<<grid, kChiBlock, smem, st>>>(qh, nq, q_scale, gal, ng, L, out_scale, rpc, k,
+                                                                                  idx_base, cd, ci, all);
     FRB_LAUNCH_OK("chisq_kernel");
     return FRB_OK;
 }
 
-template <int CHUNKS, bool WRITE_ALL>
+template <int CHUNKS, bool WRITE_ALL, bool G8>
 static int launch_chisq_c(bool intq, bool full, dim3 grid, size_t smem, const uint16_t *qh, int64_t nq, float q_scale,
-                          const uint16_t *gal, int64_t ng, int L, float out_scale, int64_t rpc, int k, int64_t idx_base, float *cd,
+                          const void *gal, int64_t ng, int L, float out_scale, int64_t rpc, int k, int64_t idx_base, float *cd,
                           int64_t *ci, float *all, cudaStream_t st)
 {
 #define FRB_CHI_ARGS grid, smem, qh, nq, q_scale, gal, ng, L, out_scale, rpc, k, idx_base, cd, ci, all, st
-    if (intq) return full ? launch_chisq_t<CHUNKS, WRITE_ALL, true, true>(FRB_CHI_ARGS) : launch_chisq_t<CHUNKS, WRITE_ALL, true, false>(FRB_CHI_ARGS);
-    return full ? launch_chisq_t<CHUNKS, WRITE_ALL, false, true>(FRB_CHI_ARGS) : launch_chisq_t<CHUNKS, WRITE_ALL, false, false>(FRB_CHI_ARGS);
+    if (intq)
+        return full ? launch_chisq_t<CHUNKS, WRITE_ALL, true, true, G8>(FRB_CHI_ARGS)
+                    : launch_chisq_t<CHUNKS, WRITE_ALL, true, false, G8>(FRB_CHI_ARGS);
+    return full ? launch_chisq_t<CHUNKS, WRITE_ALL, false, true, G8>(FRB_CHI_ARGS)
+                : launch_chisq_t<CHUNKS, WRITE_ALL, false, false, G8>(FRB_CHI_ARGS);
 #undef FRB_CHI_ARGS
 }
 
-template <bool WRITE_ALL>
-static int launch_chisq(const uint16_t *qh, int64_t nq, int q_cell_px, const uint16_t *gal, int64_t ng, int L, int g_cell_px,
-                        int64_t rpc, int64_t chunks, int k, int64_t idx_base, float *cd, int64_t *ci, float *all,
-                        cudaStream_t st)
+// gallery_bytes: 2 (u16 counts) or 1 (u8 counts, cell_px <= 255)
+template <bool WRITE_ALL, bool G8>
+static int launch_chisq_g(const uint16_t *qh, int64_t nq, int q_cell_px, const void *gal, int64_t ng, int L, int g_cell_px,
+                          int64_t rpc, int64_t chunks, int k, int64_t idx_base, float *cd, int64_t *ci, float *all,
+                          cudaStream_t st)
 {
     dim3 grid((unsigned)nq, (unsigned)chunks);
-    const int chunks_per_thread = (L / 8 + kChiThreads - 1) / kChiThreads;
+    const int bins_per_group = G8 ? 16 : 8;                 // bins in one 128-bit gallery load
+    const int groups = L / bins_per_group;
+    const int chunks_per_thread = (groups + kChiThreads - 1) / kChiThreads;
     const float q_scale = (float)g_cell_px / (float)q_cell_px;
     const float out_scale = 2.0f / (float)g_cell_px;
     const bool intq = q_cell_px == g_cell_px;  // integer counts on both sides: exact differences without a conversion
-    const size_t smem = (size_t)L * 2 * kChiSlots;  // ring of whole rows
+    const size_t smem = (size_t)L * (G8 ? 1 : 2) * kChiSlots;  // ring of whole rows
     int c = chunks_per_thread == 3 ? 4 : chunks_per_thread;
-    const bool full = (L / 8) == c * kChiThreads;
-    switch (c) {
-        case 1: return launch_chisq_c<1, WRITE_ALL>(intq, full, grid, smem, qh, nq, q_scale, gal, ng, L, out_scale, rpc, k, idx_base, cd, ci, all, st);
-        case 2: return launch_chisq_c<2, WRITE_ALL>(intq, full, grid, smem, qh, nq, q_scale, gal, ng, L, out_scale, rpc, k, idx_base, cd, ci, all, st);
-        case 4: return launch_chisq_c<4, WRITE_ALL>(intq, full, grid, smem, qh, nq, q_scale, gal, ng, L, out_scale, rpc, k, idx_base, cd, ci, all, st);
-        default:
-            set_error("chi-square: hist_len=%d exceeds the 16384 bins the kernel keeps in registers", L);
-            return FRB_ERR_UNSUPPORTED;
+    const bool full = groups == c * kChiThreads;
+#define FRB_CHI_CALL(C) \
+    launch_chisq_c<C, WRITE_ALL, G8>(intq, full, grid, smem, qh, nq, q_scale, gal, ng, L, out_scale, rpc, k, idx_base, cd, ci, all, st)
+    if (c == 1) return FRB_CHI_CALL(1);
+    if (c == 2) return FRB_CHI_CALL(2);
+    if constexpr (!G8) {                                    // 4 x 16 bins per thread would not fit the register file
+        if (c == 4) return FRB_CHI_CALL(4);
     }
+#undef FRB_CHI_CALL
+    set_error("chi-square: hist_len=%d exceeds the 16384 bins the kernel keeps in registers", L);
+    return FRB_ERR_UNSUPPORTED;
+}
+
+template <bool WRITE_ALL>
+static int launch_chisq(const uint16_t *qh, int64_t nq, int q_cell_px, const void *gal, int gallery_bytes, int64_t ng, int L,
+                        int g_cell_px, int64_t rpc, int64_t chunks, int k, int64_t idx_base, float *cd, int64_t *ci, float *all,
+                        cudaStream_t st)
+{
+    if (gallery_bytes == 1)
+        return launch_chisq_g<WRITE_ALL, true>(qh, nq, q_cell_px, gal, ng, L, g_cell_px, rpc, chunks, k, idx_base, cd, ci, all, st);
+    return launch_chisq_g<WRITE_ALL, false>(qh, nq, q_cell_px, gal, ng, L, g_cell_px, rpc, chunks, k, idx_base, cd, ci, all, st);
 }
 
 static int check_chisq_args(const char *fn, int64_t nq, int qpx, int64_t ng, int L, int gpx)
@@ -388,21 +445,22 @@ size_t frb_chisq_topk_workspace_bytes(int64_t n_query, int64_t n_gallery, int hi
     return align_up(n * sizeof(int64_t), 256) + align_up(n * sizeof(float), 256);
 }
 
-int frb_chisq_topk(const uint16_t *q_hist, int64_t n_query, int q_cell_px, const uint16_t *gallery, int64_t n_gallery,
-                   int hist_len, int g_cell_px, int k, int64_t idx_base, float *out_dist, int64_t *out_idx,
-                   void *workspace, size_t workspace_bytes, void *stream)
+static int chisq_topk_impl(const char *fn, const uint16_t *q_hist, int64_t n_query, int q_cell_px, const void *gallery,
+                           int gallery_bytes, int64_t n_gallery, int hist_len, int g_cell_px, int k, int64_t idx_base,
+                           float *out_dist, int64_t *out_idx, void *workspace, size_t workspace_bytes, void *stream)
 {
-    int rc = check_chisq_args("frb_chisq_topk", n_query, q_cell_px, n_gallery, hist_len, g_cell_px);
+    int rc = check_chisq_args(fn, n_query, q_cell_px, n_gallery, hist_len, g_cell_px);
     if (rc != FRB_OK) return rc;
-    FRB_CHECK_ARG(k >= 1 && k <= FRB_MAX_K, "frb_chisq_topk: k=%d (1..%d)", k, FRB_MAX_K);
+    FRB_CHECK_ARG(k >= 1 && k <= FRB_MAX_K, "%s: k=%d (1..%d)", fn, k, FRB_MAX_K);
+    FRB_CHECK_ARG(gallery_bytes == 2 || (hist_len % 16 == 0 && g_cell_px <= 255),
+                  "%s: a u8 gallery needs hist_len %% 16 == 0 and cell_px <= 255 (hist_len=%d, cell_px=%d)", fn, hist_len, g_cell_px);
     if (n_query == 0) return FRB_OK;
-    FRB_CHECK_ARG(q_hist && out_dist && out_idx, "frb_chisq_topk: null pointer");
-    FRB_CHECK_ARG(n_gallery == 0 || gallery, "frb_chisq_topk: null gallery");
-    FRB_CHECK_ARG(((uintptr_t)q_hist & 15) == 0 && ((uintptr_t)gallery & 15) == 0,
-                  "frb_chisq_topk: histograms must be 16-byte aligned");
+    FRB_CHECK_ARG(q_hist && out_dist && out_idx, "%s: null pointer", fn);
+    FRB_CHECK_ARG(n_gallery == 0 || gallery, "%s: null gallery", fn);
+    FRB_CHECK_ARG(((uintptr_t)q_hist & 15) == 0 && ((uintptr_t)gallery & 15) == 0, "%s: histograms must be 16-byte aligned", fn);
     size_t need = frb_chisq_topk_workspace_bytes(n_query, n_gallery, hist_len, k);
     if (!workspace || workspace_bytes < need) {
-        set_error("frb_chisq_topk: workspace %zu B < %zu B", workspace_bytes, need);
+        set_error("%s: workspace %zu B < %zu B", fn, workspace_bytes, need);
         return FRB_ERR_WORKSPACE;
     }
     int64_t rpc;
@@ -410,25 +468,56 @@ int frb_chisq_topk(const uint16_t *q_hist, int64_t n_query, int q_cell_px, const
     size_t n = (size_t)chunks * (size_t)n_query * (size_t)k;
     int64_t *ci = (int64_t *)workspace;
     float *cd = (float *)((char *)workspace + align_up(n * sizeof(int64_t), 256));
-    rc = launch_chisq<false>(q_hist, n_query, q_cell_px, gallery, n_gallery, hist_len, g_cell_px, rpc, chunks, k, idx_base,
-                             cd, ci, nullptr, (cudaStream_t)stream);
+    rc = launch_chisq<false>(q_hist, n_query, q_cell_px, gallery, gallery_bytes, n_gallery, hist_len, g_cell_px, rpc, chunks, k,
+                             idx_base, cd, ci, nullptr, (cudaStream_t)stream);
     if (rc != FRB_OK) return rc;
     return frb_topk_merge(cd, ci, (int)chunks, n_query, k, /*largest=*/0, out_dist, out_idx, stream);
+}
+
+static int chisq_dist_impl(const char *fn, const uint16_t *q_hist, int64_t n_query, int q_cell_px, const void *gallery,
+                           int gallery_bytes, int64_t n_gallery, int hist_len, int g_cell_px, float *out_dist, void *stream)
+{
+    int rc = check_chisq_args(fn, n_query, q_cell_px, n_gallery, hist_len, g_cell_px);
+    if (rc != FRB_OK) return rc;
+    FRB_CHECK_ARG(gallery_bytes == 2 || (hist_len % 16 == 0 && g_cell_px <= 255),
+                  "%s: a u8 gallery needs hist_len %% 16 == 0 and cell_px <= 255 (hist_len=%d, cell_px=%d)", fn, hist_len, g_cell_px);
+    if (n_query == 0 || n_gallery == 0) return FRB_OK;
+    FRB_CHECK_ARG(q_hist && gallery && out_dist, "%s: null pointer", fn);
+    FRB_CHECK_ARG(((uintptr_t)q_hist & 15) == 0 && ((uintptr_t)gallery & 15) == 0, "%s: histograms must be 16-byte aligned", fn);
+    int64_t rpc;
+    int64_t chunks = chi_chunks(n_query, n_gallery, &rpc);
+    return launch_chisq<true>(q_hist, n_query, q_cell_px, gallery, gallery_bytes, n_gallery, hist_len, g_cell_px, rpc, chunks, 1, 0,
+                              nullptr, nullptr, out_dist, (cudaStream_t)stream);
+}
+
+int frb_chisq_topk(const uint16_t *q_hist, int64_t n_query, int q_cell_px, const uint16_t *gallery, int64_t n_gallery,
+                   int hist_len, int g_cell_px, int k, int64_t idx_base, float *out_dist, int64_t *out_idx,
+                   void *workspace, size_t workspace_bytes, void *stream)
+{
+    return chisq_topk_impl("frb_chisq_topk", q_hist, n_query, q_cell_px, gallery, 2, n_gallery, hist_len, g_cell_px, k, idx_base,
+                           out_dist, out_idx, workspace, workspace_bytes, stream);
+}
+
+int frb_chisq_topk_g8(const uint16_t *q_hist, int64_t n_query, int q_cell_px, const uint8_t *gallery, int64_t n_gallery,
+                      int hist_len, int g_cell_px, int k, int64_t idx_base, float *out_dist, int64_t *out_idx,
+                      void *workspace, size_t workspace_bytes, void *stream)
+{
+    return chisq_topk_impl("frb_chisq_topk_g8", q_hist, n_query, q_cell_px, gallery, 1, n_gallery, hist_len, g_cell_px, k,
+                           idx_base, out_dist, out_idx, workspace, workspace_bytes, stream);
 }
 
 int frb_chisq_dist(const uint16_t *q_hist, int64_t n_query, int q_cell_px, const uint16_t *gallery, int64_t n_gallery,
                    int hist_len, int g_cell_px, float *out_dist, void *stream)
 {
-    int rc = check_chisq_args("frb_chisq_dist", n_query, q_cell_px, n_gallery, hist_len, g_cell_px);
-    if (rc != FRB_OK) return rc;
-    if (n_query == 0 || n_gallery == 0) return FRB_OK;
-    FRB_CHECK_ARG(q_hist && gallery && out_dist, "frb_chisq_dist: null pointer");
-    FRB_CHECK_ARG(((uintptr_t)q_hist & 15) == 0 && ((uintptr_t)gallery & 15) == 0,
-                  "frb_chisq_dist: histograms must be 16-byte aligned");
-    int64_t rpc;
-    int64_t chunks = chi_chunks(n_query, n_gallery, &rpc);
-    return launch_chisq<true>(q_hist, n_query, q_cell_px, gallery, n_gallery, hist_len, g_cell_px, rpc, chunks, 1, 0, nullptr,
-                              nullptr, out_dist, (cudaStream_t)stream);
+    return chisq_dist_impl("frb_chisq_dist", q_hist, n_query, q_cell_px, gallery, 2, n_gallery, hist_len, g_cell_px, out_dist,
+                           stream);
+}
+
+int frb_chisq_dist_g8(const uint16_t *q_hist, int64_t n_query, int q_cell_px, const uint8_t *gallery, int64_t n_gallery,
+                      int hist_len, int g_cell_px, float *out_dist, void *stream)
+{
+    return chisq_dist_impl("frb_chisq_dist_g8", q_hist, n_query, q_cell_px, gallery, 1, n_gallery, hist_len, g_cell_px, out_dist,
+                           stream);
 }
 
 }  // extern "C"

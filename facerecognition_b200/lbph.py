@@ -46,13 +46,23 @@ def _as_gray_u8(img) -> np.ndarray:
     return np.ascontiguousarray(a)
 
 
+def _cat_rows(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Row-wise concatenation of two count matrices of the same dtype (u8, or u16 through its int16 view)."""
+    assert a.dtype == b.dtype
+    if a.dtype == torch.uint16:
+        return torch.cat([a.view(torch.int16), b.view(torch.int16)], 0).view(torch.uint16)
+    return torch.cat([a, b], 0)
+
+
 class _Group:
     """Gallery rows that share a cell size (same image shape class)."""
 
     __slots__ = ("cell_px", "hist", "rows")
 
     def __init__(self, cell_px: int, hist: torch.Tensor, rows: torch.Tensor):
-        self.cell_px, self.hist, self.rows = cell_px, hist, rows  # hist u16 [n, L]; rows int64 [n] global row ids
+        # hist [n, L]: u8 counts when cell_px <= 255 (ops.compact_histograms: half the bytes the scan streams), else u16;
+        # rows int64 [n] global row ids
+        self.cell_px, self.hist, self.rows = cell_px, hist, rows
 
 
 class LBPHFaceRecognizer:
@@ -130,9 +140,10 @@ class LBPHFaceRecognizer:
         base = self.size
         for pos, hist, px in self._hist_by_shape(faces):
             rows = torch.tensor([base + i for i in pos], dtype=torch.int64, device=self.device)
+            hist = ops.compact_histograms(hist, px)
             for g in self._groups:
                 if g.cell_px == px:
-                    g.hist = torch.cat([g.hist.view(torch.int16), hist.view(torch.int16)], 0).view(torch.uint16)
+                    g.hist = _cat_rows(g.hist, hist)
                     g.rows = torch.cat([g.rows, rows], 0)
                     break
             else:
@@ -141,9 +152,10 @@ class LBPHFaceRecognizer:
 
     def set_gallery(self, hist_u16: torch.Tensor, cell_px: int, labels) -> None:
         """Adopt precomputed integer histograms (e.g. one shard of a distributed gallery)."""
-        assert hist_u16.dtype == torch.uint16 and hist_u16.dim() == 2 and hist_u16.shape[1] == self.hist_len
+        assert hist_u16.dtype in (torch.uint16, torch.uint8) and hist_u16.dim() == 2 and hist_u16.shape[1] == self.hist_len
         n = hist_u16.shape[0]
-        self._groups = [_Group(int(cell_px), hist_u16.contiguous(), torch.arange(n, dtype=torch.int64, device=hist_u16.device))]
+        hist = hist_u16.contiguous() if hist_u16.dtype == torch.uint8 else ops.compact_histograms(hist_u16.contiguous(), int(cell_px))
+        self._groups = [_Group(int(cell_px), hist, torch.arange(n, dtype=torch.int64, device=hist_u16.device))]
         self._labels = np.asarray(labels).astype(np.int32).reshape(-1)
         assert self._labels.shape[0] == n
 
@@ -229,7 +241,7 @@ class LBPHFaceRecognizer:
         px = np.zeros((self.size,), np.int32)
         for g in self._groups:
             rows = g.rows.cpu().numpy()
-            hist[rows] = g.hist.cpu().numpy()
+            hist[rows] = g.hist.cpu().numpy().astype(np.uint16)
             px[rows] = g.cell_px
         return hist, px
 

@@ -284,11 +284,19 @@ def lbp_hist(images: torch.Tensor, radius: int = 1, neighbors: int = 8, grid_x: 
     return out, cell_px.value
 
 
+def compact_histograms(hist_u16: torch.Tensor, cell_px: int) -> torch.Tensor:
+    """u16 cell histograms -> the u8 gallery form the chi-square kernels also read (exact: every count <= cell_px <= 255);
+    returns the input unchanged when the counts do not fit a byte or the row length is not a multiple of 16."""
+    if cell_px > 255 or hist_u16.shape[1] % 16 != 0:
+        return hist_u16
+    return hist_u16.view(torch.int16).to(torch.uint8)
+
+
 def chisq_topk(q_hist: torch.Tensor, q_cell_px: int, gallery: torch.Tensor, g_cell_px: int, k: int = 1,
                idx_base: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
-    """frb_chisq_topk: u16 [Q, L] vs u16 [N, L] -> (dist fp32 [Q, k] ascending, idx int64 [Q, k])."""
+    """frb_chisq_topk / frb_chisq_topk_g8: u16 [Q, L] vs u16 or u8 [N, L] -> (dist fp32 [Q, k] ascending, idx int64 [Q, k])."""
     dev = _require_cuda(q_hist, gallery)
-    assert q_hist.dtype == torch.uint16 and gallery.dtype == torch.uint16 and q_hist.dim() == 2 and gallery.dim() == 2
+    assert q_hist.dtype == torch.uint16 and gallery.dtype in (torch.uint16, torch.uint8) and q_hist.dim() == 2 and gallery.dim() == 2
     q, hist_len, n = q_hist.shape[0], q_hist.shape[1], gallery.shape[0]
     assert n == 0 or gallery.shape[1] == hist_len
     dist = torch.empty((q, k), dtype=torch.float32, device=dev)
@@ -296,18 +304,20 @@ def chisq_topk(q_hist: torch.Tensor, q_cell_px: int, gallery: torch.Tensor, g_ce
     with torch.cuda.device(dev):
         ws_bytes = N.lib.frb_chisq_topk_workspace_bytes(q, n, hist_len, k)
         ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=dev)
-        N.call("frb_chisq_topk", _p(q_hist), _I64(q), q_cell_px, _p(gallery), _I64(n), hist_len, g_cell_px, k,
+        N.call("frb_chisq_topk" if gallery.dtype == torch.uint16 else "frb_chisq_topk_g8", _p(q_hist), _I64(q), q_cell_px,
+               _p(gallery), _I64(n), hist_len, g_cell_px, k,
                _I64(idx_base), _p(dist), _p(idx), _p(ws), ctypes.c_size_t(ws.numel()), _stream(dev))
     return dist, idx
 
 
 def chisq_dist(q_hist: torch.Tensor, q_cell_px: int, gallery: torch.Tensor, g_cell_px: int) -> torch.Tensor:
-    """frb_chisq_dist: all distances, fp32 [Q, N]."""
+    """frb_chisq_dist / frb_chisq_dist_g8: all distances, fp32 [Q, N]; the gallery may hold u16 or u8 counts."""
     dev = _require_cuda(q_hist, gallery)
-    assert q_hist.dtype == torch.uint16 and gallery.dtype == torch.uint16
+    assert q_hist.dtype == torch.uint16 and gallery.dtype in (torch.uint16, torch.uint8)
     q, hist_len, n = q_hist.shape[0], q_hist.shape[1], gallery.shape[0]
     out = torch.empty((q, n), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        N.call("frb_chisq_dist", _p(q_hist), _I64(q), q_cell_px, _p(gallery), _I64(n), hist_len, g_cell_px, _p(out),
+        N.call("frb_chisq_dist" if gallery.dtype == torch.uint16 else "frb_chisq_dist_g8", _p(q_hist), _I64(q), q_cell_px,
+               _p(gallery), _I64(n), hist_len, g_cell_px, _p(out),
                _stream(dev))
     return out

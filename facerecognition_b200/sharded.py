@@ -144,7 +144,8 @@ def cosine_sharded(gallery_shard: torch.Tensor, row_offset: int, *, qnorm_mode: 
 
 def chisq_sharded(hist_shard: torch.Tensor, cell_px: int, row_offset: int, *, q_cell_px: Optional[int] = None,
                   group: Optional[dist.ProcessGroup] = None, peer_exchange: bool = True) -> ShardedSearch:
-    """Product wiring for K3: u16 histogram shard; queries are u16 histograms [Q, L]."""
+    """Product wiring for K3: histogram shard of u16 counts, or u8 (ops.compact_histograms) when cell_px <= 255;
+    queries are u16 histograms [Q, L]."""
     from . import ops
 
     def local(q_hist: torch.Tensor, k: int):

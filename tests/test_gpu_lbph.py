@@ -350,3 +350,48 @@ def test_predict_device_frames_equals_the_host_preprocessing(oracle_lbph):
         lab, conf = model.predict(host[j])
         assert int(model.getLabels()[int(idx[j, 0]), 0]) == lab and float(dist[j, 0]) == pytest.approx(conf, rel=1e-6, abs=1e-12)
     assert (dist[:8, 0] == 0).all()
+
+
+@pytest.mark.parametrize("L,N,Q,px,q_px", [(16384, 700, 5, 169, 169), (16384, 300, 3, 144, 169), (4096, 257, 4, 255, 255),
+                                           (2064, 90, 2, 36, 36), (16, 40, 3, 9, 9), (12288, 130, 2, 100, 121)])
+def test_chisq_u8_gallery_matches_oracle_and_u16_path(oracle_lbph, L, N, Q, px, q_px):
+    """frb_chisq_*_g8: the gallery stored as u8 counts (cell_px <= 255) gives the oracle's distances (<= 1e-5), the
+    same nearest rows as the u16 gallery, exactly 0 for a self match, first row on ties; full and partial register
+    coverage (L = 16384 / others), equal and different cell sizes."""
+    from facerecognition_b200 import ops
+    rng = np.random.default_rng(L + N)
+    gal = rng.multinomial(px, np.ones(256) / 256, size=(N, (L + 255) // 256)).reshape(N, -1)[:, :L].astype(np.uint16) \
+        if L >= 256 else rng.integers(0, px + 1, (N, L)).astype(np.uint16)
+    gal[N // 2] = gal[3]                                    # duplicate row: the first one must win
+    q = gal[rng.integers(0, N, Q)].copy()
+    q[0] = gal[3]
+    if q_px != px:
+        q = np.minimum(q.astype(np.int64) * q_px // px, q_px).astype(np.uint16)
+    g16, g8 = dev(gal), ops.compact_histograms(dev(gal), px)
+    assert g8.dtype == torch.uint8
+    ref = np.stack([oracle_lbph.c_chisq_scan_u16(gal, px, qq, q_px) for qq in q])
+    d8 = ops.chisq_dist(dev(q), q_px, g8, px).cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(d8, ref, rtol=1e-5, atol=0)
+    for k in (1, 4):
+        dist8, idx8 = ops.chisq_topk(dev(q), q_px, g8, px, k=k, idx_base=1000)
+        dist16, idx16 = ops.chisq_topk(dev(q), q_px, g16, px, k=k, idx_base=1000)
+        order = np.argsort(ref, axis=1, kind="stable")[:, :k]
+        gaps_ok = np.take_along_axis(ref, order, 1)
+        np.testing.assert_allclose(dist8.cpu().numpy(), gaps_ok, rtol=1e-5, atol=0)
+        assert torch.equal(idx8[:, 0], idx16[:, 0])
+    if q_px == px:
+        d, i = ops.chisq_topk(dev(q[:1]), q_px, g8, px, k=1)
+        assert float(d[0, 0]) == 0.0 and int(i[0, 0]) == 3
+
+
+def test_chisq_u8_gallery_limits():
+    from facerecognition_b200 import ops, _native as NV
+    q = torch.zeros((1, 4096), dtype=torch.int16, device="cuda").view(torch.uint16)
+    g = torch.zeros((4, 4096), dtype=torch.uint8, device="cuda")
+    with pytest.raises(NV.FrbError):
+        ops.chisq_topk(q, 300, g, 300, k=1)                 # counts up to 300 do not fit a byte
+    q24 = torch.zeros((1, 24), dtype=torch.int16, device="cuda").view(torch.uint16)
+    with pytest.raises(NV.FrbError):
+        ops.chisq_topk(q24, 9, torch.zeros((4, 24), dtype=torch.uint8, device="cuda"), 9, k=1)   # 24 % 16 != 0
+    h16 = torch.zeros((2, 24), dtype=torch.int16, device="cuda").view(torch.uint16)
+    assert ops.compact_histograms(h16, 9).dtype == torch.uint16 and ops.compact_histograms(h16, 300).dtype == torch.uint16
