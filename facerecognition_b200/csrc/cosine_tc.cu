@@ -43,6 +43,8 @@ constexpr int kTcPrefetchDist = 6;  // gallery tiles (256 rows = 256 KB) kept ah
 // before their demand load arrives -- measured 1.78x the gallery in DRAM reads and 3.9 TB/s instead of 6.1 TB/s
 // (profiles/r1_tc_prefetch_sweep.txt).  The distance shrinks to fit this budget; 0 turns the prefetch off.
 constexpr size_t kTcPrefetchL2Budget = 8u << 20;
+constexpr int kTcShareMinK = 8;          // lists longer than this exchange share-of-k bounds (TcParams::share)
+constexpr int kTcShareMaxGroups = 64;    // ... when a pass has at most this many gallery groups (one coalesced load each per tile)
 constexpr size_t kTcSmemLimit = 227 * 1024;
 
 struct TcBarriers {
@@ -219,6 +221,10 @@ __device__ __forceinline__ void atomic_max_f32(float *addr, float v)
     else
         atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
 }
+__device__ __forceinline__ void st_relaxed_f32(float *addr, float v)
+{
+    asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
 __device__ __forceinline__ float ld_relaxed_f32(const float *addr)
 {
     float v;
@@ -236,6 +242,13 @@ struct TcParams {
     int prefetch_dist;     // gallery tiles prefetched into L2 ahead of the TMA loads (0 = off)
     int64_t idx_base;
     float *thr;            // [n_query] shared admission thresholds, -inf on entry
+    // Long lists (k > 8) only.  share[g * n_query + q] = one ulp below the share_rank-th best score that the unit
+    // (q's tile, gallery group g) has seen, share_rank = ceil(k / n_groups); bytes 0xFF = not published yet.  The
+    // groups are disjoint row ranges, so the minimum over g is reached by n_groups * share_rank >= k rows: a valid
+    // lower bound on the final k-th best that is as tight as ONE list over all rows seen so far, whereas the maximum
+    // of the units' own k-th bests (thr) is only as tight as a list over 1/n_groups of them.  NULL: not used.
+    float *share;
+    int share_rank;
     int *cand_cnt;         // [n_query] candidates appended so far, 0 on entry
     int64_t cand_cap;      // slots per query = (total groups) * k: every unit can always append its whole list
     float *cand_scores;    // [n_query, cand_cap] unordered
@@ -387,6 +400,7 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             float gthr = q_live ? ld_relaxed_f32(p.thr + q) : INFINITY;  // dead rows admit nothing
             float adm = gthr;                                        // admit v > adm = max(kth, gthr)
             float published = gthr;
+            float pub_share = -INFINITY;
             for (int64_t t = t0; t < t1; t++) {
                 mbar_wait(&bars->tmem_full[acc], acc_phase);
                 tcgen05_fence_after();
@@ -430,7 +444,21 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 // exchange thresholds once per tile: publish ours if it improved, pick up the others'
                 if (q_live) {
-                    const float mine = next_below(kth);
+                    float mine = next_below(kth);
+                    if (RS >= 16 && p.share) {
+                        float *slot = p.share + q;   // [group][query]: a warp's 32 queries share sectors
+                        const float part = next_below(reg_kth<RS>(rs, p.share_rank));
+                        if (part > pub_share) {
+                            st_relaxed_f32(slot + grp * p.n_query, part);
+                            pub_share = part;
+                        }
+                        float m = INFINITY;
+                        for (int64_t g = 0; g < p.n_groups; g++) {
+                            const float v = ld_relaxed_f32(slot + g * p.n_query);
+                            m = (__float_as_uint(v) == 0xFFFFFFFFu) ? -INFINITY : fminf(m, v);
+                        }
+                        mine = fmaxf(mine, m);
+                    }
                     if (mine > published) {
                         atomic_max_f32(p.thr + q, mine);
                         published = mine;
@@ -528,7 +556,7 @@ struct TcPass {
 struct TcPlan {
     int64_t n_qtiles, n_tiles, n_groups;  // n_groups = total candidate lists per query
     TcPass warm, main;                     // warm.n_groups == 0: single pass
-    size_t qbf16_bytes, thr_bytes, cnt_bytes, idx_bytes, score_bytes;
+    size_t qbf16_bytes, thr_bytes, cnt_bytes, share_bytes, idx_bytes, score_bytes;
 };
 
 static void tc_split(int64_t tile_begin, int64_t tile_end, int64_t want_groups, int64_t group_base, TcPass *ps)
@@ -574,12 +602,20 @@ static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
     if (units_per_cta < 1) units_per_cta = 1;
     if (units_per_cta > 16) units_per_cta = 16;
     int64_t want_groups = ((int64_t)sms * units_per_cta + pl.n_qtiles - 1) / pl.n_qtiles;
+    if (k > kTcShareMinK) {
+        // long lists: every unit warms its own k-slot list (~k ln(rows / k) slow-path insertions per query and unit), so
+        // few long units -- at most two per CTA, and never a third round (floor, not ceil)
+        if (units_per_cta > 2) units_per_cta = 2;
+        want_groups = ((int64_t)sms * units_per_cta) / pl.n_qtiles;
+        if (want_groups < 1) want_groups = 1;
+    }
     if (want_groups > 1024) want_groups = 1024;
     tc_split(warm_tiles, pl.n_tiles, want_groups, pl.warm.n_groups, &pl.main);
     pl.n_groups = pl.warm.n_groups + pl.main.n_groups;
     size_t n = (size_t)pl.n_groups * (size_t)nq * (size_t)k;
     pl.qbf16_bytes = align_up((size_t)pl.n_qtiles * kTcBlockM * (size_t)dim * 2, 1024);
     pl.thr_bytes = align_up((size_t)nq * sizeof(float), 256);
+    pl.share_bytes = k > kTcShareMinK ? align_up((size_t)nq * 2 * kTcShareMaxGroups * sizeof(float), 256) : 0;  // one array per pass
     pl.cnt_bytes = align_up((size_t)nq * sizeof(int), 256);
     pl.idx_bytes = align_up(n * sizeof(int64_t), 256);
     pl.score_bytes = align_up(n * sizeof(float), 256);
@@ -589,7 +625,7 @@ static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
 size_t cosine_tc_workspace_bytes(int64_t n_query, int64_t n_gallery, int dim, int k)
 {
     TcPlan pl = tc_plan(n_query, n_gallery, dim, k);
-    return pl.qbf16_bytes + pl.thr_bytes + pl.cnt_bytes + pl.idx_bytes + pl.score_bytes;
+    return pl.qbf16_bytes + pl.thr_bytes + pl.cnt_bytes + pl.share_bytes + pl.idx_bytes + pl.score_bytes;
 }
 
 int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16, int64_t ng, int dim, int qnorm_mode, int k,
@@ -612,13 +648,15 @@ int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16,
     __nv_bfloat16 *qb = (__nv_bfloat16 *)w;
     float *thr = (float *)(w + pl.qbf16_bytes);
     int *cnt = (int *)(w + pl.qbf16_bytes + pl.thr_bytes);
-    int64_t *ci = (int64_t *)(w + pl.qbf16_bytes + pl.thr_bytes + pl.cnt_bytes);
-    float *cs = (float *)(w + pl.qbf16_bytes + pl.thr_bytes + pl.cnt_bytes + pl.idx_bytes);
+    float *share = (float *)(w + pl.qbf16_bytes + pl.thr_bytes + pl.cnt_bytes);
+    int64_t *ci = (int64_t *)(w + pl.qbf16_bytes + pl.thr_bytes + pl.cnt_bytes + pl.share_bytes);
+    float *cs = (float *)(w + pl.qbf16_bytes + pl.thr_bytes + pl.cnt_bytes + pl.share_bytes + pl.idx_bytes);
 
     // prologue: L2-normalise in fp32, round to bf16 (rows beyond n_query are never read: TMA zero-fills)
     // the same launch resets the shared admission thresholds (-inf) and the candidate counters (0)
     int rc = normalize_rows_impl(queries, nq, dim, qnorm_mode, qb, FRB_BF16, thr, cnt, st);
     if (rc != FRB_OK) return rc;
+    if (pl.share_bytes) FRB_CUDA_OK(cudaMemsetAsync(share, 0xFF, pl.share_bytes, st));   // 0xFFFFFFFF = not published
 
     CUtensorMap tq, tg, tpf;
     rc = make_bf16_map(&tq, qb, nq, dim, kTcBlockM);
@@ -674,6 +712,9 @@ int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16,
         if (ps.n_groups == 0) continue;
         p.tiles_per_group = ps.tiles_per_group;
         p.n_groups = ps.n_groups;
+        const bool use_share = pl.share_bytes && ps.n_groups >= 2 && ps.n_groups <= kTcShareMaxGroups;
+        p.share = use_share ? share + (size_t)ip * nq * kTcShareMaxGroups : nullptr;
+        p.share_rank = use_share ? (int)((k + ps.n_groups - 1) / ps.n_groups) : k;
         p.tile_begin = ps.tile_begin;
         p.tile_end = ng > 0 ? ps.tile_end : ps.tile_begin;  // empty gallery: units run with no tiles and emit empty lists
         const int64_t n_units = pl.n_qtiles * ps.n_groups;

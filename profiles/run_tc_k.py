@@ -7,7 +7,7 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 g = torch.Generator(device='cuda').manual_seed(1)
 gal = ops.normalize_rows(torch.randn((n, 512), generator=g, device='cuda'), NV.FRB_QNORM_CLAMP, torch.bfloat16)
 q = gal[torch.randint(0, n, (nq,), generator=g, device='cuda')].float() + 0.03 * torch.randn((nq, 512), generator=g, device='cuda')
-for k in (1, 5, 8, 10, 16, 32, 64):
+for k in (5, 8, 16, 32, 64):
     for _ in range(2):
         ops.cosine_topk(q, gal, k, qnorm_mode=NV.FRB_QNORM_CLAMP)
     torch.cuda.synchronize()
