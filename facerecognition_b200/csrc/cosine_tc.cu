@@ -175,6 +175,22 @@ __device__ __forceinline__ void reg_insert(float (&s)[RK], int (&id)[RK], float 
     }
 }
 
+// Long lists: admitted (score, column) pairs wait in a per-lane queue and are inserted by the whole warp at once
+// (see the epilogue).  A lane without an r-th pending entry re-inserts its own last slot, which is a no-op.
+constexpr int kTcQueue = 4;
+template <int RS>
+__device__ __forceinline__ void drain_queue(float (&rs)[RS], int (&ri)[RS], const float (&qv)[kTcQueue], const int (&qi)[kTcQueue],
+                                            int &qn)
+{
+#pragma unroll
+    for (int r = 0; r < kTcQueue; r++) {
+        if (!__any_sync(0xffffffffu, r < qn)) break;
+        const bool has = r < qn;
+        reg_insert<RS>(rs, ri, has ? qv[r] : rs[RS - 1], has ? qi[r] : ri[RS - 1]);
+    }
+    qn = 0;
+}
+
 // v[j] for a run-time j without spilling v[] to local memory: 5-level select tree (31 SEL)
 __device__ __forceinline__ float select32(const float *v, int j)
 {
@@ -379,6 +395,12 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // otherwise a local-memory list (k up to FRB_MAX_K), touched only on admissions.
         constexpr bool REG_LIST = RK > 0;
         constexpr int RS = REG_LIST ? RK : 1;
+        constexpr bool QUEUED = RK >= 16;   // long register lists take admissions through a per-lane queue
+        float qv[kTcQueue];
+        int qi[kTcQueue];
+        int qn = 0;
+#pragma unroll
+        for (int r = 0; r < kTcQueue; r++) { qv[r] = -INFINITY; qi[r] = -1; }
         float rs[RS];
         int ri[RS];
         float best_s[REG_LIST ? 1 : FRB_MAX_K];
@@ -416,7 +438,39 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 32; j++) v[j] = (c0 + j < valid) ? v[j] : -INFINITY;
                     }
-                    if (max32(v) > adm) {   // rare once the thresholds have warmed up
+                    if (QUEUED) {
+                        // Long lists: a sorted insert is ~6 RS instructions and, done where the candidate is found, the
+                        // whole warp pays for ONE lane's insert.  Lanes park their admitted scores in a 4-slot queue
+                        // instead; when any lane's queue is full every lane drains its own, so one pass of the insert
+                        // code serves up to 32 candidates.  Thresholds move only at a drain: a score admitted against a
+                        // stale threshold is inserted and falls off the end of the list -- redundant, never wrong.
+                        if (__any_sync(0xffffffffu, max32(v) > adm)) {
+                            uint32_t cand = 0;
+#pragma unroll
+                            for (int j = 0; j < 32; j++) cand |= (v[j] > adm) ? (1u << j) : 0u;
+                            while (__any_sync(0xffffffffu, cand != 0)) {
+                                if (cand) {
+                                    const int j = __ffs(cand) - 1;
+                                    cand &= cand - 1;
+                                    const float x = select32(v, j);
+                                    if (x > adm) {
+                                        const int id = col0 + c0 + j;
+#pragma unroll
+                                        for (int r = 0; r < kTcQueue; r++) {
+                                            qv[r] = (qn == r) ? x : qv[r];
+                                            qi[r] = (qn == r) ? id : qi[r];
+                                        }
+                                        qn++;
+                                    }
+                                }
+                                if (__any_sync(0xffffffffu, qn == kTcQueue)) {
+                                    drain_queue<RS>(rs, ri, qv, qi, qn);
+                                    kth = reg_kth<RS>(rs, p.k);
+                                    adm = fmaxf(kth, gthr);
+                                }
+                            }
+                        }
+                    } else if (max32(v) > adm) {   // rare once the thresholds have warmed up
                         // candidate mask first (straight-line), then visit this lane's candidates in column
                         // order; the warp iterates max-popcount times instead of walking 32 branchy checks
                         uint32_t cand = 0;
@@ -467,6 +521,7 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     adm = fmaxf(kth, gthr);
                 }
             }
+            if (QUEUED && __any_sync(0xffffffffu, qn > 0)) drain_queue<RS>(rs, ri, qv, qi, qn);
             if (q_live) {
                 // append this unit's admitted rows to the query's compact candidate buffer
                 int nv = 0;

@@ -91,9 +91,9 @@ def cosine_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, *, score_m
 # two unit vectors moves their inner product by at most 2 * 2^-8 + 2^-16 = 0.00783 (Cauchy-Schwarz), and
 # cosine_similarity()'s raw-dot branch (both norms within 1e-3 of 1) differs from the true cosine by at most 0.002
 REFINE_EPS = 0.0105
-# measured (profiles/run_refine.py): 4096 q x 1M rows 12.7 ms vs 131.7 ms for the fp32 tiled kernel, but 256 q x 1M
-# 17.9 ms vs 8.0 ms (a 64-slot list has to warm up in every (query tile, gallery group) unit): large batches only
-REFINE_MIN_QUERIES = 1024
+# measured (profiles/run_refine.py, 1M fp32 rows): 4096 queries 5.5 ms vs 132 ms for the fp32 tiled kernel, 256 queries
+# 4.1 ms vs 7.7 ms (a 64-slot list warms up in every (query tile, gallery group) unit, which small batches have many of)
+REFINE_MIN_QUERIES = 256
 REFINE_MIN_ROWS = 65536
 
 

@@ -375,7 +375,7 @@ def test_tensor_core_first_pass_plus_exact_rescore_equals_the_exact_kernel(N, Q,
 
 
 def test_engine_batches_on_a_large_gallery_use_the_first_pass_and_agree_with_single_queries():
-    """RecognitionEngine.recognize_embeddings with >= 1024 queries over a 70k-identity dict DB takes the tensor-core
+    """RecognitionEngine.recognize_embeddings with a large batch (>= ops.REFINE_MIN_QUERIES) over a 70k-identity dict DB takes the tensor-core
     first pass + exact re-score; each answer must equal the single-query (row-streaming, exact) answer."""
     import facerecognition_b200 as F
     from facerecognition_b200 import ops
