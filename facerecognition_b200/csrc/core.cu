@@ -481,12 +481,12 @@ __device__ __forceinline__ void merge_scan(float *s, int64_t *id, int k, const C
 
 // k rounds of warp arg-best over the lanes' sorted lists; lane 0 stores round r through (os, oi)
 template <bool LARGEST>
-__device__ __forceinline__ void merge_extract(const float *s, const int64_t *id, int k, int lane, float *os, int64_t *oi)
+__device__ __forceinline__ void merge_extract(const float *s, const int64_t *id, int kl, int k, int lane, float *os, int64_t *oi)
 {
     int head = 0;
     for (int r = 0; r < k; r++) {
-        float v = head < k ? s[head] : worst_value<LARGEST>();
-        int64_t idx = head < k ? id[head] : -1;
+        float v = head < kl ? s[head] : worst_value<LARGEST>();
+        int64_t idx = head < kl ? id[head] : -1;
         const int64_t mine = idx;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -511,19 +511,26 @@ __device__ __forceinline__ void merge_query(const Cands &c, int64_t n, int k, fl
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float s[FRB_MAX_K];
     int64_t id[FRB_MAX_K];
-    list_init<LARGEST>(s, id, k);
+    // a lane sees at most ceil(n / stride) candidates: its private list need not be longer (k = 64 with ~26 candidates
+    // per lane spent most of its time shifting empty slots in local memory)
+    const int stride = 32 * WQ;
+    int kl = (int)((n + stride - 1) / stride);
+    kl = kl < 1 ? 1 : (kl > k ? k : kl);
+    list_init<LARGEST>(s, id, kl);
     if (WQ == 1) {
-        merge_scan<LARGEST>(s, id, k, c, lane, n, 32);
-        merge_extract<LARGEST>(s, id, k, lane, os, oi);
+        merge_scan<LARGEST>(s, id, kl, c, lane, n, 32);
+        merge_extract<LARGEST>(s, id, kl, k, lane, os, oi);
     } else {
-        merge_scan<LARGEST>(s, id, k, c, threadIdx.x, n, 32 * WQ);
-        merge_extract<LARGEST>(s, id, k, lane, sh_s + warp * k, sh_i + warp * k);
+        merge_scan<LARGEST>(s, id, kl, c, threadIdx.x, n, stride);
+        merge_extract<LARGEST>(s, id, kl, k, lane, sh_s + warp * k, sh_i + warp * k);
         __syncthreads();
         if (warp == 0) {
-            list_init<LARGEST>(s, id, k);
+            int k2 = (WQ * k + 31) / 32;
+            k2 = k2 > k ? k : k2;
+            list_init<LARGEST>(s, id, k2);
             const CompactCands mine = {sh_s, sh_i};
-            merge_scan<LARGEST>(s, id, k, mine, lane, (int64_t)WQ * k, 32);
-            merge_extract<LARGEST>(s, id, k, lane, os, oi);
+            merge_scan<LARGEST>(s, id, k2, mine, lane, (int64_t)WQ * k, 32);
+            merge_extract<LARGEST>(s, id, k2, k, lane, os, oi);
         }
     }
 }
