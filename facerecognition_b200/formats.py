@@ -163,7 +163,8 @@ def read_lbph_model(model, filename: str) -> None:
     from .lbph import _Group
     for px, rows in by_px.items():
         counts = np.round(np.stack([hists[i] for i in rows]).astype(np.float64) * px).astype(np.uint16)
-        model._groups.append(_Group(px, torch.from_numpy(counts).to(model.device),
+        from . import ops
+        model._groups.append(_Group(px, ops.compact_histograms(torch.from_numpy(counts).to(model.device), px),
                                     torch.tensor(rows, dtype=torch.int64, device=model.device)))
 
 

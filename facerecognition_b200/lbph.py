@@ -47,8 +47,9 @@ def _as_gray_u8(img) -> np.ndarray:
 
 
 def _cat_rows(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """Row-wise concatenation of two count matrices of the same dtype (u8, or u16 through its int16 view)."""
-    assert a.dtype == b.dtype
+    """Row-wise concatenation of two count matrices (u8, or u16 through its int16 view; a u8 / u16 mix widens to u16)."""
+    if a.dtype != b.dtype:
+        a, b = (t if t.dtype == torch.uint16 else t.to(torch.int16).view(torch.uint16) for t in (a, b))
     if a.dtype == torch.uint16:
         return torch.cat([a.view(torch.int16), b.view(torch.int16)], 0).view(torch.uint16)
     return torch.cat([a, b], 0)

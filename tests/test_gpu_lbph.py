@@ -179,6 +179,11 @@ def test_recognizer_protocol_matches_oracle(oracle_lbph, lbph_golden, tmp_path):
     m2 = F.LBPHFaceRecognizer_create()
     m2.read(p)
     assert m2.size == model.size and m2.predict(fresh[3]) == model.predict(fresh[3])
+    # a model that was read back keeps the compact (u8) gallery form and can still be updated
+    assert all(g.hist.dtype == torch.uint8 for g in m2._groups) and all(g.hist.dtype == torch.uint8 for g in model._groups)
+    m2.update([fresh[5]], np.array([4242], np.int32))
+    assert m2.predict(fresh[5]) == (4242, 0.0) and m2.size == model.size + 1
+    np.testing.assert_array_equal(m2.get_histograms_u16()[0][:model.size], model.get_histograms_u16()[0])
     with pytest.raises(F.lbph.LBPHError):
         F.LBPHFaceRecognizer_create().predict(faces[0])
     with pytest.raises(F.lbph.LBPHError):
