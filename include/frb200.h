@@ -80,7 +80,7 @@ typedef enum frb_kernel {
     FRB_K_COUNT = 7
 } frb_kernel;
 
-/* When enabled, every launch of the four hot kernels is bracketed by a CUDA event pair on the
+/* When enabled, every launch of the kernels listed above is bracketed by a CUDA event pair on the
  * launching stream (what bench.py's roofline line is computed from).  Off by default. */
 int frb_profile_enable(int on);
 /* Waits for the recorded launches of `kernel` to finish, returns their summed device time and count,
