@@ -145,3 +145,31 @@ def test_resize_restatement_is_bit_exact_with_the_installed_cv2():
         assert np.array_equal(OR.resize_linear_u8(ramp, *dsize), cv2.resize(ramp, dsize))
         full = np.full((77, 91, 3), 255, np.uint8)
         assert np.array_equal(OR.resize_linear_u8(full, *dsize), cv2.resize(full, dsize))
+
+
+def test_chisq_filter_statement_is_complete(oracle_lbph):
+    """oracle/chisq_filter.py (the planned tensor-core candidate filter, stated on the CPU): with fp16 rank-8 features the
+    rigorous bound holds for every (query, row) pair and the filtered nearest neighbour equals the exhaustive one —
+    for planted queries, unplanted ones and exact duplicates (lowest row wins)."""
+    from oracle import chisq_filter as CF
+    rng = np.random.default_rng(12)
+    faces = rng.integers(0, 256, (260, 100, 100), dtype=np.uint8)
+    faces[:, 20:60] //= 3                                    # some structure: darker band
+    hist, px = oracle_lbph.c_lbp_hist(faces)
+    gallery, fresh = hist[:200].copy(), hist[200:]
+    gallery[150] = gallery[7]                                # duplicate row
+    u, v, err = CF.feature_tables(px, 8, np.float16)
+    assert err.max() < 0.1 and err[0].max() == 0 and err[:, 0].max() == 0      # empty bins are exact
+    queries = [gallery[7], gallery[33]] + list(fresh[:10])
+    survivors = []
+    for q in queries:
+        exact = CF.exact_distances(gallery, q)
+        approx = CF.approx_distances(gallery, q, u, v)
+        assert np.abs(approx - exact).max() <= CF.eps_bound(q, err) + 1e-6
+        row, d, kept = CF.filtered_nearest(gallery, q, u, v, err)
+        assert row == int(np.argmin(exact)) and d == exact.min()
+        survivors.append(kept)
+    assert survivors[0] <= 3 and survivors[1] <= 3           # planted: the duplicate pair / the row itself survive
+    # the count-unit distance is the kernels' distance up to the 2 / cell_px scale
+    ref = oracle_lbph.c_chisq_scan_u16(gallery, px, queries[2], px)
+    np.testing.assert_allclose(CF.exact_distances(gallery, queries[2]) * (2.0 / px), ref, rtol=1e-6)   # the C oracle works on OpenCV's float32 view
