@@ -45,11 +45,14 @@ METRIC = "queries/sec @1M-512d cosine top-5"
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
+    fallback = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+    try:
         d = json.load(open(p))
-        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
-                "source": "measured (MEASURED_PEAKS.json)"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+        burst = float(d["bf16_tflops"])
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": burst,
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained") or burst), "source": "measured (MEASURED_PEAKS.json)"}
+    except (OSError, ValueError, KeyError, TypeError):     # absent or incomplete: the recipe's stated numbers
+        return fallback
 
 
 def ncu_traffic(kernel):
