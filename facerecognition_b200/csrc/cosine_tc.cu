@@ -185,7 +185,11 @@ __device__ __forceinline__ void drain_queue(float (&rs)[RS], int (&ri)[RS], cons
 #pragma unroll
     for (int r = 0; r < kTcQueue; r++) {
         if (!__any_sync(0xffffffffu, r < qn)) break;
-        const bool has = r < qn;
+        // A queued score was admitted against the threshold of the LAST drain; earlier inserts of this drain may have
+        // raised the list's last slot above it.  reg_insert overwrites slot RS-1 unconditionally, so such an entry must
+        // be dropped here (strictly: an equal score from a later row stays behind) or, with k == RS, it would evict a
+        // row that belongs in the top-k.
+        const bool has = r < qn && qv[r] > rs[RS - 1];
         reg_insert<RS>(rs, ri, has ? qv[r] : rs[RS - 1], has ? qi[r] : ri[RS - 1]);
     }
     qn = 0;
@@ -443,7 +447,7 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         // whole warp pays for ONE lane's insert.  Lanes park their admitted scores in a 4-slot queue
                         // instead; when any lane's queue is full every lane drains its own, so one pass of the insert
                         // code serves up to 32 candidates.  Thresholds move only at a drain: a score admitted against a
-                        // stale threshold is inserted and falls off the end of the list -- redundant, never wrong.
+                        // stale threshold is re-checked against the list's last slot inside drain_queue and dropped there.
                         if (__any_sync(0xffffffffu, max32(v) > adm)) {
                             uint32_t cand = 0;
 #pragma unroll

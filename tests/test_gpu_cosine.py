@@ -136,7 +136,10 @@ def bf16_round(x):
 
 
 @pytest.mark.parametrize("Q,N,k", [(1, 1, 1), (5, 255, 5), (128, 256, 5), (129, 257, 5), (300, 5000, 5), (64, 70000, 1),
-                                   (1000, 33333, 16), (200, 20000, 9), (150, 9000, 33), (140, 30000, 64)])
+                                   (1000, 33333, 16), (200, 20000, 9), (150, 9000, 33), (140, 30000, 64),
+                                   # one (query tile, gallery group) unit supplies ALL k results with k == the register list
+                                   # length: a queued admission must not evict a top-k row (round-1 advisor finding)
+                                   (128, 256, 16), (128, 256, 32), (128, 256, 64), (100, 200, 64), (19000, 16000, 16)])
 def test_bf16_tensor_core_kernel_vs_oracle(Q, N, k):
     from facerecognition_b200 import ops, _native as NV
     rng = np.random.default_rng(Q + N)
@@ -345,7 +348,8 @@ def test_entry_points_are_reentrant_from_python_threads():
     assert not errors, errors
 
 
-@pytest.mark.parametrize("N,Q,k", [(10_000, 256, 5), (3000, 40, 1), (70_000, 333, 16)])
+@pytest.mark.parametrize("N,Q,k", [(10_000, 256, 5), (3000, 40, 1), (70_000, 333, 16),
+                                   (66_000, 38_100, 5)])   # 298 query tiles: the 64-slot first pass has ONE main gallery group
 def test_tensor_core_first_pass_plus_exact_rescore_equals_the_exact_kernel(N, Q, k):
     """ops.cosine_topk_refined (bf16 tcgen05 first pass, 64 candidates, exact fp32 re-score, completeness proof) must
     return exactly what the fp32 kernel returns whenever it reports fail_count == 0; (10000, 256, 5) is configs[1]."""
