@@ -66,6 +66,10 @@ SIGNATURES = {
     "frb_chisq_topk_g8": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_void_p,
                                   c_void_p, c_void_p, c_size_t, c_void_p]),
     "frb_chisq_dist_g8": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "frb_chisq_filter_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "frb_chisq_top1_filtered_g8": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "frb_chisq_filter_tables": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 
@@ -99,7 +103,7 @@ def call(fn: str, *args) -> None:
     check(fn, getattr(lib, fn)(*args))
 
 
-K_COSINE_TC, K_COSINE_SIMT, K_LBP_HIST, K_CHISQ, K_BGR2GRAY, K_COSINE_GEMV, K_RESIZE = 0, 1, 2, 3, 4, 5, 6
+K_COSINE_TC, K_COSINE_SIMT, K_LBP_HIST, K_CHISQ, K_BGR2GRAY, K_COSINE_GEMV, K_RESIZE, K_CHISQ_FILTER = 0, 1, 2, 3, 4, 5, 6, 7
 
 
 def profile_enable(on: bool) -> None:

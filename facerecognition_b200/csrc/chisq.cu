@@ -125,14 +125,25 @@ __device__ __forceinline__ float2 chi_quad8(uint32_t w, float2 qa, float2 ta, fl
     return chi_quad_core<INTQ>(ga, gb, qa, ta, qb, tb, acc);
 }
 
+// Optional per-query selection (all-null = the plain scan); see chisq_kernel.
+struct ChiSelect {
+    const int *q_flag;     // [n_query] or null
+    const int *row_list;   // GATHER: [n_query, cap] gallery rows to re-score
+    const int *row_cnt;    // GATHER: [n_query] rows listed
+    int64_t cap;           // candidate slots per query in cand_dist / cand_idx
+    int *cnt_out;          // [n_query] candidates written per query (read by topk_merge_compact)
+};
+
 // ---- twelve rows = two trips round the 6-slot ring, so slots and mbarrier parities are compile-time constants -----
 // Row i of the block (i = 0..11) lives in slot i % 6 during ring phase (i / 6) & 1.  While row i is consumed, warp i
 // requests row i + 4 (slot (i + 4) % 6) once every warp has released that slot's previous tenant (row i - 2).
 // GUARD: the block may run past the chunk's last row (tail block only).  FULL: every thread owns CHUNKS full groups.
 // G8: the gallery holds u8 counts (16 bins per 128-bit group, E = 8 bin pairs) instead of u16 (8 bins, E = 4).
-template <int CHUNKS, bool INTQ, bool FULL, bool GUARD, bool G8>
+// GATHER: the rows to scan are rows[0 .. n_rows) of the whole gallery (gal_chunk = its base) instead of a contiguous chunk.
+template <int CHUNKS, bool INTQ, bool FULL, bool GUARD, bool G8, bool GATHER>
 __device__ __forceinline__ void chi_block12(const unsigned char *ring, uint64_t *s_full, uint64_t *s_empty, uint32_t row_bytes,
-                                            const unsigned char *__restrict__ gal_chunk, int64_t it0, int64_t n_rows,
+                                            const unsigned char *__restrict__ gal_chunk, const int *__restrict__ rows, int64_t it0,
+                                            int64_t n_rows,
                                             const float2 (&qd)[CHUNKS][G8 ? 8 : 4], const float2 (&qs)[CHUNKS][G8 ? 8 : 4],
                                             const bool (&live)[CHUNKS], float (*part)[kChiWarps + 1], int part_row0)
 {
@@ -147,11 +158,12 @@ __device__ __forceinline__ void chi_block12(const unsigned char *ring, uint64_t 
             if (GUARD && it0 + i >= n_rows) continue;
             if (tid == i * 32) {
                 const int j = i + 4;                       // row to request, relative to the block
-                if (!GUARD || it0 + j < n_rows) {
+                if (it0 + j < n_rows) {   // also in a full block: rows 12..15 belong to the NEXT block, which may not exist
                     const int ns = j % 6;
                     const uint32_t par = (j < 6 || j >= 12) ? 1u : 0u;   // parity of the phase that released the slot
                     if (j >= 6 || it0 > 0) chi_mbar_wait(&s_empty[ns], par);
-                    chi_bulk_load(const_cast<unsigned char *>(ring) + (size_t)ns * row_bytes, gal_chunk + (it0 + j) * (int64_t)row_bytes,
+                    const int64_t src_row = GATHER ? (int64_t)rows[it0 + j] : it0 + j;
+                    chi_bulk_load(const_cast<unsigned char *>(ring) + (size_t)ns * row_bytes, gal_chunk + src_row * (int64_t)row_bytes,
                                   row_bytes, &s_full[ns]);
                 }
             }
@@ -202,11 +214,17 @@ __device__ __forceinline__ void chi_block12(const unsigned char *ring, uint64_t 
 
 // CHUNKS: 128-bit groups per thread per row (hist_len <= CHUNKS * 4096 for a u16 gallery, CHUNKS * 8192 for u8).
 // WRITE_ALL: emit every distance.  G8: gallery of u8 counts (cell_px <= 255): half the bytes per row, same arithmetic.
-template <int CHUNKS, bool WRITE_ALL, bool INTQ, bool FULL, bool G8>
+// GATHER (behind the tensor-core candidate filter, chisq_filter.cu): query q scans only the rows listed in
+// sel.row_list[q * cap ..] and writes one exact distance per listed row to the compact candidate buffer
+// cand_dist / cand_idx [q * cap + i]; the arithmetic and the summation order are those of the full scan, so a listed
+// row gets bit for bit the distance the full scan gives it.  sel.q_flag: GATHER skips flagged queries; the plain
+// top-k scan, when given q_flag, runs ONLY the flagged ones (the filter's exact fallback) and writes chunk lists to
+// cand_dist / cand_idx [q * cap + chunk * k ..].
+template <int CHUNKS, bool WRITE_ALL, bool INTQ, bool FULL, bool G8, bool GATHER>
 __global__ void __launch_bounds__(kChiBlock, 1)
 chisq_kernel(const uint16_t *__restrict__ qhist, int64_t n_query, float q_scale, const void *__restrict__ gallery_v,
              int64_t n_gallery, int hist_len, float out_scale, int64_t rows_per_chunk, int k, int64_t idx_base,
-             float *__restrict__ cand_dist, int64_t *__restrict__ cand_idx, float *__restrict__ all_dist)
+             float *__restrict__ cand_dist, int64_t *__restrict__ cand_idx, float *__restrict__ all_dist, const ChiSelect sel)
 {
     extern __shared__ __align__(128) unsigned char chi_smem[];
     __shared__ float s_part[2][kChiBatch][kChiWarps + 1];
@@ -217,9 +235,19 @@ chisq_kernel(const uint16_t *__restrict__ qhist, int64_t n_query, float q_scale,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t q = blockIdx.x;
     const int64_t chunk = blockIdx.y;
-    const int64_t row_begin = chunk * rows_per_chunk;
+    if (sel.q_flag) {   // uniform over the CTA
+        const bool flagged = sel.q_flag[q] != 0;
+        if (GATHER ? flagged : !flagged) return;
+    }
+    const int64_t row_begin = GATHER ? 0 : chunk * rows_per_chunk;
     int64_t row_end = row_begin + rows_per_chunk;
     if (row_end > n_gallery) row_end = n_gallery;
+    const int *rows = nullptr;
+    if (GATHER) {
+        int64_t n = sel.row_cnt[q];
+        row_end = n < sel.cap ? n : sel.cap;
+        rows = sel.row_list + q * sel.cap;
+    }
     const int64_t n_rows = row_end - row_begin;
     constexpr int E = G8 ? 8 : 4;                          // bin pairs per 128-bit gallery group
     const int vec_per_row = hist_len >> (G8 ? 4 : 3);      // uint4 per gallery row
@@ -237,7 +265,8 @@ chisq_kernel(const uint16_t *__restrict__ qhist, int64_t n_query, float q_scale,
     // the first four rows are requested up front; after that warp i of a 12-row block requests row i + 4
     if (tid == 0) {
         for (int64_t i = 0; i < 4 && i < n_rows; i++)
-            chi_bulk_load(chi_smem + (size_t)i * row_bytes, gal_chunk + i * (int64_t)row_bytes, row_bytes, &s_full[i]);
+            chi_bulk_load(chi_smem + (size_t)i * row_bytes, gal_chunk + (GATHER ? (int64_t)rows[i] : i) * (int64_t)row_bytes, row_bytes,
+                          &s_full[i]);
     }
 
     // ---- query bins -> registers ------------------------------------------------------------------------------
@@ -285,11 +314,11 @@ chisq_kernel(const uint16_t *__restrict__ qhist, int64_t n_query, float q_scale,
         for (int h = 0; h < 2; h++) {
             const int64_t b0 = it0 + h * 12;
             if (b0 + 12 <= n_rows)
-                chi_block12<CHUNKS, INTQ, FULL, false, G8>(chi_smem, s_full, s_empty, row_bytes, gal_chunk, b0, n_rows, qd, qs, live,
-                                                           s_part[buf], h * 12);
+                chi_block12<CHUNKS, INTQ, FULL, false, G8, GATHER>(chi_smem, s_full, s_empty, row_bytes, gal_chunk, rows, b0, n_rows, qd, qs,
+                                                                   live, s_part[buf], h * 12);
             else if (b0 < n_rows)
-                chi_block12<CHUNKS, INTQ, FULL, true, G8>(chi_smem, s_full, s_empty, row_bytes, gal_chunk, b0, n_rows, qd, qs, live,
-                                                          s_part[buf], h * 12);
+                chi_block12<CHUNKS, INTQ, FULL, true, G8, GATHER>(chi_smem, s_full, s_empty, row_bytes, gal_chunk, rows, b0, n_rows, qd, qs,
+                                                                  live, s_part[buf], h * 12);
         }
         __syncthreads();
         if (warp == 0) {
@@ -301,6 +330,11 @@ chisq_kernel(const uint16_t *__restrict__ qhist, int64_t n_query, float q_scale,
             d *= out_scale;
             if (WRITE_ALL) {
                 if (valid) all_dist[q * n_gallery + row] = d;
+            } else if (GATHER) {
+                if (valid) {
+                    cand_dist[q * sel.cap + row] = d;                       // row = position in the query's list
+                    cand_idx[q * sel.cap + row] = idx_base + rows[row];
+                }
             } else {
                 unsigned m = __ballot_sync(0xffffffffu, valid && d < kth);
                 while (m) {
@@ -317,13 +351,16 @@ chisq_kernel(const uint16_t *__restrict__ qhist, int64_t n_query, float q_scale,
         }
         // no second barrier: s_part is double-buffered and warp 0 reaches the next barrier only after reading
     }
-    if (!WRITE_ALL && warp == 0) {
+    if (GATHER) {
+        if (tid == 0) sel.cnt_out[q] = (int)n_rows;
+    } else if (!WRITE_ALL && warp == 0) {
         __syncwarp();
-        const int64_t o = (chunk * n_query + q) * k;
+        const int64_t o = sel.q_flag ? q * sel.cap + chunk * k : (chunk * n_query + q) * k;
         for (int j = lane; j < k; j += 32) {
             cand_dist[o + j] = s_best[j];
             cand_idx[o + j] = s_bidx[j];
         }
+        if (sel.q_flag && lane == 0 && chunk == 0) sel.cnt_out[q] = (int)gridDim.y * k;
     }
 }
 
@@ -346,24 +383,24 @@ static int64_t chi_chunks(int64_t n_query, int64_t n_gallery, int64_t *rows_per_
     return chunks < 1 ? 1 : chunks;
 }
 
-template <int CHUNKS, bool WRITE_ALL, bool INTQ, bool FULL, bool G8>
+template <int CHUNKS, bool WRITE_ALL, bool INTQ, bool FULL, bool G8, bool GATHER = false>
 static int launch_chisq_t(dim3 grid, size_t smem, const uint16_t *qh, int64_t nq, float q_scale, const void *gal, int64_t ng,
                           int L, float out_scale, int64_t rpc, int k, int64_t idx_base, float *cd, int64_t *ci, float *all,
-                          cudaStream_t st)
+                          cudaStream_t st, const ChiSelect sel = ChiSelect{nullptr, nullptr, nullptr, 0, nullptr})
 {
     static thread_local int attr_dev = -1;
     static thread_local size_t attr_smem = 0;
     int dev = 0;
     FRB_CUDA_OK(cudaGetDevice(&dev));
     if (attr_dev != dev || attr_smem < smem) {
-        FRB_CUDA_OK(cudaFuncSetAttribute(chisq_kernel<CHUNKS, WRITE_ALL, INTQ, FULL, G8>,
+        FRB_CUDA_OK(cudaFuncSetAttribute(chisq_kernel<CHUNKS, WRITE_ALL, INTQ, FULL, G8, GATHER>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_dev = dev;
         attr_smem = smem;
     }
     ProfileScope prof(FRB_K_CHISQ, st);
-    chisq_kernel<CHUNKS, WRITE_ALL, INTQ, FULL, G8><<<grid, kChiBlock, smem, st>>>(qh, nq, q_scale, gal, ng, L, out_scale, rpc, k,
-                                                                                  idx_base, cd, ci, all);
+    chisq_kernel<CHUNKS, WRITE_ALL, INTQ, FULL, G8, GATHER><<<grid, kChiBlock, smem, st>>>(qh, nq, q_scale, gal, ng, L, out_scale, rpc,
+                                                                                          k, idx_base, cd, ci, all, sel);
     FRB_LAUNCH_OK("chisq_kernel");
     return FRB_OK;
 }
@@ -418,6 +455,51 @@ static int launch_chisq(const uint16_t *qh, int64_t nq, int q_cell_px, const voi
     if (gallery_bytes == 1)
         return launch_chisq_g<WRITE_ALL, true>(qh, nq, q_cell_px, gal, ng, L, g_cell_px, rpc, chunks, k, idx_base, cd, ci, all, st);
     return launch_chisq_g<WRITE_ALL, false>(qh, nq, q_cell_px, gal, ng, L, g_cell_px, rpc, chunks, k, idx_base, cd, ci, all, st);
+}
+
+// ---- entry points for the candidate filter (chisq_filter.cu): u8 gallery, equal cell sizes --------------------------
+// exact distances of the listed rows -> cand_dist / cand_idx [q * cap + i], cnt_out[q] = rows listed; flagged queries skipped
+int chisq_gather_g8(const uint16_t *qh, int64_t nq, const uint8_t *gal, int64_t ng, int L, int cell_px, int64_t idx_base,
+                    const int *q_flag, const int *row_list, const int *row_cnt, int64_t cap, float *cd, int64_t *ci, int *cnt_out,
+                    cudaStream_t st)
+{
+    const int groups = L / 16;
+    const int c = (groups + kChiThreads - 1) / kChiThreads;
+    const bool full = groups == c * kChiThreads;
+    const size_t smem = (size_t)L * kChiSlots;
+    const dim3 grid((unsigned)nq, 1);
+    const ChiSelect sel{q_flag, row_list, row_cnt, cap, cnt_out};
+    const float out_scale = 2.0f / (float)cell_px;
+#define FRB_CHI_GATHER(C, F) \
+    launch_chisq_t<C, false, true, F, true, true>(grid, smem, qh, nq, 1.0f, gal, ng, L, out_scale, ng, 1, idx_base, cd, ci, nullptr, st, sel)
+    if (c == 1) return full ? FRB_CHI_GATHER(1, true) : FRB_CHI_GATHER(1, false);
+    if (c == 2) return full ? FRB_CHI_GATHER(2, true) : FRB_CHI_GATHER(2, false);
+#undef FRB_CHI_GATHER
+    set_error("chi-square gather: hist_len=%d exceeds the 16384 bins the kernel keeps in registers", L);
+    return FRB_ERR_UNSUPPORTED;
+}
+
+// the plain exact top-k scan for the flagged queries only, `chunks` chunk lists per query -> cand [q * cap + chunk * k ..]
+int chisq_flagged_topk_g8(const uint16_t *qh, int64_t nq, const uint8_t *gal, int64_t ng, int L, int cell_px, int k,
+                          int64_t idx_base, const int *q_flag, int chunks, int64_t cap, float *cd, int64_t *ci, int *cnt_out,
+                          cudaStream_t st)
+{
+    const int groups = L / 16;
+    const int c = (groups + kChiThreads - 1) / kChiThreads;
+    const bool full = groups == c * kChiThreads;
+    const size_t smem = (size_t)L * kChiSlots;
+    int64_t rpc = (ng + chunks - 1) / chunks;
+    if (rpc < 1) rpc = 1;
+    const dim3 grid((unsigned)nq, (unsigned)chunks);
+    const ChiSelect sel{q_flag, nullptr, nullptr, cap, cnt_out};
+    const float out_scale = 2.0f / (float)cell_px;
+#define FRB_CHI_FLAGGED(C, F) \
+    launch_chisq_t<C, false, true, F, true, false>(grid, smem, qh, nq, 1.0f, gal, ng, L, out_scale, rpc, k, idx_base, cd, ci, nullptr, st, sel)
+    if (c == 1) return full ? FRB_CHI_FLAGGED(1, true) : FRB_CHI_FLAGGED(1, false);
+    if (c == 2) return full ? FRB_CHI_FLAGGED(2, true) : FRB_CHI_FLAGGED(2, false);
+#undef FRB_CHI_FLAGGED
+    set_error("chi-square: hist_len=%d exceeds the 16384 bins the kernel keeps in registers", L);
+    return FRB_ERR_UNSUPPORTED;
 }
 
 static int check_chisq_args(const char *fn, int64_t nq, int qpx, int64_t ng, int L, int gpx)

@@ -77,7 +77,8 @@ typedef enum frb_kernel {
     FRB_K_BGR2GRAY = 4,    /* bgr2gray_kernel                                       */
     FRB_K_COSINE_GEMV = 5, /* cosine_gemv_kernel (1..4 queries, HBM-bound row streaming) */
     FRB_K_RESIZE = 6,      /* resize_linear_kernel (cv2.resize INTER_LINEAR, optionally fused with BGR2GRAY) */
-    FRB_K_COUNT = 7
+    FRB_K_CHISQ_FILTER = 7, /* chisq_filter_kernel (fp16 tcgen05 candidate filter in front of the chi-square scan) */
+    FRB_K_COUNT = 8
 } frb_kernel;
 
 /* When enabled, every launch of the kernels listed above is bracketed by a CUDA event pair on the
@@ -250,6 +251,32 @@ int frb_chisq_topk_g8(const uint16_t *q_hist_dev, int64_t n_query, int q_cell_px
                       void *stream);
 int frb_chisq_dist_g8(const uint16_t *q_hist_dev, int64_t n_query, int q_cell_px, const uint8_t *gallery_dev,
                       int64_t n_gallery, int hist_len, int g_cell_px, float *out_dist_dev, void *stream);
+
+/* ---- batched LBPH predict through the tensor cores (candidate filter + exact re-score) --------------------------- */
+/* The N predicts of the reference's evaluation loops (models/lbphmodel/evaluate_lbph.py:31-33, threshold_lbph.py:47-50,
+ * web_app.py:587 per frame) as ONE call that returns, for every query, exactly what frb_chisq_topk_g8(k = 1) returns —
+ * same fp32 distance bits, same row, first row wins ties — while almost every (query, row) pair is decided by an fp16
+ * GEMM on tcgen05 instead of the 65 k-flop exact formula:
+ *   sum_j (g_j - q_j)^2 / (g_j + q_j) = sum g + sum q - 4 sum_j f(g_j, q_j),  f(a, b) = ab / (a + b);
+ *   f ~ <u(a), v(b)> with rank-8 fp16 feature tables (frb_chisq_filter_tables), so sum_j f is an inner product of
+ *   length 8 * hist_len; the table error bounds |approx - exact| per query for EVERY row, rows outside the resulting
+ *   window around the best approximate score cannot win, and the survivors are re-scored with the exact kernel's own
+ *   arithmetic.  A query whose survivor list overflows is answered by the plain exact scan inside the same call.
+ * Needs equal cell sizes on both sides (cell_px <= 255, u8 gallery), hist_len % 16 == 0, hist_len <= 16384.
+ *   stats_dev  int32 [4] or NULL, incremented: [0] queries answered by the exact fallback, [1] survivors re-scored,
+ *              [2] raw candidates appended by the filter kernel, [3] unused.
+ *   approx_scores_dev  fp32 [n_query, n_gallery] or NULL: every approximate sum_j f (tests / calibration only).
+ * The first call for a (device, cell_px) builds and uploads the tables with blocking copies; later calls are
+ * stream-ordered and capturable. */
+size_t frb_chisq_filter_workspace_bytes(int64_t n_query, int64_t n_gallery, int hist_len);
+int frb_chisq_top1_filtered_g8(const uint16_t *q_hist_dev, int64_t n_query, const uint8_t *gallery_dev, int64_t n_gallery,
+                               int hist_len, int cell_px, int64_t idx_base, float *out_dist_dev, int64_t *out_idx_dev,
+                               int *stats_dev, float *approx_scores_dev, void *workspace_dev, size_t workspace_bytes,
+                               void *stream);
+/* The filter's tables for one cell size (host pointers): u_f16 / v_f16 [256, 8] fp16 bit patterns (gallery / query side,
+ * rows above cell_px zero), emax [256] = max_a |<u(a), v(b)> - f(a, b)| and absmax [256] = max_a sum_m |u_m(a) v_m(b)|
+ * per query count b.  Exposed so that tests can check the bound against the float64 oracle (oracle/chisq_filter.py). */
+int frb_chisq_filter_tables(int cell_px, uint16_t *u_f16, uint16_t *v_f16, float *emax, float *absmax);
 
 #ifdef __cplusplus
 }
