@@ -43,6 +43,8 @@ SIGNATURES = {
     "frb_cosine_topk_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int]),
     "frb_cosine_topk": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_int, c_int,
                                 c_int, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "frb_cosine_topk_bf16q": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p,
+                                      c_size_t, c_void_p]),
     "frb_cosine_rescore_topk": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                         c_int, c_int, c_float, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "frb_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
@@ -55,6 +57,8 @@ SIGNATURES = {
     "frb_exchange_open": (c_int, [c_void_p, c_void_p]),
     "frb_exchange_destroy": (c_int, [c_void_p]),
     "frb_exchange_topk_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "frb_exchange_status": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "frb_exchange_reset": (c_int, [c_void_p]),
     "frb_exchange_emulate": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "frb_lbp_codes_u8": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "frb_lbp_hist_u8": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

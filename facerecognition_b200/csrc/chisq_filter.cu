@@ -6,8 +6,9 @@
 // as a gallery chunk is shared by several queries.  Here almost every pair is decided by a GEMM instead.
 //
 // Algebra.  With integer counts g, q of equal cell size,  sum_j (g_j - q_j)^2 / (g_j + q_j) = sum g + sum q - 4 S(g, q),
-// S = sum_j f(g_j, q_j),  f(a, b) = a b / (a + b).  Both sums are the same constant for every histogram (grid cells x
-// cell_px), so the nearest row is the row with the LARGEST S.  f on [0, cell_px]^2 is a symmetric table whose weighted
+// S = sum_j f(g_j, q_j),  f(a, b) = a b / (a + b), so the nearest row is the row with the LARGEST  S - (sum g) / 4
+// (for LBPH histograms sum g is the same constant for every row; the kernel does not rely on that: the generator
+// threads see every count of their row anyway and hand the row totals to the epilogue).  f on [0, cell_px]^2 is a symmetric table whose weighted
 // eigen-decomposition truncated to rank 8 gives per-count feature vectors u(a), v(b) in fp16 with
 // f(a, b) = <u(a), v(b)> + E(a, b), |E| known exactly (host, float64).  S~(g, q) = sum_j <u(g_j), v(q_j)> is an inner
 // product of length 8 * hist_len: a GEMM with K = 131072 for the 8x8x256 histogram.
@@ -78,12 +79,12 @@ struct CfParams {
     const uint8_t *gallery;             // [n_gallery, hist_len] u8 counts
     const uint4 *u_table;               // [256] gallery-side features, 8 x fp16 per count
     const float *window;                // [n_query] w(q) in S units
-    float *best;                        // [n_query] running max of S~, -inf on entry
+    float *best;                        // [n_query] running max of the score S~ - (row total) / 4, -inf on entry
     int *cnt;                           // [n_query] candidates appended (may exceed cap)
     int cap;
     int *cand_row;                      // [n_query, cap]
     float *cand_s;                      // [n_query, cap]
-    float *all_scores;                  // debug: [n_query, n_gallery] S~ of every pair, or null
+    float *all_scores;                  // debug: [n_query, n_gallery] S~ of every pair (the raw accumulators), or null
 };
 
 __device__ __forceinline__ float cf_atomic_max(float *addr, float v)   // returns the value before the update
@@ -100,7 +101,8 @@ chisq_filter_kernel(const __grid_constant__ CUtensorMap tmap_f, const CfParams p
     unsigned char *smem_a = smem;
     unsigned char *smem_b = smem + (size_t)kCfAStages * kCfAStageBytes;
     uint4 *tbl = reinterpret_cast<uint4 *>(smem_b + (size_t)kCfBStages * kCfBStageBytes);
-    CfBarriers *bars = reinterpret_cast<CfBarriers *>(tbl + kCfTableRows);
+    float *rowsum = reinterpret_cast<float *>(tbl + kCfTableRows);      // [2][256]: (sum of the row's counts) / 4, by unit parity
+    CfBarriers *bars = reinterpret_cast<CfBarriers *>(rowsum + 2 * kCfBlockN);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_units = p.n_qpairs * p.n_gtiles;
@@ -187,9 +189,10 @@ chisq_filter_kernel(const __grid_constant__ CUtensorMap tmap_f, const CfParams p
         const uint32_t xr = (uint32_t)(r & 7) << 4;              // 128-byte swizzle: 16-byte chunk c of row r sits at c ^ (r & 7)
         const int n_iter = p.n_kblocks >> 1;                     // 16 bins (one 128-bit load) = two k-blocks per iteration
         int sb = 0;
-        uint32_t pb = 0;
-        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+        uint32_t pb = 0, upar = 0;
+        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, upar ^= 1) {
             const int64_t gt = u % p.n_gtiles;
+            uint32_t rsum = 0;
             const int64_t row = gt * kCfBlockN + r;
             const bool valid = row < p.n_gallery;
             const uint4 *src = reinterpret_cast<const uint4 *>(p.gallery + (valid ? row : 0) * (int64_t)p.hist_len);
@@ -201,6 +204,11 @@ chisq_filter_kernel(const __grid_constant__ CUtensorMap tmap_f, const CfParams p
                 nxt = nxt2;
                 if (valid && it + 2 < n_iter) nxt2 = __ldg(src + it + 2);
                 const uint32_t wds[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+                for (int wq = 0; wq < 4; wq++) rsum = __dp4a(wds[wq], 0x01010101u, rsum);
+                // the row total is complete with the last counts; it is published before this iteration's b_full arrivals,
+                // which the MMA thread's final commit (tmem_full) orders before the epilogue's reads
+                if (it == n_iter - 1) rowsum[upar * kCfBlockN + r] = 0.25f * (float)rsum;
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     mbar_wait(&bars->b_empty[sb], pb ^ 1);
@@ -220,8 +228,9 @@ chisq_filter_kernel(const __grid_constant__ CUtensorMap tmap_f, const CfParams p
     } else if (warp >= 4) {
         // ===================== epilogue: running maximum + candidates within the window =====================
         const int ew = warp & 3;
-        uint32_t acc_phase = 0;
-        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+        uint32_t acc_phase = 0, upar = 0;
+        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, upar ^= 1) {
+            const float *rs = rowsum + upar * kCfBlockN;
             const int64_t pair = u / p.n_gtiles, gt = u % p.n_gtiles;
             const int64_t left = p.n_qtiles - pair * kCfQTiles;
             const int nqt = left < kCfQTiles ? (int)left : kCfQTiles;
@@ -240,7 +249,7 @@ chisq_filter_kernel(const __grid_constant__ CUtensorMap tmap_f, const CfParams p
                     float v[32];
                     tmem_ld_32x32(taddr + (uint32_t)c0, v);
 #pragma unroll
-                    for (int j = 0; j < 32; j++) m = (c0 + j < valid) ? fmaxf(m, v[j]) : m;
+                    for (int j = 0; j < 32; j++) m = (c0 + j < valid) ? fmaxf(m, v[j] - rs[c0 + j]) : m;
                     if (p.all_scores && live) {
 #pragma unroll
                         for (int j = 0; j < 32; j++)
@@ -258,11 +267,12 @@ chisq_filter_kernel(const __grid_constant__ CUtensorMap tmap_f, const CfParams p
                     tmem_ld_32x32(taddr + (uint32_t)c0, v);
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
-                        if (c0 + j < valid && v[j] >= thr) {
+                        const float sc = v[j] - rs[c0 + j];
+                        if (c0 + j < valid && sc >= thr) {
                             const int pos = atomicAdd(p.cnt + q, 1);
                             if (pos < p.cap) {
                                 p.cand_row[q * p.cap + pos] = (int)(n0 + c0 + j);
-                                p.cand_s[q * p.cap + pos] = v[j];
+                                p.cand_s[q * p.cap + pos] = sc;
                             }
                         }
                     }
@@ -288,7 +298,8 @@ chisq_filter_kernel(const __grid_constant__ CUtensorMap tmap_f, const CfParams p
 __global__ void __launch_bounds__(256)
 chisq_feat_kernel(const uint16_t *__restrict__ qhist, int hist_len, const uint4 *__restrict__ v_table,
                   const float *__restrict__ emax, const float *__restrict__ absmax, float acc_rel, uint4 *__restrict__ feat,
-                  float *__restrict__ window, float *__restrict__ best, int *__restrict__ cnt, int *__restrict__ flag)
+                  float *__restrict__ window, float *__restrict__ qtot, float *__restrict__ best, int *__restrict__ cnt,
+                  int *__restrict__ flag)
 {
     __shared__ float s_red[3][8];
     const int64_t q = blockIdx.x;
@@ -321,6 +332,7 @@ chisq_feat_kernel(const uint16_t *__restrict__ qhist, int hist_len, const uint4 
         // e_tab: table error (exact tables, summed in fp32: + 1e-4 relative); e_acc: accumulation allowance of the fp32
         // tensor-core sum; last term: the exact scan's own rounding (<= 1e-5 relative on a distance <= 2 * total counts)
         window[q] = 2.0f * (es * 1.0001f + acc_rel * as) + 1e-5f * ts;
+        qtot[q] = ts;                                   // exact: an integer below 2^24
         best[q] = -INFINITY;
         cnt[q] = 0;
         flag[q] = 0;
@@ -332,7 +344,8 @@ chisq_feat_kernel(const uint16_t *__restrict__ qhist, int hist_len, const uint4 
 __global__ void __launch_bounds__(256)
 chisq_survivor_kernel(int64_t n_query, int cap, const float *__restrict__ best, const float *__restrict__ window,
                       const int *__restrict__ raw_cnt, const int *__restrict__ raw_row, const float *__restrict__ raw_s,
-                      int *__restrict__ list_row, int *__restrict__ list_cnt, int *__restrict__ flag, int *__restrict__ stats)
+                      int *__restrict__ list_row, float *__restrict__ list_s, int *__restrict__ list_cnt, int *__restrict__ flag,
+                      int *__restrict__ stats)
 {
     const int64_t q = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -353,9 +366,14 @@ chisq_survivor_kernel(int64_t n_query, int cap, const float *__restrict__ best, 
     int kept = 0;
     for (int i0 = 0; i0 < n_raw; i0 += 32) {
         const int i = i0 + lane;
-        const bool keep = i < n_raw && raw_s[q * cap + i] >= thr;
+        const float sc = i < n_raw ? raw_s[q * cap + i] : 0.f;
+        const bool keep = i < n_raw && sc >= thr;
         const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (keep) list_row[q * cap + kept + __popc(m & ((1u << lane) - 1u))] = raw_row[q * cap + i];
+        if (keep) {
+            const int64_t o = q * cap + kept + __popc(m & ((1u << lane) - 1u));
+            list_row[o] = raw_row[q * cap + i];
+            list_s[o] = sc;
+        }
         kept += __popc(m);
     }
     if (lane == 0) {
@@ -363,6 +381,36 @@ chisq_survivor_kernel(int64_t n_query, int cap, const float *__restrict__ best, 
         if (stats) {
             atomicAdd(stats + 1, kept);
             atomicAdd(stats + 2, n_raw);
+        }
+    }
+}
+
+// ---- audit: every re-scored row has both its exact distance and its filter score ----------------------------------------
+// score = S~ - (sum g)/4 and d = (2 / cell_px) (sum g + sum q - 4 S), so the exact score is (sum q - d cell_px / 2) / 4.
+// |score - exact score| must be within e(q) = window / 2 — the bound the survivor rule rests on.  A violation (which the
+// table bound excludes and the accumulation allowance is sized never to see) flags the query for the exact scan and is
+// counted in stats[3]; the call then still returns the exact answer for it.
+__global__ void __launch_bounds__(256)
+chisq_audit_kernel(int64_t n_query, int cap, float half_cell_px, const int *__restrict__ list_cnt, const float *__restrict__ list_s,
+                   const float *__restrict__ cand_dist, const float *__restrict__ qtot, const float *__restrict__ window,
+                   int *__restrict__ flag, int *__restrict__ stats)
+{
+    const int64_t q = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= n_query || flag[q]) return;
+    const int n = list_cnt[q];
+    const float e = 0.5f * window[q], tq = qtot[q];
+    int bad = 0;
+    for (int i = lane; i < n; i += 32) {
+        const float exact = 0.25f * (tq - cand_dist[q * cap + i] * half_cell_px);
+        bad += fabsf(list_s[q * cap + i] - exact) > e ? 1 : 0;
+    }
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if (lane == 0 && bad) {
+        flag[q] = 1;
+        if (stats) {
+            atomicAdd(stats + 0, 1);
+            atomicAdd(stats + 3, bad);
         }
     }
 }
@@ -503,7 +551,7 @@ static int get_tables(int cell_px, CfTables *out)
 struct CfPlan {
     int64_t pass_q;        // queries per pass
     int cap;
-    size_t feat, window, best, cnt, flag, list_cnt, raw_row, raw_s, list_row, cand_idx, total;
+    size_t feat, window, qtot, best, cnt, flag, list_cnt, raw_row, raw_s, list_row, list_s, cand_idx, total;
 };
 
 static CfPlan cf_plan(int64_t nq, int64_t ng, int L)
@@ -518,6 +566,7 @@ static CfPlan cf_plan(int64_t nq, int64_t ng, int L)
     auto take = [&o](size_t bytes) { const size_t at = o; o += align_up(bytes, 1024); return at; };
     pl.feat = take(qpad * (size_t)L * kCfRank * 2);
     pl.window = take(qpad * 4);
+    pl.qtot = take(qpad * 4);
     pl.best = take(qpad * 4);
     pl.cnt = take(qpad * 4);
     pl.flag = take(qpad * 4);
@@ -525,6 +574,7 @@ static CfPlan cf_plan(int64_t nq, int64_t ng, int L)
     pl.raw_row = take(n * 4);
     pl.raw_s = take(n * 4);       // reused as the exact distances of the survivors (cand_dist)
     pl.list_row = take(n * 4);
+    pl.list_s = take(n * 4);
     pl.cand_idx = take(n * 8);
     pl.total = o;
     return pl;
@@ -536,7 +586,7 @@ static float cf_acc_rel()
     // (measured error of the accumulated sum vs float64 on the same fp16 features, times a margin).
     // The environment override exists for the tests (a huge value forces the overflow -> exact-scan fallback).
     const char *e = getenv("FRB_CHISQ_FILTER_ACC_REL");
-    return e ? (float)atof(e) : 2.5e-4f;
+    return e ? (float)atof(e) : 1e-4f;
 }
 
 }  // namespace frb
@@ -597,14 +647,14 @@ int frb_chisq_top1_filtered_g8(const uint16_t *q_hist, int64_t n_query, const ui
     }
     char *w = (char *)workspace;
     uint4 *feat = (uint4 *)(w + pl.feat);
-    float *window = (float *)(w + pl.window), *best = (float *)(w + pl.best);
+    float *window = (float *)(w + pl.window), *best = (float *)(w + pl.best), *qtot = (float *)(w + pl.qtot);
     int *cnt = (int *)(w + pl.cnt), *flag = (int *)(w + pl.flag), *list_cnt = (int *)(w + pl.list_cnt);
     int *raw_row = (int *)(w + pl.raw_row), *list_row = (int *)(w + pl.list_row);
-    float *raw_s = (float *)(w + pl.raw_s);
+    float *raw_s = (float *)(w + pl.raw_s), *list_s = (float *)(w + pl.list_s);
     int64_t *cand_idx = (int64_t *)(w + pl.cand_idx);
 
     const size_t smem = 1024 + (size_t)kCfAStages * kCfAStageBytes + (size_t)kCfBStages * kCfBStageBytes +
-                        kCfTableRows * sizeof(uint4) + sizeof(CfBarriers);
+                        kCfTableRows * sizeof(uint4) + 2 * kCfBlockN * sizeof(float) + sizeof(CfBarriers);
     {
         static thread_local int attr_dev = -1;
         if (attr_dev != dev) {
@@ -616,8 +666,8 @@ int frb_chisq_top1_filtered_g8(const uint16_t *q_hist, int64_t n_query, const ui
     for (int64_t q0 = 0; q0 < n_query; q0 += pl.pass_q) {
         const int64_t nq = (n_query - q0) < pl.pass_q ? (n_query - q0) : pl.pass_q;
         const uint16_t *qh = q_hist + q0 * hist_len;
-        chisq_feat_kernel<<<(unsigned)nq, 256, 0, st>>>(qh, hist_len, tb.d_v, tb.d_emax, tb.d_absmax, cf_acc_rel(), feat, window, best,
-                                                       cnt, flag);
+        chisq_feat_kernel<<<(unsigned)nq, 256, 0, st>>>(qh, hist_len, tb.d_v, tb.d_emax, tb.d_absmax, cf_acc_rel(), feat, window, qtot,
+                                                       best, cnt, flag);
         FRB_LAUNCH_OK("chisq_feat_kernel");
         if (n_gallery > 0) {
             CUtensorMap tf;
@@ -657,13 +707,16 @@ int frb_chisq_top1_filtered_g8(const uint16_t *q_hist, int64_t n_query, const ui
                 FRB_LAUNCH_OK("chisq_filter_kernel");
             }
         }
-        chisq_survivor_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(nq, pl.cap, best, window, cnt, raw_row, raw_s, list_row, list_cnt,
-                                                                        flag, stats);
+        chisq_survivor_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(nq, pl.cap, best, window, cnt, raw_row, raw_s, list_row, list_s,
+                                                                        list_cnt, flag, stats);
         FRB_LAUNCH_OK("chisq_survivor_kernel");
         // exact distances of the survivors (cnt[q] = survivors) ...
         rc = chisq_gather_g8(qh, nq, gallery, n_gallery, hist_len, cell_px, idx_base, flag, list_row, list_cnt, pl.cap, raw_s, cand_idx,
                              cnt, st);
         if (rc != FRB_OK) return rc;
+        chisq_audit_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(nq, pl.cap, 0.5f * (float)cell_px, list_cnt, list_s, raw_s, qtot,
+                                                                     window, flag, stats);
+        FRB_LAUNCH_OK("chisq_audit_kernel");
         // ... and the plain exact scan for the flagged queries (CTAs of the others exit at once)
         rc = chisq_flagged_topk_g8(qh, nq, gallery, n_gallery, hist_len, cell_px, 1, idx_base, flag, kCfFallbackChunks, pl.cap, raw_s,
                                    cand_idx, cnt, st);

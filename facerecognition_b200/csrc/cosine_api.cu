@@ -12,8 +12,8 @@ int launch_cosine_simt(const float *queries, int64_t nq, const void *gallery, in
                        float *cand_scores, int64_t *cand_idx, int64_t tiles_per_chunk, int64_t chunks, cudaStream_t st);
 
 size_t cosine_tc_workspace_bytes(int64_t n_query, int64_t n_gallery, int dim, int k);
-int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16, int64_t ng, int dim, int qnorm_mode,
-                     int k, int64_t idx_base, float *out_scores, int64_t *out_idx, void *ws, size_t ws_bytes,
+int launch_cosine_tc(const float *queries, const void *queries_bf16, int64_t nq, const void *gallery_bf16, int64_t ng, int dim,
+                     int qnorm_mode, int k, int64_t idx_base, float *out_scores, int64_t *out_idx, void *ws, size_t ws_bytes,
                      cudaStream_t st);
 
 bool gemv_applicable(int64_t n_query, int dim, int gallery_dtype);
@@ -129,7 +129,7 @@ int frb_cosine_topk(const float *queries, int64_t n_query, const void *gallery, 
     }
 
     if (gallery_dtype == FRB_BF16) {
-        return launch_cosine_tc(queries, n_query, gallery, n_gallery, dim, qnorm_mode, k, idx_base, out_scores, out_idx,
+        return launch_cosine_tc(queries, nullptr, n_query, gallery, n_gallery, dim, qnorm_mode, k, idx_base, out_scores, out_idx,
                                 workspace, workspace_bytes, st);
     }
 
@@ -149,6 +149,38 @@ int frb_cosine_topk(const float *queries, int64_t n_query, const void *gallery, 
                                 cs, ci, p.tiles_per_chunk, p.chunks, st);
     if (rc != FRB_OK) return rc;
     return frb_topk_merge(cs, ci, (int)p.chunks, n_query, k, /*largest=*/1, out_scores, out_idx, stream);
+}
+
+int frb_cosine_topk_bf16q(const void *queries_bf16, int64_t n_query, const void *gallery_bf16, int64_t n_gallery, int dim, int k,
+                          int64_t idx_base, float *out_scores, int64_t *out_idx, void *workspace, size_t workspace_bytes, void *stream)
+{
+    const char *fn = "frb_cosine_topk_bf16q";
+    FRB_CHECK_ARG(n_query >= 0 && n_gallery >= 0, "%s: n_query=%lld n_gallery=%lld", fn, (long long)n_query, (long long)n_gallery);
+    FRB_CHECK_ARG(dim > 0 && (dim % 8) == 0, "%s: dim=%d must be a positive multiple of 8", fn, dim);
+    FRB_CHECK_ARG(k >= 1 && k <= FRB_MAX_K, "%s: k=%d (1..%d)", fn, k, FRB_MAX_K);
+    if (n_query == 0) return FRB_OK;
+    FRB_CHECK_ARG(queries_bf16 && out_scores && out_idx, "%s: null pointer", fn);
+    FRB_CHECK_ARG(n_gallery == 0 || gallery_bf16, "%s: null gallery", fn);
+    FRB_CHECK_ARG(((uintptr_t)queries_bf16 & 15) == 0 && ((uintptr_t)gallery_bf16 & 15) == 0, "%s: queries and gallery must be 16-byte aligned", fn);
+    const size_t need = frb_cosine_topk_workspace_bytes(n_query, n_gallery, dim, FRB_BF16, k);
+    if (!workspace || workspace_bytes < need) {
+        set_error("%s: workspace %zu B < %zu B", fn, workspace_bytes, need);
+        return FRB_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (gemv_applicable(n_query, dim, FRB_BF16)) {
+        GemvPlan p = gemv_plan(n_query, n_gallery, dim, k);
+        char *ws = (char *)workspace;
+        int *cnt = (int *)(ws + p.q_bytes);
+        int64_t *ci = (int64_t *)(ws + p.q_bytes + p.cnt_bytes);
+        float *cs = (float *)(ws + p.q_bytes + p.cnt_bytes + p.idx_bytes);
+        int rc = launch_cosine_gemv(queries_bf16, n_query, gallery_bf16, FRB_BF16, n_gallery, dim, nullptr, nullptr, FRB_SCORE_IP, k, idx_base,
+                                    cs, ci, cnt, p.rows_per_cta, p.ctas, st);
+        if (rc != FRB_OK) return rc;
+        return topk_merge_compact(cs, ci, cnt, p.ctas * k, n_query, k, /*largest=*/1, out_scores, out_idx, st);
+    }
+    return launch_cosine_tc(nullptr, queries_bf16, n_query, gallery_bf16, n_gallery, dim, FRB_QNORM_NONE, k, idx_base, out_scores, out_idx,
+                            workspace, workspace_bytes, st);
 }
 
 }  // extern "C"

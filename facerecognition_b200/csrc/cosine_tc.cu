@@ -586,8 +586,22 @@ size_t cosine_tc_workspace_bytes(int64_t n_query, int64_t n_gallery, int dim, in
     return pl.qbf16_bytes + pl.thr_bytes + pl.cnt_bytes + pl.share_bytes + pl.idx_bytes + pl.score_bytes;
 }
 
-int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16, int64_t ng, int dim, int qnorm_mode, int k,
-                     int64_t idx_base, float *out_scores, int64_t *out_idx, void *ws, size_t ws_bytes, cudaStream_t st)
+// per-query scratch reset for callers that bring their own normalised bf16 queries (no prologue launch to ride on)
+__global__ void __launch_bounds__(256) tc_reset_kernel(float *__restrict__ thr, int *__restrict__ cnt, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) {
+        thr[i] = -INFINITY;
+        cnt[i] = 0;
+    }
+}
+
+// queries: fp32 rows that the prologue normalises (qnorm_mode) and rounds to bf16 — or, when queries_bf16 is given, rows
+// that are ALREADY normalised bf16 (e.g. all-gathered from the ranks that normalised their own slice of the batch): the
+// TMA reads them in place and no prologue runs.
+int launch_cosine_tc(const float *queries, const void *queries_bf16, int64_t nq, const void *gallery_bf16, int64_t ng, int dim,
+                     int qnorm_mode, int k, int64_t idx_base, float *out_scores, int64_t *out_idx, void *ws, size_t ws_bytes,
+                     cudaStream_t st)
 {
     (void)ws_bytes;
     if (dim % kTcBlockK != 0 || dim / kTcBlockK > kTcMaxKBlocks) {
@@ -612,8 +626,15 @@ int launch_cosine_tc(const float *queries, int64_t nq, const void *gallery_bf16,
 
     // prologue: L2-normalise in fp32, round to bf16 (rows beyond n_query are never read: TMA zero-fills)
     // the same launch resets the shared admission thresholds (-inf) and the candidate counters (0)
-    int rc = normalize_rows_impl(queries, nq, dim, qnorm_mode, qb, FRB_BF16, thr, cnt, st);
-    if (rc != FRB_OK) return rc;
+    int rc = FRB_OK;
+    if (queries_bf16) {
+        qb = (__nv_bfloat16 *)const_cast<void *>(queries_bf16);
+        tc_reset_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(thr, cnt, nq);
+        FRB_LAUNCH_OK("tc_reset_kernel");
+    } else {
+        rc = normalize_rows_impl(queries, nq, dim, qnorm_mode, qb, FRB_BF16, thr, cnt, st);
+        if (rc != FRB_OK) return rc;
+    }
     if (pl.share_bytes) FRB_CUDA_OK(cudaMemsetAsync(share, 0xFF, pl.share_bytes, st));   // 0xFFFFFFFF = not published
 
     CUtensorMap tq, tg, tpf;

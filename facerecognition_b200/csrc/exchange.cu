@@ -11,7 +11,11 @@
 //   4. merges the R lists of its queries under the total order (key, then lowest global row).
 // Buffers are double-buffered by epoch parity: a rank can only be one step ahead of a peer (it had to see the
 // peer's flag of the previous step), and the peer's kernel of two steps ago has finished by then.
-// The spin is bounded (~10 s): a rank that never arrives traps the kernel instead of hanging the GPU.
+// The epoch lives in DEVICE memory (ctl[0] of the rank's own buffer): every CTA reads it on entry and the last CTA
+// to finish advances it, so a launch carries no per-call host state and the step can be replayed from a CUDA graph.
+// The spin is bounded (~10 s): a rank that never arrives is counted in ctl[2] (frb_exchange_status) and the kernel
+// returns instead of hanging the GPU; after any failure the ranks call frb_exchange_reset in lockstep to restart
+// the epochs from zero.
 //
 // Replaces: torch.distributed all_gather_into_tensor + frb_topk_merge_strided (facerecognition_b200/sharded.py),
 // which stay as the portable path (gloo tests, hosts without IPC).  There is no reference counterpart: the
@@ -26,11 +30,11 @@ struct frb_exchange {
     int max_k, max_ctas;
     size_t rec_bytes;    // one rank's record for max_query x max_k: ids then scores, padded to 16
     size_t flags_off;    // byte offset of the flags: u32 [2 parities][world][max_ctas]
+    size_t ctl_off;      // byte offset of the control words: u32 {epoch of the last finished step, CTAs finished, timeouts}
     size_t total_bytes;
     unsigned char *local;            // this rank's buffer (cudaMalloc)
     unsigned char *peer[FRB_EXCHANGE_MAX_WORLD];  // every rank's buffer as mapped here (peer[rank] == local)
     bool opened[FRB_EXCHANGE_MAX_WORLD];
-    unsigned epoch;
 };
 
 namespace frb {
@@ -40,9 +44,8 @@ constexpr int kExThreads = 128;
 struct ExParams {
     unsigned char *peer[FRB_EXCHANGE_MAX_WORLD];
     int world, rank;
-    size_t rec_bytes, flags_off;
+    size_t rec_bytes, flags_off, ctl_off;
     int max_ctas;
-    unsigned epoch;
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
@@ -75,7 +78,13 @@ __global__ void __launch_bounds__(kExThreads) topk_exchange_merge_kernel(const f
         os += (int64_t)rank * n_query * k;
         oi += (int64_t)rank * n_query * k;
     }
-    const unsigned parity = ex.epoch & 1u;
+    // this step's epoch: one more than the last finished step of THIS rank (advanced below by the last CTA to finish)
+    unsigned *ctl = reinterpret_cast<unsigned *>(ex.peer[rank] + ex.ctl_off);
+    __shared__ unsigned s_epoch;
+    if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile unsigned *>(ctl) + 1u;
+    __syncthreads();
+    const unsigned epoch = s_epoch;
+    const unsigned parity = epoch & 1u;
     const int64_t q = (int64_t)blockIdx.x * kExThreads + threadIdx.x;
     const bool live = q < n_query;
 
@@ -95,18 +104,30 @@ __global__ void __launch_bounds__(kExThreads) topk_exchange_merge_kernel(const f
     __syncthreads();
     if (threadIdx.x < ex.world) {
         unsigned *flags = reinterpret_cast<unsigned *>(ex.peer[threadIdx.x] + ex.flags_off);
-        st_release_sys(flags + ((size_t)parity * ex.world + rank) * ex.max_ctas + blockIdx.x, ex.epoch);
+        st_release_sys(flags + ((size_t)parity * ex.world + rank) * ex.max_ctas + blockIdx.x, epoch);
     }
     // 3. wait for the same CTA of every rank
     if (threadIdx.x < ex.world) {
         const unsigned *flags = reinterpret_cast<const unsigned *>(ex.peer[rank] + ex.flags_off);
         const unsigned *f = flags + ((size_t)parity * ex.world + threadIdx.x) * ex.max_ctas + blockIdx.x;
         const long long t0 = clock64();
-        while (ld_acquire_sys(f) != ex.epoch) {
-            if (clock64() - t0 > 20000000000LL) __trap();  // ~10 s: a rank never arrived
+        while (ld_acquire_sys(f) != epoch) {
+            if (clock64() - t0 > 20000000000LL) {          // ~10 s: a rank never arrived; report, do not hang
+                atomicAdd(ctl + 2, 1u);
+                break;
+            }
         }
     }
     __syncthreads();
+    // the last CTA of this rank to get here advances the epoch (every CTA has read it by then)
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ctl + 1, 1u) == gridDim.x - 1) {
+            ctl[1] = 0;
+            __threadfence();
+            *reinterpret_cast<volatile unsigned *>(ctl) = epoch;
+        }
+    }
     if (!live) return;
 
     // 4. merge (L1 is bypassed: these lines were written by other GPUs)
@@ -144,15 +165,15 @@ static int check_call(const char *fn, const frb_exchange *ex, int64_t n_query, i
     return FRB_OK;
 }
 
-static void fill_params(const frb_exchange *ex, ExParams *p, unsigned epoch)
+static void fill_params(const frb_exchange *ex, ExParams *p)
 {
     for (int i = 0; i < FRB_EXCHANGE_MAX_WORLD; i++) p->peer[i] = ex->peer[i];
     p->world = ex->world;
     p->rank = ex->rank;
     p->rec_bytes = ex->rec_bytes;
     p->flags_off = ex->flags_off;
+    p->ctl_off = ex->ctl_off;
     p->max_ctas = ex->max_ctas;
-    p->epoch = epoch;
 }
 
 }  // namespace frb
@@ -176,8 +197,8 @@ int frb_exchange_create(int world, int rank, int64_t max_query, int max_k, frb_e
     ex->max_ctas = (int)((max_query + kExThreads - 1) / kExThreads);
     ex->rec_bytes = align_up((size_t)max_query * max_k * 12, 16);
     ex->flags_off = align_up(2 * (size_t)world * ex->rec_bytes, 256);
-    ex->total_bytes = ex->flags_off + 2 * (size_t)world * ex->max_ctas * sizeof(unsigned);
-    ex->epoch = 0;
+    ex->ctl_off = align_up(ex->flags_off + 2 * (size_t)world * ex->max_ctas * sizeof(unsigned), 256);
+    ex->total_bytes = ex->ctl_off + 256;
     for (int i = 0; i < FRB_EXCHANGE_MAX_WORLD; i++) {
         ex->peer[i] = nullptr;
         ex->opened[i] = false;
@@ -238,17 +259,35 @@ int frb_exchange_topk_merge(frb_exchange *ex, const float *local_scores, const i
     int rc = check_call("frb_exchange_topk_merge", ex, n_query, k);
     if (rc != FRB_OK) return rc;
     for (int p = 0; p < ex->world; p++) FRB_CHECK_ARG(ex->peer[p], "frb_exchange_topk_merge: rank %d's buffer is not mapped (frb_exchange_open)", p);
-    ex->epoch++;  // every rank calls in lockstep, so epochs agree
-    if (n_query == 0) return FRB_OK;
+    if (n_query == 0) return FRB_OK;   // no launch, no epoch: every rank sees the same n_query
     FRB_CHECK_ARG(local_scores && local_idx && out_scores && out_idx, "frb_exchange_topk_merge: null pointer");
     ExParams p;
-    fill_params(ex, &p, ex->epoch);
+    fill_params(ex, &p);
     const unsigned grid = (unsigned)((n_query + kExThreads - 1) / kExThreads);
     if (largest)
         topk_exchange_merge_kernel<true, false><<<grid, kExThreads, 0, (cudaStream_t)stream>>>(local_scores, local_idx, n_query, k, p, out_scores, out_idx);
     else
         topk_exchange_merge_kernel<false, false><<<grid, kExThreads, 0, (cudaStream_t)stream>>>(local_scores, local_idx, n_query, k, p, out_scores, out_idx);
     FRB_LAUNCH_OK("topk_exchange_merge_kernel");
+    return FRB_OK;
+}
+
+int frb_exchange_status(frb_exchange *ex, int *timeouts, unsigned *epoch)
+{
+    FRB_CHECK_ARG(ex, "frb_exchange_status: null exchange");
+    unsigned ctl[3] = {0, 0, 0};
+    FRB_CUDA_OK(cudaMemcpy(ctl, ex->local + ex->ctl_off, sizeof(ctl), cudaMemcpyDeviceToHost));   // waits for the stream work before it
+    if (epoch) *epoch = ctl[0];
+    if (timeouts) *timeouts = (int)ctl[2];
+    return FRB_OK;
+}
+
+int frb_exchange_reset(frb_exchange *ex)
+{
+    FRB_CHECK_ARG(ex, "frb_exchange_reset: null exchange");
+    FRB_CUDA_OK(cudaDeviceSynchronize());
+    FRB_CUDA_OK(cudaMemset(ex->local + ex->flags_off, 0, ex->total_bytes - ex->flags_off));   // flags + control words
+    FRB_CUDA_OK(cudaDeviceSynchronize());
     return FRB_OK;
 }
 
@@ -266,12 +305,8 @@ int frb_exchange_emulate(frb_exchange *const *ranks, int world, const float *loc
     // every CTA of every emulated rank must be resident at once (they wait for one another)
     FRB_CHECK_ARG((int64_t)grid_x * world <= (int64_t)sm_count() * 8, "frb_exchange_emulate: %u x %d CTAs cannot all be resident", grid_x, world);
     ExParams p;
-    fill_params(ranks[0], &p, 0);
-    for (int r = 0; r < world; r++) {
-        p.peer[r] = ranks[r]->local;  // same process: no IPC mapping needed
-        ranks[r]->epoch++;
-    }
-    p.epoch = ranks[0]->epoch;
+    fill_params(ranks[0], &p);
+    for (int r = 0; r < world; r++) p.peer[r] = ranks[r]->local;  // same process: no IPC mapping needed
     if (n_query == 0) return FRB_OK;
     dim3 grid(grid_x, (unsigned)world);
     if (largest)

@@ -119,6 +119,15 @@ int frb_cosine_topk(const float *queries_dev, int64_t n_query, const void *galle
                     int score_mode, int qnorm_mode, int k, int64_t idx_base, float *out_scores_dev,
                     int64_t *out_idx_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* The bf16 path of frb_cosine_topk for queries that are ALREADY L2-normalised and rounded to bf16 ([n_query, dim],
+ * e.g. by frb_normalize_rows(..., FRB_BF16)): the tensor-core kernel reads them in place and no prologue runs.  This is
+ * what a sharded search calls after all-gathering the ranks' normalised query slices (half the NVLink bytes of the fp32
+ * batch, and no rank normalises another rank's queries).  Same results as frb_cosine_topk with FRB_QNORM_CLAMP/EPS on
+ * the fp32 rows those bf16 rows came from.  Workspace: frb_cosine_topk_workspace_bytes(..., FRB_BF16, k). */
+int frb_cosine_topk_bf16q(const void *queries_bf16_dev, int64_t n_query, const void *gallery_bf16_dev, int64_t n_gallery,
+                          int dim, int k, int64_t idx_base, float *out_scores_dev, int64_t *out_idx_dev,
+                          void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* Exact fp32 top-k from a tensor-core first pass.  cand_idx / cand_approx [n_query, kp] are the (local row, score) lists
  * frb_cosine_topk returned for a unit-norm bf16 copy of the gallery with kp > k.  Each listed row is re-scored in fp32
  * under score_mode (queries as that rule takes them: normalised rows for FRB_SCORE_IP, raw rows + norms for
@@ -182,8 +191,11 @@ int frb_resize_linear_u8(const uint8_t *src_dev, int64_t count, int src_rows, in
  * passes all `world` of them, in rank order, to frb_exchange_open, which maps the peers' buffers.
  * frb_exchange_topk_merge is then ONE kernel per step: each CTA stores its queries' local candidates into every
  * rank's buffer (peer stores), release-stores the step's epoch into the peers' flags, acquire-waits for the same
- * CTA of every rank, and merges (ties -> lowest global id).  All ranks must call it in lockstep (the epoch is a
- * per-context call counter).  A rank that does not arrive within ~10 s traps the kernel.
+ * CTA of every rank, and merges (ties -> lowest global id).  All ranks must call it in lockstep.  The epoch is kept in
+ * device memory and advanced by the kernel itself, so the step (local search + exchange) can be captured once into a
+ * CUDA graph and replayed.  A rank that does not arrive within ~10 s is counted (frb_exchange_status) and the kernel
+ * returns with that step's output undefined; frb_exchange_reset, called by every rank between two host barriers,
+ * restarts the epochs — e.g. after one rank raised an error and skipped a step.
  * Replaces the all-gather + frb_topk_merge_strided pair of facerecognition_b200/sharded.py; no reference
  * counterpart (the reference is single-device). */
 #define FRB_EXCHANGE_MAX_WORLD 8
@@ -196,6 +208,12 @@ int frb_exchange_destroy(frb_exchange *ex);
 int frb_exchange_topk_merge(frb_exchange *ex, const float *local_scores_dev, const int64_t *local_idx_dev,
                             int64_t n_query, int k, int largest, float *out_scores_dev, int64_t *out_idx_dev,
                             void *stream);
+/* timeouts: kernels of this rank that gave up waiting for a peer since creation / the last reset; epoch: steps
+ * finished.  Synchronises with the device. */
+int frb_exchange_status(frb_exchange *ex, int *timeouts, unsigned *epoch);
+/* Clears this rank's flags, epoch and timeout count (device-synchronising).  Collective by convention: every rank calls
+ * it after a barrier that guarantees no exchange kernel is in flight anywhere, and barriers again before the next step. */
+int frb_exchange_reset(frb_exchange *ex);
 /* Test hook: `world` contexts created in ONE process on one device act as the ranks of a single launch
  * (local_* and out_* are [world, n_query, k]); exercises the store / flag / wait / merge protocol without
  * a second GPU. */
@@ -262,9 +280,11 @@ int frb_chisq_dist_g8(const uint16_t *q_hist_dev, int64_t n_query, int q_cell_px
  *   length 8 * hist_len; the table error bounds |approx - exact| per query for EVERY row, rows outside the resulting
  *   window around the best approximate score cannot win, and the survivors are re-scored with the exact kernel's own
  *   arithmetic.  A query whose survivor list overflows is answered by the plain exact scan inside the same call.
- * Needs equal cell sizes on both sides (cell_px <= 255, u8 gallery), hist_len % 16 == 0, hist_len <= 16384.
+ * Needs equal cell sizes on both sides (cell_px <= 255, u8 gallery), hist_len % 16 == 0, hist_len <= 16384.  Rows need
+ * not sum to the same total (LBPH rows always do): the kernel ranks by sum_j f - (row total) / 4.
  *   stats_dev  int32 [4] or NULL, incremented: [0] queries answered by the exact fallback, [1] survivors re-scored,
- *              [2] raw candidates appended by the filter kernel, [3] unused.
+ *              [2] raw candidates appended by the filter kernel, [3] re-scored rows whose filter score missed the exact
+ *              one by more than the bound (audit of every survivor; such a query is re-answered by the exact scan).
  *   approx_scores_dev  fp32 [n_query, n_gallery] or NULL: every approximate sum_j f (tests / calibration only).
  * The first call for a (device, cell_px) builds and uploads the tables with blocking copies; later calls are
  * stream-ordered and capturable. */
