@@ -19,8 +19,11 @@ One JSON line on stdout (rank 0).  Extra legs inside it: `e2e` (host buffers: ea
 the batch from pinned memory, an all-gather replicates the queries over NVLink, results come back to the host,
 all inside the timed region), `roofline` (the tcgen05 kernel alone, event-timed per launch inside libfrb200),
 `cpu_baseline` (oracle port of the reference's batched numpy path on the host cores, rank 0 at N=1 only),
-`lbph` (K2/K3 secondary numbers with their own rooflines), `strong` (N > 1: the 4096-query batch on the sharded
-gallery, i.e. total work fixed).
+`lbph` (N = 1: K2, K3 in predict mode (one query: HBM) and batched mode (exact: FP32 pipe; tensor-core filter: tensor
+pipe), each with the roofline that actually bounds it), `strong` (N > 1: the 4096-query batch on the sharded gallery,
+i.e. total work fixed), `c4` (configs[3]: a 100M-row bf16 gallery sharded over the N ranks, 4096 / 256 / 1 queries)
+and `c5` (configs[4]: 1024 frames, LBPH extract + chi-square NN against 1M histograms sharded over the N ranks),
+`engine_e2e` (N = 1: configs[1] through RecognitionEngine.recognize_embeddings with host numpy in and out).
 """
 import argparse
 import json
@@ -41,6 +44,12 @@ TOPK = 5
 BLOCK_ROWS = 65536          # generation granularity: block b is seeded with 1234 + b on every rank / world size
 L2_FLUSH_BYTES = 256 << 20
 METRIC = "queries/sec @1M-512d cosine top-5"
+C4_ROWS = 100_000_000       # configs[3]
+C4_BLOCK = 1 << 20          # generation granularity of the 100M gallery (global block b is seeded with 9000 + b)
+C5_ROWS = 1_000_000         # configs[4]
+C5_FRAMES = 1024
+C5_CHUNK = 16384            # faces generated per chunk (global chunk c is seeded with 500 + c)
+FP32_PEAK_TFLOPS = 72.0     # measured on this GPU by profiles/micro/fp32_peak.cu (FFMA and FFMA2 alike), DESIGN.md §3
 
 
 def measured_peaks():
@@ -205,13 +214,15 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     val = sample_q * args.steps / dt
     cfg = workload_config(world, N_GALLERY, N_QUERY * world)
-    cfg["cpu_step"] = f"{sample_q}-query sample of the batch against the full 1M fp32 gallery"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "queries/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg,
             "cpu_baseline": {"value": val, "unit": "queries/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample_q} queries x full 1M fp32 gallery per step, numpy sgemm + argpartition, {cores} threads"},
+                             "sample": (f"each step = a {sample_q}-query sample of the batch x the full 1M fp32 gallery: numpy sgemm on {cores} threads + "
+                                        "argpartition, which numpy runs on ONE thread -- a floor for the reference's batched "
+                                        "numpy path, not a tuned CPU baseline (the reference's own per-query Python loop is "
+                                        "~20x slower still, BASELINE.md)")},
             "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -231,8 +242,32 @@ def synthetic_faces(torch, n, h, w, device, seed=2024):
     return faces
 
 
-def lbph_leg(torch, ops, NV, device, peaks):
-    """Secondary: K2 (LBP + grid histogram), K3 (chi-square scan) and the C5-shaped extract+match step."""
+def blocky_faces(torch, n, side, device, seed):
+    """Gray faces with structure at two scales (a 4x-upsampled random field + pixel noise): LBP count spread closer to
+    real faces than pure noise; the generator of tests/test_gpu_chisq_filter.py."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    base = torch.randint(0, 256, (n, side // 4 + 2, side // 4 + 2), generator=g, device=device).float()
+    up = base.repeat_interleave(4, 1).repeat_interleave(4, 2)[:, :side, :side]
+    return (up + 12.0 * torch.randn((n, side, side), generator=g, device=device)).clamp(0, 255).to(torch.uint8)
+
+
+def event_ms(torch, fn, reps, flush=None):
+    """Median device time of fn() over `reps` runs (CUDA events on the current stream; optional L2 flush before each)."""
+    times = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    return statistics.median(times)
+
+
+def lbph_leg(torch, ops, NV, device, peaks, flush):
+    """Secondary (N = 1): K2 (LBP + grid histogram), K3 in its three regimes, the front end, the C5-shaped step."""
     out = {}
     gen = torch.Generator(device=device).manual_seed(2024)
     n_faces = 65536
@@ -253,36 +288,59 @@ def lbph_leg(torch, ops, NV, device, peaks):
                       "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                    "frac": gbs / peaks["hbm_gbs"], **ncu_traffic("lbp_hist_kernel"),
                                    "note": "algorithmic bytes = 112*112 + 32768 per face; the kernel is issue-bound (DESIGN.md §3)"}}
-    # K3: 64 query histograms against a 100k-row u16 gallery (3.3 GB), each query streams the gallery
-    n_gal, n_q = 100_000, 64
-    gal = hist.view(torch.int16)[torch.randint(0, n_faces, (n_gal,), generator=gen, device=device)].contiguous().view(torch.uint16)
+    # ---- K3, predict mode: ONE query streams the gallery (what cv2's predict() does per call): HBM-bound --------
+    n_gal = 100_000
+    pick = torch.randint(0, n_faces, (n_gal,), generator=gen, device=device)
+    gal16 = hist.view(torch.int16)[pick].contiguous().view(torch.uint16)
+    gal8 = ops.compact_histograms(gal16, px)
+    q1 = hist[:1].contiguous()
+    for name, gal, row_bytes in (("predict_q1_u16_gallery", gal16, 32768), ("predict_q1_u8_gallery", gal8, 16384)):
+        for _ in range(2):
+            ops.chisq_topk(q1, px, gal, px, 1)
+        ms1 = event_ms(torch, lambda: ops.chisq_topk(q1, px, gal, px, 1), 5, flush)
+        NV.profile_read(NV.K_CHISQ)
+        flush.zero_()
+        ops.chisq_topk(q1, px, gal, px, 1)
+        kms, kn = NV.profile_read(NV.K_CHISQ)
+        gbs = n_gal * row_bytes / (kms / kn * 1e-3) / 1e9
+        out[name] = {"predicts_per_s": 1e3 / ms1, "ms_per_call": ms1, "ms_in_kernel": kms / kn, "gallery_rows": n_gal,
+                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                                  **ncu_traffic("chisq_kernel_q1_u16" if row_bytes == 32768 else "chisq_kernel_q1_u8"),
+                                  "note": f"physical bytes: one pass over the {n_gal} x {row_bytes} B gallery (L2 flushed before the call; "
+                                          "the gallery is 13-26x the L2)"}}
+    # ---- K3, batched EXACT scan (64 queries share each gallery chunk through L2): FP32-pipe bound ------------------
+    n_q = 64
     qh = hist[:n_q].contiguous()
-    for _ in range(2):
-        d, i = ops.chisq_topk(qh, px, gal, px, 1)
-    NV.profile_read(NV.K_CHISQ)
-    for _ in range(3):
-        d, i = ops.chisq_topk(qh, px, gal, px, 1)
-    ms, n = NV.profile_read(NV.K_CHISQ)
-    NV.profile_enable(False)
+    saved = ops.FILTER_ENABLED
+    ops.FILTER_ENABLED = False
+    try:
+        for _ in range(2):
+            d, i = ops.chisq_topk(qh, px, gal16, px, 1)
+        NV.profile_read(NV.K_CHISQ)
+        for _ in range(3):
+            d, i = ops.chisq_topk(qh, px, gal16, px, 1)
+        ms, n = NV.profile_read(NV.K_CHISQ)
+    finally:
+        ops.FILTER_ENABLED = saved
     per = ms / n
     pairs = n_gal * n_q
-    gbs = pairs * 32768 / (per * 1e-3) / 1e9
-    out["match"] = {"pairs_per_s": pairs / (per * 1e-3), "predicts_per_s_at_100k_gallery": n_q / (per * 1e-3), "ms_per_launch": per,
-                    "queries": n_q, "gallery_rows": n_gal,
-                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                 "frac": gbs / peaks["hbm_gbs"], **ncu_traffic("chisq_kernel"),
-                                 "note": "algorithmic bytes = 32768 B per (query, gallery row) pair: every query streams the gallery"}}
+    tf = pairs * 65536 / (per * 1e-3) / 1e12
+    out["match_exact_batched"] = {"pairs_per_s": pairs / (per * 1e-3), "predicts_per_s_at_100k_gallery": n_q / (per * 1e-3),
+                                  "ms_per_launch": per, "queries": n_q, "gallery_rows": n_gal,
+                                  "roofline": {"bound": "fp32", "achieved": tf, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+                                               "frac": tf / FP32_PEAK_TFLOPS, **ncu_traffic("chisq_kernel"),
+                                               "note": "SURVEY §8d: 65536 flop per (query, row) pair against the measured FP32 peak "
+                                                       "(72 TFLOP/s, profiles/micro/fp32_peak.cu); the gallery chunk is shared through L2, "
+                                                       "so DRAM traffic (`traffic`) is a small fraction of pairs x 32 KiB and HBM is not the bound"}}
     # front end: interleaved BGR video crops -> gray (3 B read + 1 B written per pixel)
     n_fr = 32768
     bgr = torch.randint(0, 256, (n_fr, 112, 112, 3), generator=gen, device=device, dtype=torch.uint8)
     for _ in range(2):
         gray = ops.bgr_to_gray(bgr)
-    NV.profile_enable(True)
     NV.profile_read(NV.K_BGR2GRAY)
     for _ in range(5):
         gray = ops.bgr_to_gray(bgr)
     ms, n = NV.profile_read(NV.K_BGR2GRAY)
-    NV.profile_enable(False)
     gbs = n_fr * 112 * 112 * 4 / (ms / n * 1e-3) / 1e9
     out["bgr2gray"] = {"frames_per_s": n_fr / (ms / n * 1e-3), "ms_per_launch": ms / n, "frames_per_launch": n_fr,
                        "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -294,37 +352,193 @@ def lbph_leg(torch, ops, NV, device, peaks):
     big = torch.randint(0, 256, (n_fr, sh, sw, 3), generator=gen, device=device, dtype=torch.uint8)
     for _ in range(2):
         small = ops.resize_linear(big, (112, 112), to_gray=True)
-    NV.profile_enable(True)
     NV.profile_read(NV.K_RESIZE)
     for _ in range(5):
         small = ops.resize_linear(big, (112, 112), to_gray=True)
     ms, n = NV.profile_read(NV.K_RESIZE)
-    NV.profile_enable(False)
     gbs = n_fr * (sh * sw * 3 + 112 * 112) / (ms / n * 1e-3) / 1e9
     out["resize_gray"] = {"frames_per_s": n_fr / (ms / n * 1e-3), "ms_per_launch": ms / n, "frames_per_launch": n_fr,
                           "frame": f"{sh}x{sw}x3 -> 112x112 gray",
                           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                        "frac": gbs / peaks["hbm_gbs"], "traffic": None,
                                        "note": "algorithmic bytes = the whole source frame read once + the gray crop written"}}
-    del big, small
+    del big, small, gal16, gal8, faces, hist
+    NV.profile_enable(False)
     # C5 shape on one GPU's share: 1024 frames, extract + chi-square NN against 125 000 histograms (1M / 8 GPUs)
-    frames = faces[:1024].contiguous()
-    gal5 = hist.view(torch.int16)[torch.randint(0, n_faces, (125_000,), generator=gen, device=device)].contiguous().view(torch.uint16)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    qh5, px5 = ops.lbp_hist(frames)
-    ops.chisq_topk(qh5[:64].contiguous(), px5, gal5, px5, 1)
-    torch.cuda.synchronize()
-    ev0.record()
-    qh5, px5 = ops.lbp_hist(frames)
-    d5, i5 = ops.chisq_topk(qh5, px5, gal5, px5, 1)
-    ev1.record()
-    torch.cuda.synchronize()
-    ms5 = ev0.elapsed_time(ev1)
-    gbs5 = (1024 * 125_000 * 32768 + 1024 * bytes_per_face) / (ms5 * 1e-3) / 1e9
-    out["extract_match_c5_share"] = {"faces_per_s": 1024 / (ms5 * 1e-3), "ms_per_step": ms5, "frames": 1024, "gallery_rows": 125_000,
-                                     "roofline": {"bound": "hbm", "achieved": gbs5, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                                  "frac": gbs5 / peaks["hbm_gbs"], "traffic": None}}
+    out["extract_match_c5_share"] = c5_step(torch, ops, NV, device, peaks, 125_000, 0, None)
     return out
+
+
+def c5_gallery(torch, ops, device, lo, hi):
+    """u8 LBPH histograms of global gallery faces [lo, hi) (chunk c of C5_CHUNK faces is seeded with 500 + c on any rank)."""
+    parts, px = [], None
+    for c in range(lo // C5_CHUNK, (hi + C5_CHUNK - 1) // C5_CHUNK):
+        r0 = c * C5_CHUNK
+        h, px = ops.lbp_hist(blocky_faces(torch, C5_CHUNK, 112, device, 500 + c))
+        a, e = max(lo, r0), min(hi, r0 + C5_CHUNK)
+        parts.append(ops.compact_histograms(h[a - r0:e - r0].contiguous(), px))
+    return torch.cat(parts, 0), px
+
+
+def c5_step(torch, ops, NV, device, peaks, rows, lo, search_factory, reps=3):
+    """configs[4]-shaped step on this rank: C5_FRAMES frames -> LBP histograms (K2) -> chi-square nearest neighbour against
+    gallery rows [lo, lo + rows) through the tensor-core filter + exact re-score (-> cross-rank merge when sharded)."""
+    gal8, px = c5_gallery(torch, ops, device, lo, lo + rows)
+    gen = torch.Generator(device=device).manual_seed(77)
+    n_plant = C5_FRAMES // 4
+    src = torch.randint(0, min(C5_CHUNK, C5_ROWS), (n_plant,), generator=gen, device=device)      # global rows in chunk 0
+    chunk0 = blocky_faces(torch, C5_CHUNK, 112, device, 500)
+    planted = (chunk0[src].float() + 6.0 * torch.randn((n_plant, 112, 112), generator=gen, device=device)).clamp(0, 255).to(torch.uint8)
+    frames = torch.cat([planted, blocky_faces(torch, C5_FRAMES - n_plant, 112, device, 31337)], 0).contiguous()
+    del chunk0
+    search = search_factory(gal8, px) if search_factory else None
+    stats = torch.zeros(4, dtype=torch.int32, device=device)
+
+    def step():
+        qh, qpx = ops.lbp_hist(frames)
+        if search is not None:
+            return search.search(qh, 1)
+        return ops.chisq_top1_filtered(qh, gal8, px, idx_base=lo, stats=stats)
+
+    for _ in range(2):
+        d, i = step()
+    torch.cuda.synchronize()
+    NV.profile_enable(True)
+    NV.profile_read(NV.K_CHISQ_FILTER)
+    stats.zero_()
+    ms = event_ms(torch, step, reps)
+    kms, kn = NV.profile_read(NV.K_CHISQ_FILTER)
+    NV.profile_enable(False)
+    d, i = step()
+    flop = 2.0 * C5_FRAMES * rows * gal8.shape[1] * 8
+    tf = flop / (kms / max(kn, 1) * 1e-3) / 1e12 if kn else 0.0
+    st = stats.cpu().tolist()
+    return {"faces_per_s": C5_FRAMES / (ms * 1e-3), "ms_per_step": ms, "frames": C5_FRAMES, "gallery_rows": rows,
+            "gallery": "u8 LBPH histograms (16 KiB per face) of blocky synthetic 112x112 faces; 1/4 of the frames are noisy re-shots "
+                       "of gallery faces, 3/4 have no match",
+            "planted_top1": (i[:n_plant, 0], src),
+            "filter": {"fallback_queries_per_step": st[0] / max(reps, 1), "survivors_per_query": st[1] / max(reps, 1) / C5_FRAMES,
+                       "audit_violations": st[3]} if search is None else None,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"],
+                         "frac_of_sustained": tf / peaks["bf16_tflops_sustained"], "kernel": "chisq_filter_kernel",
+                         "ms_in_kernel": kms / max(kn, 1), "traffic": (ncu_traffic("chisq_filter_kernel")["traffic"] if rows == 125_000 else None),
+                         "note": "algorithmic flops = 2 x frames x rows x 16384 bins x 8 fp16 features (the rank-8 feature GEMM that "
+                                 "decides every pair; exact re-score of the few survivors and K2 are inside ms_per_step); peak = "
+                                 "the measured cuBLAS bf16 figure (fp16 runs at the same tensor rate)"}}
+
+
+def c4_leg(torch, dist, ops, NV, device, peaks, world, rank, cosine_sharded, shard_bounds, steps=3):
+    """configs[3]: 100M-row bf16 gallery sharded by identity over the ranks; the SAME 4096-query batch on every N, so
+    ms_per_step x N flat = linear scaling.  Also 256-query and single-query latency through the same sharded search."""
+    lo, hi = shard_bounds(C4_ROWS, world, rank)
+    free, _ = torch.cuda.mem_get_info(device)
+    need = (hi - lo) * DIM * 2 + (6 << 30)
+    if free < need:
+        return {"skipped": f"shard needs {need >> 30} GiB, {free >> 30} GiB free"}
+    shard = torch.empty((hi - lo, DIM), dtype=torch.bfloat16, device=device)
+    gen_q = torch.Generator(device=device).manual_seed(99)
+    src = torch.randint(0, C4_ROWS, (N_QUERY,), generator=gen_q, device=device)
+    noise = torch.randn((N_QUERY, DIM), generator=gen_q, device=device)
+    n_rand = N_QUERY // 10
+    for b in range(lo // C4_BLOCK, (hi + C4_BLOCK - 1) // C4_BLOCK):
+        r0, r1 = b * C4_BLOCK, min((b + 1) * C4_BLOCK, C4_ROWS)
+        gen = torch.Generator(device=device).manual_seed(9000 + b)
+        rows = ops.normalize_rows(torch.randn((r1 - r0, DIM), generator=gen, device=device), NV.FRB_QNORM_CLAMP, torch.bfloat16)
+        a, e = max(lo, r0), min(hi, r1)
+        shard[a - lo:e - lo] = rows[a - r0:e - r0]
+        del rows
+    # planted queries: the owner of a source row contributes (its stored bf16 row + noise), one all-reduce replicates
+    queries = torch.zeros((N_QUERY, DIM), dtype=torch.float32, device=device)
+    mine = (src >= lo) & (src < hi)
+    mine[:n_rand] = False
+    queries[mine] = shard[src[mine] - lo].float() + 0.03 * noise[mine]
+    if world > 1:
+        dist.all_reduce(queries)
+    queries[:n_rand] = noise[:n_rand]
+    search = cosine_sharded(shard, lo, qnorm_mode=NV.FRB_QNORM_CLAMP)
+
+    def timed(q, reps, graph):
+        for _ in range(2):
+            s, i = search.search(q, TOPK, graph=graph)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in ev:
+            a.record()
+            s, i = search.search(q, TOPK, graph=graph)
+            b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([statistics.median(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), s, i
+
+    NV.profile_enable(True)
+    NV.profile_read(NV.K_COSINE_TC)
+    ms, s, i = timed(queries, steps, False)
+    k_ms, k_n = NV.profile_read(NV.K_COSINE_TC)
+    NV.profile_enable(False)
+    ok = torch.tensor([1 if bool(torch.equal(i[n_rand:, 0], src[n_rand:])) else 0], device=device)
+    kernel_ms = k_ms / (steps + 2)                       # summed over the launches of one step (warm-up pass + main pass)
+    tf = 2.0 * N_QUERY * (hi - lo) * DIM / (kernel_ms * 1e-3) / 1e12
+    fr = torch.tensor([tf], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        dist.all_reduce(fr, op=dist.ReduceOp.MIN)
+    q256 = queries[n_rand:n_rand + 256].contiguous()
+    q1 = queries[n_rand:n_rand + 1].contiguous()
+    ms256, _, _ = timed(q256, 5, True)
+    ms1, _, i1 = timed(q1, 9, True)
+    ok1 = bool(int(i1[0, 0]) == int(src[n_rand]))
+    del shard, search
+    torch.cuda.empty_cache()
+    return {"workload": "configs[3]: 100M x 512 bf16 gallery sharded by identity, 4096-query batch (fixed for every N), top-5",
+            "rows_total": C4_ROWS, "rows_per_gpu": hi - lo, "gallery_bytes_per_gpu": (hi - lo) * DIM * 2,
+            "ms_per_step": ms, "ms_per_step_x_gpus": ms * world, "queries_per_s": N_QUERY / (ms * 1e-3),
+            "roofline": {"bound": "tensor", "kernel": "cosine_tc_kernel", "achieved": float(fr.item()), "unit": "TFLOP/s per GPU (slowest rank)",
+                         "peak": peaks["bf16_tflops_sustained"], "frac": float(fr.item()) / peaks["bf16_tflops_sustained"],
+                         "frac_of_burst": float(fr.item()) / peaks["bf16_tflops"], "ms_per_step_in_kernel": kernel_ms, "traffic": None,
+                         "note": "a step keeps the tensor pipe busy for 0.04-0.3 s: the cuBLAS SUSTAINED figure is the denominator"},
+            "latency_ms": {"q4096": ms, "q256": ms256, "q1": ms1,
+                           "note": "whole sharded call (local search + NVLink exchange), CUDA-graph replay for 256 / 1 queries; "
+                                   "one query streams the shard once: HBM-bound row streaming kernel"},
+            "q1_gbs_per_gpu": (hi - lo) * DIM * 2 / (ms1 * 1e-3) / 1e9,
+            "planted_top1_correct": bool(ok.item()) and ok1}
+
+
+def engine_e2e_leg(torch, np, F):
+    """configs[1] through the reference-named API: RecognitionEngine.recognize_embeddings, host numpy in, Python tuples out
+    (ArcFace 512-d cosine, 10k-identity dict gallery, 256-query batch, fp32 exact path, top-1 + threshold)."""
+    rng = np.random.default_rng(7)
+    gal = rng.standard_normal((10_000, DIM)).astype(np.float32)
+    gal /= np.linalg.norm(gal, axis=1, keepdims=True)
+    eng = F.RecognitionEngine(model_path=None, threshold=0.5, use_face_detection=False)
+    eng.db = {f"id_{i:05d}": g for i, g in enumerate(gal)}
+    src = rng.integers(0, 10_000, 256)
+    q = (gal[src] + 0.03 * rng.standard_normal((256, DIM))).astype(np.float32)
+    for _ in range(3):
+        res = eng.recognize_embeddings(q)
+    t0 = time.perf_counter()
+    reps = 20
+    for _ in range(reps):
+        res = eng.recognize_embeddings(q)
+    dt = (time.perf_counter() - t0) / reps
+    ok = all(r[0] == f"id_{j:05d}" for r, j in zip(res, src))
+    qd = torch.from_numpy(q).cuda()
+    for _ in range(3):
+        eng.recognize_embeddings(qd)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        res_d = eng.recognize_embeddings(qd)
+    dt_d = (time.perf_counter() - t0) / reps
+    return {"workload": "configs[1]: ArcFace 512-d cosine, 10k-identity dict gallery, 256-query batch, fp32, top-5 + threshold",
+            "queries_per_s": 256 / dt, "ms_per_call": dt * 1e3, "h2d_bytes_per_call": 256 * DIM * 4, "d2h_bytes_per_call": 256 * 5 * 12,
+            "device_tensor_in": {"queries_per_s": 256 / dt_d, "ms_per_call": dt_d * 1e3},
+            "all_identities_correct": bool(ok) and all(r[0] == f"id_{j:05d}" for r, j in zip(res_d, src)),
+            "note": "wall clock around RecognitionEngine.recognize_embeddings (numpy in -> list of (name, score, top-5) out), "
+                    "gallery resident on the GPU as engine state; device_tensor_in = the same call with a CUDA tensor"}
 
 
 def main():
@@ -337,6 +551,9 @@ def main():
     ap.add_argument("--queries", type=int, default=N_QUERY, help="queries per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lbph", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip configs[3] (100M-row sharded gallery)")
+    ap.add_argument("--no-c5", action="store_true", help="skip configs[4] (LBPH 1024 frames vs 1M sharded histograms)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying its CUDA graph")
     ap.add_argument("--min-warm-seconds", type=float, default=1.0,
                     help="keep warming until this much time has passed under load (clock samples); 0 for ncu launch lists")
     args = ap.parse_args()
@@ -350,7 +567,7 @@ def main():
     import facerecognition_b200 as F  # loads libfrb200.so or raises
     from facerecognition_b200 import _native as NV
     from facerecognition_b200 import ops
-    from facerecognition_b200.sharded import HostBatchPipeline, cosine_sharded, shard_bounds
+    from facerecognition_b200.sharded import HostBatchPipeline, chisq_sharded, cosine_sharded, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -368,19 +585,22 @@ def main():
     search = cosine_sharded(shard, lo, qnorm_mode=NV.FRB_QNORM_CLAMP)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
 
+    use_graph = not args.no_graph
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_steps(queries, steps):
+    def timed_steps(queries, steps, graph=None):
         """K steps, CUDA events per step on the launching stream, L2 flushed outside the brackets; MAX over ranks (ms)."""
+        graph = use_graph if graph is None else graph
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
         for a, b in ev:
             flush.zero_()
             a.record()
-            s, i = search.search(queries, TOPK)
+            s, i = search.search(queries, TOPK, graph=graph)
             b.record()
         barrier()
         total = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=device)
@@ -393,19 +613,25 @@ def main():
         t_w = time.perf_counter()
         done = 0
         while done < warmup or time.perf_counter() - t_w < args.min_warm_seconds:      # >= W steps and >= 1 s under load (clock samples)
-            s, i = search.search(q_dev, TOPK)
+            s, i = search.search(q_dev, TOPK, graph=use_graph)
             done += 1
             if done % 16 == 0:
                 torch.cuda.synchronize()
         barrier()
         # correctness of what is being timed: planted queries must come back as their source row
         ok = bool(torch.equal(i[n_rand:, 0], src[n_rand:]))
+        total_ms, s, i = timed_steps(q_dev, args.steps)
+        value = n_query * args.steps / (total_ms * 1e-3)
+        # the roofline's kernel time: the same K steps once more, launched kernel by kernel so that libfrb200 can bracket
+        # every cosine_tc_kernel launch with an event pair on the launching stream (a graph replay has no host-side
+        # launch to bracket); same inputs, same L2 flush, directly after the timed region
+        for _ in range(3):                       # torch.cuda.graph() empties the caching allocator: re-warm the eager path
+            search.search(q_dev, TOPK, graph=False)
         NV.profile_enable(True)
         NV.profile_read(NV.K_COSINE_TC)
-        total_ms, s, i = timed_steps(q_dev, args.steps)
+        eager_ms, _, _ = timed_steps(q_dev, args.steps, graph=False)
         k_ms, k_n = NV.profile_read(NV.K_COSINE_TC)
         NV.profile_enable(False)
-        value = n_query * args.steps / (total_ms * 1e-3)
         # the step launches cosine_tc_kernel twice (threshold warm-up pass over ~1/64 of the shard + main pass);
         # achieved = the step's algorithmic flops / the summed device time of those launches
         kernel_ms_per_step = k_ms / args.steps
@@ -421,13 +647,16 @@ def main():
         q_host = q_dev[q0:q1].cpu().pin_memory()
         out_s = torch.empty((q_per_gpu, TOPK), dtype=torch.float32).pin_memory()
         out_i = torch.empty((q_per_gpu, TOPK), dtype=torch.int64).pin_memory()
-        q_stage = torch.empty_like(q_dev)
+        q_stage = torch.empty((q_per_gpu, DIM), dtype=torch.float32, device=device) if world > 1 else torch.empty_like(q_dev)
+        q_stage16 = torch.empty((n_query, DIM), dtype=torch.bfloat16, device=device) if world > 1 else None
 
         def e2e_step():
-            q_stage[q0:q1].copy_(q_host, non_blocking=True)
+            q_stage.copy_(q_host, non_blocking=True)
             if world > 1:
-                dist.all_gather_into_tensor(q_stage, q_stage[q0:q1])
-            s, i = search.search(q_stage, TOPK)
+                # each rank normalises ITS slice, one all-gather of bf16 rows, tensor-core search on the gathered batch
+                s, i = search.search(search.gather_normalized(q_stage, q_stage16, q0), TOPK, graph=use_graph)
+            else:
+                s, i = search.search(q_stage, TOPK, graph=use_graph)
             out_s.copy_(s[q0:q1], non_blocking=True)
             out_i.copy_(i[q0:q1], non_blocking=True)
             torch.cuda.synchronize()
@@ -452,7 +681,7 @@ def main():
 
         # the serving form of the same call: sharded.HostBatchPipeline keeps two batches in flight so the copies of
         # one batch overlap the search of the other (every batch's H2D and D2H are still inside the timed region)
-        pipe = HostBatchPipeline(search.search, n_query, DIM, TOPK, device, rows=(q0, q1))
+        pipe = HostBatchPipeline(search, n_query, DIM, TOPK, device, rows=(q0, q1), graph=use_graph)
         last = {}
 
         def run_pipelined(n):
@@ -473,7 +702,7 @@ def main():
             # total work fixed: the 4096-query batch against the sharded gallery
             qs = q_dev[:q_per_gpu].contiguous()
             for _ in range(3):
-                search.search(qs, TOPK)
+                search.search(qs, TOPK, graph=use_graph)
             ms_s, _, _ = timed_steps(qs, args.steps)
             strong = {"value": q_per_gpu * args.steps / (ms_s * 1e-3), "unit": "queries/s", "ms_per_step": ms_s / args.steps,
                       "queries_per_step": q_per_gpu, "note": "same 1M gallery, batch NOT grown: total work fixed"}
@@ -496,14 +725,18 @@ def main():
         "config": workload_config(world, n_gallery, n_query),
         "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": n_query * DIM * 4,
                 "d2h_bytes_per_step": n_query * TOPK * 12, "blocking_call_value": e2e_sync,
-                "note": "pinned host fp32 queries -> GPU (each rank its 1/N slice, all-gathered over NVLink), search, "
-                        "(score, id) lists -> host; bytes are whole-job totals; gallery resident in HBM as engine state. "
+                "note": "pinned host fp32 queries -> GPU (each rank its 1/N slice, normalised there, bf16 rows all-gathered over "
+                        "NVLink), search, (score, id) lists -> host; bytes are whole-job totals; gallery resident in HBM as engine state. "
                         "value: sharded.HostBatchPipeline, two batches in flight (copies of one overlap the search of "
                         "the other); blocking_call_value: one batch at a time, host waits for each"},
         "gpu_launches": launches_per_step * args.steps,
+        "launch_mode": "the step's kernels are replayed from one CUDA graph (ShardedSearch.search(graph=True))" if use_graph else "kernel by kernel",
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      **traffic, "kernel": "cosine_tc_kernel", "ms_per_step_in_kernel": kernel_ms_per_step,
                      "launches_timed": k_n, "launches_per_step": tc_per_step, "flops_per_step": flops_per_step,
+                     "ms_per_step_kernel_by_kernel": eager_ms / args.steps,
+                     "timed_on": ("the K steps repeated kernel by kernel right after the graph-replayed timed region (event pairs around "
+                                  "each launch inside libfrb200)" if use_graph else "the timed region itself"),
                      "frac_of_burst": achieved / peaks["bf16_tflops"], "frac_of_sustained": achieved / peaks["bf16_tflops_sustained"],
                      "peak_source": peaks["source"] + (", bf16 SUSTAINED figure: the timed steps ran power-capped (median SM clock < 90 % of max, see clocks) after >= 1 s of load"
                                                        if sustained else ", bf16 BURST figure: the SM clock stayed near its maximum during the run")},
@@ -528,11 +761,45 @@ def main():
         line["cpu_baseline"] = {"value": done / dt, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"{done} of the {n_query} queries x full 1M fp32 gallery, numpy sgemm + argpartition (oracle.cosine.batched_topk_fast)"}
         del gal_f32
+    del shard, search, q_dev
+    torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_lbph:
         try:
-            line["lbph"] = lbph_leg(torch, ops, NV, device, peaks)
+            line["lbph"] = lbph_leg(torch, ops, NV, device, peaks, flush)
+            pl = line["lbph"]["extract_match_c5_share"].pop("planted_top1")
+            line["lbph"]["extract_match_c5_share"]["planted_top1_correct"] = bool(torch.equal(pl[0], pl[1]))
         except Exception as e:  # the secondary leg must never cost the headline line
             line["lbph"] = {"error": repr(e)}
+        try:
+            line["engine_e2e"] = engine_e2e_leg(torch, np, F)
+        except Exception as e:
+            line["engine_e2e"] = {"error": repr(e)}
+    if not args.no_c5:
+        try:
+            lo5, hi5 = shard_bounds(C5_ROWS, world, rank)
+            c5 = c5_step(torch, ops, NV, device, peaks, hi5 - lo5, lo5,
+                         (lambda g8, px: chisq_sharded(g8, px, lo5)) if world > 1 else None)
+            got, want = c5.pop("planted_top1")
+            ok5 = torch.tensor([1 if bool(torch.equal(got, want)) else 0], device=device)
+            t5 = torch.tensor([c5["ms_per_step"], -c5["roofline"]["achieved"]], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(ok5, op=dist.ReduceOp.MIN)
+                dist.all_reduce(t5, op=dist.ReduceOp.MAX)            # slowest rank's step time, lowest kernel rate
+            c5.update({"workload": "configs[4]: LBPH extract + chi-square NN, 1024 frames of 112x112 vs 1M histograms sharded by identity",
+                       "rows_total": C5_ROWS, "ms_per_step": float(t5[0]), "faces_per_s": C5_FRAMES / (float(t5[0]) * 1e-3),
+                       "ms_per_step_x_gpus": float(t5[0]) * world, "planted_top1_correct": bool(ok5.item())})
+            c5["roofline"]["achieved"] = -float(t5[1])
+            c5["roofline"]["frac"] = c5["roofline"]["achieved"] / peaks["bf16_tflops"]
+            c5["roofline"]["frac_of_sustained"] = c5["roofline"]["achieved"] / peaks["bf16_tflops_sustained"]
+            line["c5"] = c5
+        except Exception as e:
+            line["c5"] = {"error": repr(e)}
+        torch.cuda.empty_cache()
+    if not args.no_c4:
+        try:
+            line["c4"] = c4_leg(torch, dist, ops, NV, device, peaks, world, rank, cosine_sharded, shard_bounds)
+        except Exception as e:
+            line["c4"] = {"error": repr(e)}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

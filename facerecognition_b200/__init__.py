@@ -11,7 +11,7 @@ Importing the package loads libfrb200.so and fails loudly if it is missing: ther
 from . import _native  # noqa: F401  (loads libfrb200.so; raises ImportError if it is not built)
 from . import ops  # noqa: F401
 from .lbph import (LBPHFaceRecognizer, LBPHFaceRecognizer_create, evaluate_lbph, find_optimal_threshold,  # noqa: F401
-                   preprocess_frames_device, recognize_face, train_lbph_model)
+                   preprocess_frames_device, recognize_face, recognize_face_web, train_lbph_model, web_confidence)
 from .recognition_engine import (DeviceGallery, FlatIPIndex, RecognitionEngine, build_db_from_embeddings,  # noqa: F401
                                  build_faiss_index, compute_prototypes, cosine_similarity,
                                  create_engine_from_embeddings_dir, group_plan, match_facenet, mean_embedding)

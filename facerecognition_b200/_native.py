@@ -63,6 +63,10 @@ SIGNATURES = {
     "frb_lbp_codes_u8": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "frb_lbp_hist_u8": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p]),
+    "frb_lbp_hist_u8_counts8": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                        c_void_p]),
+    "frb_counts_u16_to_u8": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "frb_index_remap": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "frb_chisq_topk_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
     "frb_chisq_topk": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_void_p,
                                c_void_p, c_void_p, c_size_t, c_void_p]),

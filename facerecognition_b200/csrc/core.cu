@@ -561,6 +561,28 @@ __global__ void __launch_bounds__(256) topk_merge_lists_kernel(const float *__re
     merge_query<LARGEST, WQ>(c, (int64_t)n_lists * k, k, os + q * k, oi + q * k);
 }
 
+// u16 counts -> u8 counts (the caller guarantees every count <= 255), 8 per thread
+__global__ void __launch_bounds__(256) counts_narrow_kernel(const uint16_t *__restrict__ src, int64_t n, uint8_t *__restrict__ dst)
+{
+    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
+    if (i >= n) return;
+    if (i + 8 <= n && ((reinterpret_cast<uintptr_t>(src + i) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst + i) & 7) == 0)) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(src + i);
+        *reinterpret_cast<uint2 *>(dst + i) = make_uint2(__byte_perm(v.x, v.y, 0x6420), __byte_perm(v.z, v.w, 0x6420));
+    } else {
+        for (int64_t j = i; j < n && j < i + 8; j++) dst[j] = (uint8_t)src[j];
+    }
+}
+
+__global__ void __launch_bounds__(256) index_remap_kernel(int64_t *__restrict__ idx, int64_t n, const int64_t *__restrict__ table,
+                                                          int64_t table_len)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int64_t v = idx[i];
+    if (v >= 0 && v < table_len) idx[i] = table[v];
+}
+
 int topk_merge_compact(const float *cs, const int64_t *ci, const int *cnt, int64_t cap, int64_t n_query, int k, int largest,
                        float *os, int64_t *oi, cudaStream_t st)
 {
@@ -683,6 +705,27 @@ static int topk_merge_launch(const char *fn, const float *cs, const int64_t *ci,
             topk_merge_kernel<false><<<grid, 128, 0, st>>>(cs, ci, s_stride, i_stride, n_lists, n_query, k, os, oi);
     }
     FRB_LAUNCH_OK("topk_merge_kernel");
+    return FRB_OK;
+}
+
+int frb_counts_u16_to_u8(const uint16_t *src, int64_t n, uint8_t *dst, void *stream)
+{
+    FRB_CHECK_ARG(n >= 0, "frb_counts_u16_to_u8: n=%lld", (long long)n);
+    if (n == 0) return FRB_OK;
+    FRB_CHECK_ARG(src && dst, "frb_counts_u16_to_u8: null pointer");
+    const int64_t threads = (n + 7) / 8;
+    counts_narrow_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, n, dst);
+    FRB_LAUNCH_OK("counts_narrow_kernel");
+    return FRB_OK;
+}
+
+int frb_index_remap(int64_t *idx, int64_t n, const int64_t *table, int64_t table_len, void *stream)
+{
+    FRB_CHECK_ARG(n >= 0 && table_len >= 0, "frb_index_remap: n=%lld table_len=%lld", (long long)n, (long long)table_len);
+    if (n == 0) return FRB_OK;
+    FRB_CHECK_ARG(idx && (table || table_len == 0), "frb_index_remap: null pointer");
+    index_remap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(idx, n, table, table_len);
+    FRB_LAUNCH_OK("index_remap_kernel");
     return FRB_OK;
 }
 

@@ -529,6 +529,42 @@ static void tc_split(int64_t tile_begin, int64_t tile_end, int64_t want_groups, 
     ps->group_base = group_base;
 }
 
+// Group count whose round-robin schedule (CTA p runs units p, p + P, ...) finishes earliest.  The rule of thumb above
+// (16 units per CTA) is exact when n_qtiles divides P * 16 (32 query tiles: 2368 units on 148 CTAs) but loses a whole
+// round of ~50-tile units otherwise: 256 query tiles x 10 groups = 2560 units = 17.3 rounds -> 18 (measured on one GPU,
+// same flops: 2.74 ms at 4096 x 1M against 2.99 ms at 32768 x 125k, profiles/r2_tc_shapes.txt).  Cost model per unit:
+// its tiles + ~1 tile-time (the query tile is single-buffered: the next unit's 128 KB A load starts when the last MMA
+// of this one retires).  Evaluated exactly per CTA for every feasible group count.
+static int64_t tc_balanced_groups(int64_t tiles, int64_t n_qt, int P, int64_t fallback)
+{
+    static thread_local int64_t c_tiles = -1, c_qt = -1, c_best = 0;
+    static thread_local int c_P = 0;
+    if (tiles == c_tiles && n_qt == c_qt && P == c_P) return c_best;
+    const double ov = 1.0;
+    int64_t g_max = (int64_t)32 * P / n_qt + 1;
+    if (g_max > tiles) g_max = tiles;
+    if (g_max > 1024) g_max = 1024;
+    double best_t = 1e300;
+    int64_t best = fallback;
+    for (int64_t g = 1; g <= g_max; g++) {
+        const int64_t tpg = (tiles + g - 1) / g;
+        if ((tiles + tpg - 1) / tpg != g) continue;           // same split as a smaller g
+        if (tpg < 12 && g > 1) break;                          // shorter units only add per-unit overhead
+        if (tpg > 64) continue;                                // measured: units of ~120 tiles ran 8 % slower than the model says
+        const int64_t U = g * n_qt, last0 = U - n_qt, last_len = tiles - (g - 1) * tpg;
+        double worst = 0.0;
+        for (int p = 0; p < P && p < U; p++) {
+            const int64_t cnt = (U - 1 - p) / P + 1;                                             // units of CTA p
+            const int64_t cl = last0 > p ? (U - 1 - p) / P - (last0 - 1 - p) / P : cnt;          // ... of which in the last group
+            const double t = (double)(cnt - cl) * ((double)tpg + ov) + (double)cl * ((double)last_len + ov);
+            if (t > worst) worst = t;
+        }
+        if (worst < best_t - 1e-9) { best_t = worst; best = g; }
+    }
+    c_tiles = tiles; c_qt = n_qt; c_P = P; c_best = best;
+    return best;
+}
+
 static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
 {
     TcPlan pl;
@@ -568,6 +604,11 @@ static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
         if (want_groups < 1) want_groups = 1;
     }
     if (want_groups > 1024) want_groups = 1024;
+    {
+        const char *bal = getenv("FRB_TC_BALANCE");      // experiments: 0 keeps the rule of thumb
+        if (k <= kTcShareMinK && tiles_per_cta >= 48 && !(bal && bal[0] == '0'))
+            want_groups = tc_balanced_groups(main_tiles, pl.n_qtiles, sms, want_groups);
+    }
     tc_split(warm_tiles, pl.n_tiles, want_groups, pl.warm.n_groups, &pl.main);
     pl.n_groups = pl.warm.n_groups + pl.main.n_groups;
     size_t n = (size_t)pl.n_groups * (size_t)nq * (size_t)k;

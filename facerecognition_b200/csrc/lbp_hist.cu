@@ -222,11 +222,45 @@ __device__ __forceinline__ void lbp_emit_row2(const LbpRow2 &top, const LbpRow2 
     }
 }
 
-template <bool ALIGNED16>
+// Write-out of one cell pair's counters (u32 words: low half = upper cell's bin, high half = lower cell's bin) and their
+// reset for the next image.  OUT8 = false: [cell][bin] u16, 8 bins per 128-bit store; OUT8 = true: u8 counts (valid when
+// a cell has <= 255 pixels: the gallery form the chi-square kernels stream), 16 bins per 128-bit store.
+__device__ __forceinline__ uint32_t lbp_pack8(uint4 u, unsigned sel)
+{
+    return __byte_perm(__byte_perm(u.x, u.y, sel), __byte_perm(u.z, u.w, sel), 0x5410);
+}
+template <bool OUT8>
+__device__ __forceinline__ void lbp_write_pair(uint4 *hist_pair, void *out_image, unsigned pair, unsigned j, bool has_lower,
+                                               unsigned lower_cell)
+{
+    if (OUT8) {
+        uint4 *grp = hist_pair + 4 * j;                      // 16 bins
+        const uint4 a = grp[0], b = grp[1], c = grp[2], d = grp[3];
+        grp[0] = grp[1] = grp[2] = grp[3] = make_uint4(0, 0, 0, 0);
+        uint4 *dst = reinterpret_cast<uint4 *>(out_image);   // [cell][bin] u8: 16 groups per cell
+        dst[pair * 16 + j] = make_uint4(lbp_pack8(a, 0x0040), lbp_pack8(b, 0x0040), lbp_pack8(c, 0x0040), lbp_pack8(d, 0x0040));
+        if (has_lower)
+            dst[lower_cell * 16 + j] = make_uint4(lbp_pack8(a, 0x0062), lbp_pack8(b, 0x0062), lbp_pack8(c, 0x0062), lbp_pack8(d, 0x0062));
+    } else {
+        uint4 *grp = hist_pair + 2 * j;                      // 8 bins
+        const uint4 u = grp[0], v = grp[1];
+        grp[0] = make_uint4(0, 0, 0, 0);
+        grp[1] = make_uint4(0, 0, 0, 0);
+        uint4 *dst = reinterpret_cast<uint4 *>(out_image);   // [cell][bin] u16: 32 groups per cell
+        dst[pair * 32 + j] = make_uint4(__byte_perm(u.x, u.y, 0x5410), __byte_perm(u.z, u.w, 0x5410),
+                                        __byte_perm(v.x, v.y, 0x5410), __byte_perm(v.z, v.w, 0x5410));
+        if (has_lower)
+            dst[lower_cell * 32 + j] = make_uint4(__byte_perm(u.x, u.y, 0x7632), __byte_perm(u.z, u.w, 0x7632),
+                                                  __byte_perm(v.x, v.y, 0x7632), __byte_perm(v.z, v.w, 0x7632));
+    }
+}
+
+template <bool ALIGNED16, bool OUT8>
 __global__ void __launch_bounds__(kLbpMaxThreads, 3) lbp_hist_kernel(const uint8_t *__restrict__ img, int64_t count, int rows,
                                                                      int cols, int grid_x, int grid_y, int img_smem_bytes,
-                                                                     uint16_t *__restrict__ out)
+                                                                     void *__restrict__ out_v)
 {
+    unsigned char *out = reinterpret_cast<unsigned char *>(out_v);
     // shared: [2 mbarriers][image buffer 0][image buffer 1][counters]
     extern __shared__ __align__(16) unsigned char smem[];
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem);
@@ -306,18 +340,12 @@ __global__ void __launch_bounds__(kLbpMaxThreads, 3) lbp_hist_kernel(const uint8
 
         // write-out: 8 bins of a cell pair per step = two 16-byte groups -> low halves to the upper cell, high halves
         // to the lower cell ([cell][bin] u16 order, 128-bit stores); the same thread clears them for the next image
-        uint4 *dst = reinterpret_cast<uint4 *>(out + b * (int64_t)gx * gy * 256);
-        for (unsigned w = tid; w < pairs * 32; w += nthreads) {
-            const unsigned pair = w >> 5, j = w & 31;
-            uint4 *grp = reinterpret_cast<uint4 *>(s_hist) + pair * kLbpPairVec + 2 * j;
-            const uint4 u = grp[0], v = grp[1];
-            grp[0] = make_uint4(0, 0, 0, 0);
-            grp[1] = make_uint4(0, 0, 0, 0);
-            dst[pair * 32 + j] = make_uint4(__byte_perm(u.x, u.y, 0x5410), __byte_perm(u.z, u.w, 0x5410),
-                                            __byte_perm(v.x, v.y, 0x5410), __byte_perm(v.z, v.w, 0x5410));
-            if (pair + half * gx < gx * gy)
-                dst[(pair + half * gx) * 32 + j] = make_uint4(__byte_perm(u.x, u.y, 0x7632), __byte_perm(u.z, u.w, 0x7632),
-                                                               __byte_perm(v.x, v.y, 0x7632), __byte_perm(v.z, v.w, 0x7632));
+        constexpr unsigned kSteps = OUT8 ? 16 : 32;         // 128-bit stores per cell
+        unsigned char *dst = out + b * (int64_t)gx * gy * 256 * (OUT8 ? 1 : 2);
+        for (unsigned w = tid; w < pairs * kSteps; w += nthreads) {
+            const unsigned pair = w / kSteps, j = w % kSteps;
+            lbp_write_pair<OUT8>(reinterpret_cast<uint4 *>(s_hist) + pair * kLbpPairVec, dst, pair, j, pair + half * gx < gx * gy,
+                                 pair + half * gx);
         }
         __syncthreads();  // counters are clear before the next image's atomics
     }
@@ -357,11 +385,12 @@ __device__ __forceinline__ void lbp_mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(lbp_smem_u32(bar)) : "memory");
 }
 
-template <bool ALIGNED16>
+template <bool ALIGNED16, bool OUT8>
 __global__ void __launch_bounds__(kLbpPipeThreads, 2) lbp_hist_pipe_kernel(const uint8_t *__restrict__ img, int64_t count, int rows,
                                                                           int cols, int grid_x, int grid_y, int img_smem_bytes,
-                                                                          int hist_smem_bytes, uint16_t *__restrict__ out)
+                                                                          int hist_smem_bytes, void *__restrict__ out_v)
 {
+    unsigned char *out = reinterpret_cast<unsigned char *>(out_v);
     // shared: [full[2], done[2], clean[2] mbarriers][image buffers 0, 1][counter buffers 0, 1]
     extern __shared__ __align__(16) unsigned char smem[];
     uint64_t *s_full = reinterpret_cast<uint64_t *>(smem), *s_done = s_full + 2, *s_clean = s_full + 4;
@@ -407,18 +436,11 @@ __global__ void __launch_bounds__(kLbpPipeThreads, 2) lbp_hist_pipe_kernel(const
             const int64_t nxt = b + 2 * (int64_t)gridDim.x;
             if (lane == 0 && nxt < count) lbp_bulk_load(s_img0 + buf * img_smem_bytes, img + nxt * img_bytes, img_bytes, &s_full[buf]);
             uint4 *hist = reinterpret_cast<uint4 *>(s_hist0 + (size_t)buf * hist_smem_bytes);
-            uint4 *dst = reinterpret_cast<uint4 *>(out + b * (int64_t)gx * gy * 256);
-            for (unsigned w = lane; w < pairs * 32; w += 32) {
-                const unsigned pair = w >> 5, j = w & 31;
-                uint4 *grp = hist + pair * kLbpPairVec + 2 * j;
-                const uint4 u = grp[0], v = grp[1];
-                grp[0] = make_uint4(0, 0, 0, 0);
-                grp[1] = make_uint4(0, 0, 0, 0);
-                dst[pair * 32 + j] = make_uint4(__byte_perm(u.x, u.y, 0x5410), __byte_perm(u.z, u.w, 0x5410),
-                                                __byte_perm(v.x, v.y, 0x5410), __byte_perm(v.z, v.w, 0x5410));
-                if (pair + half * gx < gx * gy)
-                    dst[(pair + half * gx) * 32 + j] = make_uint4(__byte_perm(u.x, u.y, 0x7632), __byte_perm(u.z, u.w, 0x7632),
-                                                                   __byte_perm(v.x, v.y, 0x7632), __byte_perm(v.z, v.w, 0x7632));
+            constexpr unsigned kSteps = OUT8 ? 16 : 32;
+            unsigned char *dst = out + b * (int64_t)gx * gy * 256 * (OUT8 ? 1 : 2);
+            for (unsigned w = lane; w < pairs * kSteps; w += 32) {
+                const unsigned pair = w / kSteps, j = w % kSteps;
+                lbp_write_pair<OUT8>(hist + pair * kLbpPairVec, dst, pair, j, pair + half * gx < gx * gy, pair + half * gx);
             }
             __syncwarp();
             if (lane == 0) lbp_mbar_arrive(&s_clean[buf]);
@@ -480,6 +502,90 @@ static int check_lbp_args(const char *fn, int64_t count, int rows, int cols, int
     return FRB_OK;
 }
 
+// OUT8: u8 counts (cells of <= 255 pixels) instead of u16
+template <bool OUT8>
+static int lbp_hist_impl(const uint8_t *images, int64_t count, int rows, int cols, int radius, int neighbors, int grid_x,
+                         int grid_y, void *out_hist, int *out_cell_px, void *stream)
+{
+    int rc = check_lbp_args("frb_lbp_hist_u8", count, rows, cols, radius, neighbors);
+    if (rc != FRB_OK) return rc;
+    FRB_CHECK_ARG(grid_x >= 1 && grid_y >= 1, "frb_lbp_hist_u8: grid %dx%d", grid_x, grid_y);
+    const int cw = (cols - 2) / grid_x, ch = (rows - 2) / grid_y;
+    if (out_cell_px) *out_cell_px = cw * ch;
+    if (cw * ch > (OUT8 ? 255 : 65535)) {
+        set_error("frb_lbp_hist_u8: %d pixels per cell overflow the %s counters", cw * ch, OUT8 ? "u8" : "u16");
+        return FRB_ERR_UNSUPPORTED;
+    }
+    if (count == 0) return FRB_OK;
+    FRB_CHECK_ARG(images && out_hist, "frb_lbp_hist_u8: null pointer");
+    // +16: the right-most column pair reads up to 2 bytes past the image (zeroed, never used in a code it emits)
+    const int img_smem = (int)align_up((size_t)rows * cols, 16) + 16;
+    // counters: one u32 per (cell pair, bin), pairs = ceil(grid_y / 2) * grid_x, plus one scratch pair
+    const size_t hist_bytes = ((size_t)grid_x * ((grid_y + 1) / 2) + 1) * (kLbpPairVec * 16);
+    const bool aligned16 = (cols % 2) == 0;
+    // one thread per (band pair, column pair) when that fits a CTA
+    const int items = ((cw * grid_x + 1) / 2) * ((grid_y + 1) / 2);
+    // images the TMA can fetch (16-byte aligned, a multiple of 16 bytes) take the pipelined kernel: double-buffered
+    // counters, a writer warp, no block-wide barrier
+    const bool bulk_ok = (((size_t)rows * cols) & 15) == 0 && ((uintptr_t)images & 15) == 0;
+    const size_t pipe_smem = 64 + 2 * (size_t)img_smem + 2 * hist_bytes;
+    if (bulk_ok && pipe_smem <= 113 * 1024) {
+        int threads = (items + 31) / 32 * 32 + 32;
+        if (threads > kLbpPipeThreads) threads = kLbpPipeThreads;
+        int per_sm = 1;
+        if (aligned16) {
+            FRB_CUDA_OK(cudaFuncSetAttribute(lbp_hist_pipe_kernel<true, OUT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem));
+            FRB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbp_hist_pipe_kernel<true, OUT8>, threads, pipe_smem));
+        } else {
+            FRB_CUDA_OK(cudaFuncSetAttribute(lbp_hist_pipe_kernel<false, OUT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem));
+            FRB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbp_hist_pipe_kernel<false, OUT8>, threads, pipe_smem));
+        }
+        if (per_sm < 1) per_sm = 1;
+        const int64_t cap = (int64_t)sm_count() * per_sm;
+        const int grid = (int)(count < cap ? count : cap);
+        {
+            ProfileScope prof(FRB_K_LBP_HIST, (cudaStream_t)stream);
+            if (aligned16)
+                lbp_hist_pipe_kernel<true, OUT8><<<grid, threads, pipe_smem, (cudaStream_t)stream>>>(images, count, rows, cols, grid_x, grid_y, img_smem, (int)hist_bytes, out_hist);
+            else
+                lbp_hist_pipe_kernel<false, OUT8><<<grid, threads, pipe_smem, (cudaStream_t)stream>>>(images, count, rows, cols, grid_x, grid_y, img_smem, (int)hist_bytes, out_hist);
+        }
+        FRB_LAUNCH_OK("lbp_hist_pipe_kernel");
+        return FRB_OK;
+    }
+    const size_t smem = 16 + 2 * (size_t)img_smem + hist_bytes;
+    if (smem > 227 * 1024) {
+        set_error("frb_lbp_hist_u8: image %dx%d with grid %dx%d needs %zu B of shared memory (> 227 KB)", rows, cols,
+                  grid_x, grid_y, smem);
+        return FRB_ERR_UNSUPPORTED;
+    }
+    if (aligned16)
+        FRB_CUDA_OK(cudaFuncSetAttribute(lbp_hist_kernel<true, OUT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+        FRB_CUDA_OK(cudaFuncSetAttribute(lbp_hist_kernel<false, OUT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int threads = (items + 31) / 32 * 32;
+    if (threads < 64) threads = 64;
+    if (threads > kLbpMaxThreads) threads = kLbpMaxThreads;
+    int per_sm = 1;  // persistent grid = exactly the CTAs that can be resident
+    if (aligned16)
+        FRB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbp_hist_kernel<true, OUT8>, threads, smem));
+    else
+        FRB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbp_hist_kernel<false, OUT8>, threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    int64_t cap = (int64_t)sm_count() * per_sm;
+    int grid = (int)(count < cap ? count : cap);
+    {
+        ProfileScope prof(FRB_K_LBP_HIST, (cudaStream_t)stream);
+        if (aligned16)
+            lbp_hist_kernel<true, OUT8><<<grid, threads, smem, (cudaStream_t)stream>>>(images, count, rows, cols, grid_x, grid_y, img_smem, out_hist);
+        else
+            lbp_hist_kernel<false, OUT8><<<grid, threads, smem, (cudaStream_t)stream>>>(images, count, rows, cols, grid_x, grid_y, img_smem, out_hist);
+    }
+    FRB_LAUNCH_OK("lbp_hist_kernel");
+    return FRB_OK;
+}
+
+
 extern "C" {
 
 int frb_lbp_codes_u8(const uint8_t *images, int64_t count, int rows, int cols, int radius, int neighbors,
@@ -501,82 +607,13 @@ int frb_lbp_codes_u8(const uint8_t *images, int64_t count, int rows, int cols, i
 int frb_lbp_hist_u8(const uint8_t *images, int64_t count, int rows, int cols, int radius, int neighbors, int grid_x,
                     int grid_y, uint16_t *out_hist, int *out_cell_px, void *stream)
 {
-    int rc = check_lbp_args("frb_lbp_hist_u8", count, rows, cols, radius, neighbors);
-    if (rc != FRB_OK) return rc;
-    FRB_CHECK_ARG(grid_x >= 1 && grid_y >= 1, "frb_lbp_hist_u8: grid %dx%d", grid_x, grid_y);
-    const int cw = (cols - 2) / grid_x, ch = (rows - 2) / grid_y;
-    if (out_cell_px) *out_cell_px = cw * ch;
-    if (cw * ch > 65535) {
-        set_error("frb_lbp_hist_u8: %d pixels per cell overflow the u16 counters", cw * ch);
-        return FRB_ERR_UNSUPPORTED;
-    }
-    if (count == 0) return FRB_OK;
-    FRB_CHECK_ARG(images && out_hist, "frb_lbp_hist_u8: null pointer");
-    // +16: the right-most column pair reads up to 2 bytes past the image (zeroed, never used in a code it emits)
-    const int img_smem = (int)align_up((size_t)rows * cols, 16) + 16;
-    // counters: one u32 per (cell pair, bin), pairs = ceil(grid_y / 2) * grid_x, plus one scratch pair
-    const size_t hist_bytes = ((size_t)grid_x * ((grid_y + 1) / 2) + 1) * (kLbpPairVec * 16);
-    const bool aligned16 = (cols % 2) == 0;
-    // one thread per (band pair, column pair) when that fits a CTA
-    const int items = ((cw * grid_x + 1) / 2) * ((grid_y + 1) / 2);
-    // images the TMA can fetch (16-byte aligned, a multiple of 16 bytes) take the pipelined kernel: double-buffered
-    // counters, a writer warp, no block-wide barrier
-    const bool bulk_ok = (((size_t)rows * cols) & 15) == 0 && ((uintptr_t)images & 15) == 0;
-    const size_t pipe_smem = 64 + 2 * (size_t)img_smem + 2 * hist_bytes;
-    if (bulk_ok && pipe_smem <= 113 * 1024) {
-        int threads = (items + 31) / 32 * 32 + 32;
-        if (threads > kLbpPipeThreads) threads = kLbpPipeThreads;
-        int per_sm = 1;
-        if (aligned16) {
-            FRB_CUDA_OK(cudaFuncSetAttribute(lbp_hist_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem));
-            FRB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbp_hist_pipe_kernel<true>, threads, pipe_smem));
-        } else {
-            FRB_CUDA_OK(cudaFuncSetAttribute(lbp_hist_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem));
-            FRB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbp_hist_pipe_kernel<false>, threads, pipe_smem));
-        }
-        if (per_sm < 1) per_sm = 1;
-        const int64_t cap = (int64_t)sm_count() * per_sm;
-        const int grid = (int)(count < cap ? count : cap);
-        {
-            ProfileScope prof(FRB_K_LBP_HIST, (cudaStream_t)stream);
-            if (aligned16)
-                lbp_hist_pipe_kernel<true><<<grid, threads, pipe_smem, (cudaStream_t)stream>>>(images, count, rows, cols, grid_x, grid_y, img_smem, (int)hist_bytes, out_hist);
-            else
-                lbp_hist_pipe_kernel<false><<<grid, threads, pipe_smem, (cudaStream_t)stream>>>(images, count, rows, cols, grid_x, grid_y, img_smem, (int)hist_bytes, out_hist);
-        }
-        FRB_LAUNCH_OK("lbp_hist_pipe_kernel");
-        return FRB_OK;
-    }
-    const size_t smem = 16 + 2 * (size_t)img_smem + hist_bytes;
-    if (smem > 227 * 1024) {
-        set_error("frb_lbp_hist_u8: image %dx%d with grid %dx%d needs %zu B of shared memory (> 227 KB)", rows, cols,
-                  grid_x, grid_y, smem);
-        return FRB_ERR_UNSUPPORTED;
-    }
-    if (aligned16)
-        FRB_CUDA_OK(cudaFuncSetAttribute(lbp_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else
-        FRB_CUDA_OK(cudaFuncSetAttribute(lbp_hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int threads = (items + 31) / 32 * 32;
-    if (threads < 64) threads = 64;
-    if (threads > kLbpMaxThreads) threads = kLbpMaxThreads;
-    int per_sm = 1;  // persistent grid = exactly the CTAs that can be resident
-    if (aligned16)
-        FRB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbp_hist_kernel<true>, threads, smem));
-    else
-        FRB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbp_hist_kernel<false>, threads, smem));
-    if (per_sm < 1) per_sm = 1;
-    int64_t cap = (int64_t)sm_count() * per_sm;
-    int grid = (int)(count < cap ? count : cap);
-    {
-        ProfileScope prof(FRB_K_LBP_HIST, (cudaStream_t)stream);
-        if (aligned16)
-            lbp_hist_kernel<true><<<grid, threads, smem, (cudaStream_t)stream>>>(images, count, rows, cols, grid_x, grid_y, img_smem, out_hist);
-        else
-            lbp_hist_kernel<false><<<grid, threads, smem, (cudaStream_t)stream>>>(images, count, rows, cols, grid_x, grid_y, img_smem, out_hist);
-    }
-    FRB_LAUNCH_OK("lbp_hist_kernel");
-    return FRB_OK;
+    return lbp_hist_impl<false>(images, count, rows, cols, radius, neighbors, grid_x, grid_y, out_hist, out_cell_px, stream);
+}
+
+int frb_lbp_hist_u8_counts8(const uint8_t *images, int64_t count, int rows, int cols, int radius, int neighbors, int grid_x,
+                            int grid_y, uint8_t *out_hist, int *out_cell_px, void *stream)
+{
+    return lbp_hist_impl<true>(images, count, rows, cols, radius, neighbors, grid_x, grid_y, out_hist, out_cell_px, stream);
 }
 
 }  // extern "C"

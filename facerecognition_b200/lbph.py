@@ -70,12 +70,19 @@ class LBPHFaceRecognizer:
     """cv2.face.LBPHFaceRecognizer protocol: train / update / predict / save / read / setThreshold ..."""
 
     def __init__(self, radius: int = 1, neighbors: int = 8, grid_x: int = 8, grid_y: int = 8,
-                 threshold: float = DBL_MAX, device: Optional[str] = None):
+                 threshold: float = DBL_MAX, device: Optional[str] = None, group=None):
+        """`group` (new; a torch.distributed process group, or True for the default group): the gallery is sharded by
+        training sample over the group's ranks.  Every rank makes the SAME train / update / predict calls with the same
+        data; rank r keeps the histograms of its slice of each train()/update() batch on its GPU (global row ids), every
+        rank extracts the query histograms, searches its shard, and ONE fused NVLink exchange + merge kernel gives all
+        ranks the answer a single-GPU model gives (first row wins ties)."""
         self._radius, self._neighbors, self._grid_x, self._grid_y = int(radius), int(neighbors), int(grid_x), int(grid_y)
         self._threshold = float(threshold)
         self.device = torch.device(device or "cuda")
         if self.device.type != "cuda":
             raise ValueError("LBPHFaceRecognizer runs on CUDA only (no CPU fallback)")
+        self.group = group
+        self._sharded = None
         self._groups: List[_Group] = []
         self._labels = np.zeros((0,), np.int32)
         self._label_info: Dict[int, str] = {}
@@ -104,21 +111,22 @@ class LBPHFaceRecognizer:
         return self._grid_x * self._grid_y * (1 << self._neighbors)
 
     # ---- feature extraction -------------------------------------------------------------------
-    def compute_histograms(self, images: torch.Tensor) -> Tuple[torch.Tensor, int]:
-        """u8 CUDA tensor [B, H, W] -> (u16 [B, L], cell_px) via frb_lbp_hist_u8."""
-        return ops.lbp_hist(images, self._radius, self._neighbors, self._grid_x, self._grid_y)
+    def compute_histograms(self, images: torch.Tensor, counts8: bool = False) -> Tuple[torch.Tensor, int]:
+        """u8 CUDA tensor [B, H, W] -> (u16 [B, L], cell_px) via frb_lbp_hist_u8; counts8: the gallery form (u8 counts
+        straight from the kernel when a cell has <= 255 pixels)."""
+        return ops.lbp_hist(images, self._radius, self._neighbors, self._grid_x, self._grid_y, counts8=counts8)
 
     def _upload(self, imgs: Sequence[np.ndarray]) -> torch.Tensor:
         stack = np.stack(imgs, 0)
         return torch.from_numpy(stack).to(self.device, non_blocking=False)
 
-    def _hist_by_shape(self, faces: Sequence[np.ndarray]):
-        """Yield (positions, hist u16 [n, L], cell_px) per distinct image shape, positions ascending."""
+    def _hist_by_shape(self, faces: Sequence[np.ndarray], counts8: bool = False):
+        """Yield (positions, hist u16 (or u8 with counts8) [n, L], cell_px) per distinct image shape, positions ascending."""
         by_shape: Dict[Tuple[int, int], List[int]] = {}
         for i, f in enumerate(faces):
             by_shape.setdefault(f.shape, []).append(i)
         for shape, pos in by_shape.items():
-            hist, px = self.compute_histograms(self._upload([faces[i] for i in pos]))
+            hist, px = self.compute_histograms(self._upload([faces[i] for i in pos]), counts8)
             yield pos, hist, px
 
     # ---- train / update (LBPH::train, LBPH::update) ------------------------------------------
@@ -139,9 +147,17 @@ class LBPHFaceRecognizer:
             raise LBPHError(f"The number of samples (src) must equal the number of labels (labels). "
                             f"Was len(samples)={len(faces)}, len(labels)={lab.shape[0]}.")
         base = self.size
-        for pos, hist, px in self._hist_by_shape(faces):
+        world, rank = self._world_rank()
+        keep = None
+        if world > 1:                                   # this rank's slice of the batch; labels stay global
+            from .sharded import shard_bounds
+            lo, hi = shard_bounds(len(faces), world, rank)
+            keep = range(lo, hi)
+        mine = faces if keep is None else [faces[i] for i in keep]
+        for pos, hist, px in (self._hist_by_shape(mine, counts8=True) if mine else ()):   # u8 counts straight from K2 when they fit
+            if keep is not None:
+                pos = [keep[i] for i in pos]
             rows = torch.tensor([base + i for i in pos], dtype=torch.int64, device=self.device)
-            hist = ops.compact_histograms(hist, px)
             for g in self._groups:
                 if g.cell_px == px:
                     g.hist = _cat_rows(g.hist, hist)
@@ -151,25 +167,55 @@ class LBPHFaceRecognizer:
                 self._groups.append(_Group(px, hist, rows))
         self._labels = np.concatenate([self._labels, lab])
 
-    def set_gallery(self, hist_u16: torch.Tensor, cell_px: int, labels) -> None:
-        """Adopt precomputed integer histograms (e.g. one shard of a distributed gallery)."""
+    def set_gallery(self, hist_u16: torch.Tensor, cell_px: int, labels, row_offset: int = 0) -> None:
+        """Adopt precomputed integer histograms: the whole gallery, or — with `group` — THIS rank's shard, whose first
+        row has global id `row_offset`; `labels` always lists every gallery row of the whole model."""
         assert hist_u16.dtype in (torch.uint16, torch.uint8) and hist_u16.dim() == 2 and hist_u16.shape[1] == self.hist_len
         n = hist_u16.shape[0]
         hist = hist_u16.contiguous() if hist_u16.dtype == torch.uint8 else ops.compact_histograms(hist_u16.contiguous(), int(cell_px))
-        self._groups = [_Group(int(cell_px), hist, torch.arange(n, dtype=torch.int64, device=hist_u16.device))]
+        rows = torch.arange(row_offset, row_offset + n, dtype=torch.int64, device=hist_u16.device)
+        self._groups = [_Group(int(cell_px), hist, rows)] if n else []
         self._labels = np.asarray(labels).astype(np.int32).reshape(-1)
-        assert self._labels.shape[0] == n
+        assert self._world_rank()[0] > 1 or self._labels.shape[0] == n
+        self._sharded = None
 
     # ---- predict (LBPH::predict + StandardCollector) -----------------------------------------
+    def _dist_group(self):
+        return None if self.group is True else self.group
+
+    def _world_rank(self) -> Tuple[int, int]:
+        import torch.distributed as dist
+        if self.group is None or not (dist.is_available() and dist.is_initialized()):
+            return 1, 0
+        g = self._dist_group()
+        return dist.get_world_size(g), dist.get_rank(g)
+
     def _search(self, q_hist: torch.Tensor, q_px: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        """(dist fp32 [Q, k], global row int64 [Q, k]) over all gallery groups; ties -> lowest row."""
+        """(dist fp32 [Q, k], global row int64 [Q, k]) over the whole gallery (all ranks' shards); ties -> lowest row."""
+        if self._world_rank()[0] > 1:
+            if self._sharded is None:
+                self._sharded = self._make_sharded()
+            self._sharded.local_search = lambda qh, kk: self._search_local(qh, q_px, kk)
+            return self._sharded.search(q_hist, k)
+        return self._search_local(q_hist, q_px, k)
+
+    def _make_sharded(self):
+        """The cross-rank step behind a sharded model: local nearest rows with global ids -> fused NVLink exchange + merge."""
+        from .sharded import ShardedSearch
+        return ShardedSearch(None, ops.topk_merge, False, self._dist_group(), merge_packed=ops.topk_merge_packed, peer_exchange=True)
+
+    def _search_local(self, q_hist: torch.Tensor, q_px: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The same over THIS device's gallery groups."""
         outs = []
         for g in self._groups:
             d, i = ops.chisq_topk(q_hist, q_px, g.hist, g.cell_px, k)
             if len(self._groups) > 1 or g.rows.shape[0] != self.size:
-                valid = i >= 0
-                i = torch.where(valid, g.rows[i.clamp_min(0)], i)
+                ops.index_remap(i, g.rows)                               # local group rows -> global row ids
             outs.append((d, i))
+        if not outs:                                                     # a rank whose shard is empty
+            n = q_hist.shape[0]
+            return (torch.full((n, k), float("inf"), dtype=torch.float32, device=self.device),
+                    torch.full((n, k), -1, dtype=torch.int64, device=self.device))
         if len(outs) == 1:
             return outs[0]
         cd = torch.stack([o[0] for o in outs], 0).contiguous()
@@ -238,6 +284,9 @@ class LBPHFaceRecognizer:
 
     def get_histograms_u16(self) -> Tuple[np.ndarray, np.ndarray]:
         """(u16 [N, L] counts in training order, cell_px int32 [N])."""
+        if self._world_rank()[0] > 1:
+            raise LBPHError("a sharded LBPH model holds only its shard of the histograms on each rank; "
+                            "save / getHistograms need a single-GPU model")
         hist = np.zeros((self.size, self.hist_len), np.uint16)
         px = np.zeros((self.size,), np.int32)
         for g in self._groups:
@@ -264,9 +313,9 @@ class LBPHFaceRecognizer:
 
 
 def LBPHFaceRecognizer_create(radius: int = 1, neighbors: int = 8, grid_x: int = 8, grid_y: int = 8,
-                              threshold: float = DBL_MAX, device: Optional[str] = None) -> LBPHFaceRecognizer:
+                              threshold: float = DBL_MAX, device: Optional[str] = None, group=None) -> LBPHFaceRecognizer:
     """cv2.face.LBPHFaceRecognizer_create (models/lbphmodel/train_lbph.py:24-29; no-arg form web_app.py:245)."""
-    return LBPHFaceRecognizer(radius, neighbors, grid_x, grid_y, threshold, device)
+    return LBPHFaceRecognizer(radius, neighbors, grid_x, grid_y, threshold, device, group)
 
 
 # ---- mirrors of the reference's wrappers ------------------------------------------------------------
@@ -293,6 +342,22 @@ def recognize_face(model, face_img, threshold):
     if conf < threshold:
         return {"label": pred, "confidence": conf, "status": "known"}
     return {"label": None, "confidence": conf, "status": "unknown"}
+
+
+def web_confidence(distance: float) -> float:
+    """web_app.py:597 (and :684): the UI's confidence from a chi-square distance, max(0, min(1, (200 - d) / 200)) below 200, else 0."""
+    return max(0, min(1, (200 - distance) / 200)) if distance < 200 else 0.0
+
+
+def recognize_face_web(model, face_img, threshold, label_map=None):
+    """The LBPH branch of the web UI (web_app.py:587-605): predict, identity from the label map (`Person_<label>` without
+    one), confidence = web_confidence(distance), and "Unknown" when distance > threshold — note the strict '>' here
+    against `conf < threshold` in inference_lbph.recognize_face (a distance equal to the threshold is known in both)."""
+    label, distance = model.predict(face_img)
+    identity = label_map.get(label, f"Person_{label}") if label_map else f"Person_{label}"
+    if distance > threshold:
+        identity = "Unknown"
+    return {"identity": identity, "confidence": float(web_confidence(distance)), "distance": float(distance), "label": int(label)}
 
 
 def evaluate_lbph(model, faces, labels, threshold):

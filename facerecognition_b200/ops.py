@@ -50,12 +50,18 @@ def row_norms(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def normalize_rows(x: torch.Tensor, mode: int = N.FRB_QNORM_EPS, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
-    """frb_normalize_rows: fp32 [R, D] -> fp32|bf16 [R, D], x/max(|x|,1e-12) (CLAMP) or x/(|x|+1e-8) (EPS)."""
-    dev = _require_cuda(x)
+def normalize_rows(x: torch.Tensor, mode: int = N.FRB_QNORM_EPS, out_dtype: torch.dtype = torch.float32,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """frb_normalize_rows: fp32 [R, D] -> fp32|bf16 [R, D], x/max(|x|,1e-12) (CLAMP) or x/(|x|+1e-8) (EPS).
+    `out`: write into this contiguous [R, D] tensor (its dtype wins) instead of allocating."""
+    dev = _require_cuda(x, out)
     assert x.dtype == torch.float32 and x.dim() == 2
-    assert out_dtype in (torch.float32, torch.bfloat16)
-    out = torch.empty(x.shape, dtype=out_dtype, device=dev)
+    if out is None:
+        assert out_dtype in (torch.float32, torch.bfloat16)
+        out = torch.empty(x.shape, dtype=out_dtype, device=dev)
+    else:
+        assert out.shape == x.shape and out.dtype in (torch.float32, torch.bfloat16)
+        out_dtype = out.dtype
     with torch.cuda.device(dev):
         N.call("frb_normalize_rows", _p(x), _I64(x.shape[0]), x.shape[1], mode, _p(out),
                N.FRB_F32 if out_dtype == torch.float32 else N.FRB_BF16, _stream(dev))
@@ -87,6 +93,29 @@ def cosine_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, *, score_m
     return scores, idx
 
 
+def cosine_topk_bf16q(queries_bf16: torch.Tensor, gallery_bf16: torch.Tensor, k: int, *, idx_base: int = 0,
+                      out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """frb_cosine_topk_bf16q: ALREADY normalised bf16 queries [Q, D] x bf16 gallery [N, D] -> (scores, idx); the
+    tensor-core kernel reads the queries in place (no prologue launch).  The sharded search calls this after
+    all-gathering the ranks' normalised query slices."""
+    dev = _require_cuda(queries_bf16, gallery_bf16)
+    assert queries_bf16.dtype == torch.bfloat16 and gallery_bf16.dtype == torch.bfloat16
+    assert queries_bf16.dim() == 2 and gallery_bf16.dim() == 2
+    assert gallery_bf16.shape[0] == 0 or gallery_bf16.shape[1] == queries_bf16.shape[1]
+    q, d, n = queries_bf16.shape[0], queries_bf16.shape[1], gallery_bf16.shape[0]
+    if out is None:
+        scores = torch.empty((q, k), dtype=torch.float32, device=dev)
+        idx = torch.empty((q, k), dtype=torch.int64, device=dev)
+    else:
+        scores, idx = out
+    with torch.cuda.device(dev):
+        ws_bytes = N.lib.frb_cosine_topk_workspace_bytes(q, n, d, N.FRB_BF16, k)
+        ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=dev)
+        N.call("frb_cosine_topk_bf16q", _p(queries_bf16), _I64(q), _p(gallery_bf16), _I64(n), d, k, _I64(idx_base), _p(scores),
+               _p(idx), _p(ws), ctypes.c_size_t(ws.numel()), _stream(dev))
+    return scores, idx
+
+
 # >= |exact score - bf16 first-pass score| for ANY pair: bf16 keeps 8 significant bits (unit roundoff 2^-8), so rounding
 # two unit vectors moves their inner product by at most 2 * 2^-8 + 2^-16 = 0.00783 (Cauchy-Schwarz), and
 # cosine_similarity()'s raw-dot branch (both norms within 1e-3 of 1) differs from the true cosine by at most 0.002
@@ -95,6 +124,11 @@ REFINE_EPS = 0.0105
 # 4.1 ms vs 7.7 ms (a 64-slot list warms up in every (query tile, gallery group) unit, which small batches have many of)
 REFINE_MIN_QUERIES = 256
 REFINE_MIN_ROWS = 65536
+
+
+def refine_min_queries(k: int) -> int:
+    """Smallest batch that takes the tensor-core first pass + exact re-score instead of the fp32 tiled kernel."""
+    return REFINE_MIN_QUERIES
 
 
 def refine_list_length(k: int) -> int:
@@ -234,6 +268,18 @@ class Exchange:
                    _stream(dev))
         return out_s, out_i
 
+    def status(self) -> Tuple[int, int]:
+        """(kernels that gave up waiting for a peer, steps finished); synchronises with the device."""
+        t, e = ctypes.c_int(0), ctypes.c_uint(0)
+        with torch.cuda.device(self.device):
+            N.call("frb_exchange_status", self._ctx, ctypes.byref(t), ctypes.byref(e))
+        return t.value, e.value
+
+    def reset(self) -> None:
+        """frb_exchange_reset: clear flags / epoch / timeouts.  Every rank calls it between two host barriers."""
+        with torch.cuda.device(self.device):
+            N.call("frb_exchange_reset", self._ctx)
+
     def close(self) -> None:
         if self._ctx:
             N.lib.frb_exchange_destroy(self._ctx)
@@ -270,26 +316,48 @@ def lbp_codes(images: torch.Tensor, radius: int = 1, neighbors: int = 8) -> torc
     return out
 
 
-def lbp_hist(images: torch.Tensor, radius: int = 1, neighbors: int = 8, grid_x: int = 8, grid_y: int = 8
-             ) -> Tuple[torch.Tensor, int]:
-    """frb_lbp_hist_u8: u8 [B, H, W] -> (u16 [B, grid_x*grid_y*256] cell histograms, pixels per cell)."""
+def lbp_cell_px(rows: int, cols: int, grid_x: int = 8, grid_y: int = 8) -> int:
+    """Pixels per LBP grid cell (OpenCV spatial_histogram: floor((cols-2)/grid_x) x floor((rows-2)/grid_y))."""
+    return max((cols - 2) // grid_x, 0) * max((rows - 2) // grid_y, 0)
+
+
+def lbp_hist(images: torch.Tensor, radius: int = 1, neighbors: int = 8, grid_x: int = 8, grid_y: int = 8,
+             counts8: bool = False) -> Tuple[torch.Tensor, int]:
+    """frb_lbp_hist_u8: u8 [B, H, W] -> (u16 [B, grid_x*grid_y*256] cell histograms, pixels per cell).
+    counts8=True: frb_lbp_hist_u8_counts8 — the same histograms written as u8 counts (the gallery form) when a cell
+    has <= 255 pixels; larger cells still come back as u16."""
     dev = _require_cuda(images)
     assert images.dtype == torch.uint8 and images.dim() == 3
     b, h, w = images.shape
-    out = torch.empty((b, grid_x * grid_y * 256), dtype=torch.uint16, device=dev)
+    as8 = counts8 and lbp_cell_px(h, w, grid_x, grid_y) <= 255
+    out = torch.empty((b, grid_x * grid_y * 256), dtype=torch.uint8 if as8 else torch.uint16, device=dev)
     cell_px = ctypes.c_int(0)
     with torch.cuda.device(dev):
-        N.call("frb_lbp_hist_u8", _p(images), _I64(b), h, w, radius, neighbors, grid_x, grid_y, _p(out),
-               ctypes.byref(cell_px), _stream(dev))
+        N.call("frb_lbp_hist_u8_counts8" if as8 else "frb_lbp_hist_u8", _p(images), _I64(b), h, w, radius, neighbors, grid_x,
+               grid_y, _p(out), ctypes.byref(cell_px), _stream(dev))
     return out, cell_px.value
 
 
 def compact_histograms(hist_u16: torch.Tensor, cell_px: int) -> torch.Tensor:
-    """u16 cell histograms -> the u8 gallery form the chi-square kernels also read (exact: every count <= cell_px <= 255);
-    returns the input unchanged when the counts do not fit a byte or the row length is not a multiple of 16."""
-    if cell_px > 255 or hist_u16.shape[1] % 16 != 0:
+    """frb_counts_u16_to_u8: u16 cell histograms -> the u8 gallery form the chi-square kernels also read (exact: every
+    count <= cell_px <= 255); returns the input unchanged when the counts do not fit a byte or the row length is not a
+    multiple of 16.  (LBPH train()/update() do not need it: lbp_hist(counts8=True) writes u8 directly.)"""
+    if cell_px > 255 or hist_u16.shape[1] % 16 != 0 or hist_u16.dtype == torch.uint8:
         return hist_u16
-    return hist_u16.view(torch.int16).to(torch.uint8)
+    dev = _require_cuda(hist_u16)
+    out = torch.empty(hist_u16.shape, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.call("frb_counts_u16_to_u8", _p(hist_u16), _I64(hist_u16.numel()), _p(out), _stream(dev))
+    return out
+
+
+def index_remap(idx: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    """frb_index_remap: idx int64 [...] in place, idx >= 0 -> table[idx] (negative entries are padding and stay)."""
+    dev = _require_cuda(idx, table)
+    assert idx.dtype == torch.int64 and table.dtype == torch.int64
+    with torch.cuda.device(dev):
+        N.call("frb_index_remap", _p(idx), _I64(idx.numel()), _p(table), _I64(table.numel()), _stream(dev))
+    return idx
 
 
 # Batches at least this large against galleries at least this long go through the tensor-core candidate filter

@@ -39,16 +39,31 @@ def _to_dev(a: np.ndarray, dev: torch.device) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
 
 
+def _pad8(t: torch.Tensor) -> torch.Tensor:
+    """Zero-pad the columns of [R, D] to a multiple of 8 (the kernels' vector width).  Zero columns change neither dot
+    products nor norms, so any embedding dimension the reference accepts works here too."""
+    d = t.shape[1]
+    if d % 8 == 0:
+        return t.contiguous()
+    return torch.nn.functional.pad(t, (0, 8 - d % 8)).contiguous()
+
+
+def _queries_to_dev(emb, dim: int, dev: torch.device) -> torch.Tensor:
+    """Query embeddings as a padded fp32 CUDA matrix [Q, pad8(dim)]: numpy / lists are uploaded, CUDA tensors (the
+    embedding network's output, inference/extract_embeddings.py:392-443) are taken where they are."""
+    if isinstance(emb, torch.Tensor):
+        q = emb.detach().to(device=dev, dtype=torch.float32).reshape(-1, dim)
+    else:
+        q = _to_dev(np.asarray(emb).astype(np.float32).reshape(-1, dim), dev)
+    return _pad8(q)
+
+
 def cosine_similarity(a: np.ndarray, b: np.ndarray) -> float:
     """inference/recognition_engine.py:41-63, evaluated by the CUDA kernel (Q = N = 1):
     0.0 if either norm is 0; raw dot if both norms are within 1e-3 of 1; else dot/(na*nb)."""
     dev = torch.device("cuda")
-    qa = _to_dev(np.asarray(a).astype(np.float32).reshape(1, -1), dev)
-    gb = _to_dev(np.asarray(b).astype(np.float32).reshape(1, -1), dev)
-    if qa.shape[1] % 8:
-        pad = 8 - qa.shape[1] % 8
-        qa = torch.nn.functional.pad(qa, (0, pad)).contiguous()
-        gb = torch.nn.functional.pad(gb, (0, pad)).contiguous()
+    qa = _pad8(_to_dev(np.asarray(a).astype(np.float32).reshape(1, -1), dev))
+    gb = _pad8(_to_dev(np.asarray(b).astype(np.float32).reshape(1, -1), dev))
     s, _ = ops.cosine_topk(qa, gb, 1, score_mode=N.FRB_SCORE_REF_COSINE, q_norms=ops.row_norms(qa),
                            g_norms=ops.row_norms(gb))
     return float(s[0, 0].item())
@@ -86,21 +101,35 @@ class _GalleryDict(dict):
     def setdefault(self, k, d=None):
         r = super().setdefault(k, d); self._bump(); return r
 
+    def __ior__(self, other):
+        r = super().__ior__(other); self._bump(); return r
+
+    def invalidate(self):
+        """Call after editing a stored vector IN PLACE (engine.db[name][:] = v): nothing else can notice that."""
+        self._bump()
+
 
 class DeviceGallery:
     """Row-major fp32 [N, D] copy of a {name: vector} dict on the GPU, with per-row norms.
     Row i <-> i-th dict key (insertion order), which is what makes ties resolve as the reference's
     stable sort does."""
 
-    def __init__(self, db: Dict[str, np.ndarray], device: torch.device):
+    def __init__(self, db: Dict[str, np.ndarray], device: torch.device, bounds: Optional[Tuple[int, int]] = None):
+        """bounds = (lo, hi): keep only rows [lo, hi) on this device (one shard of an identity-sharded gallery); `names`
+        always lists every identity and the searches report GLOBAL row ids (idx_base = lo)."""
         self.names: List[str] = list(db.keys())
+        self.lo, self.hi = bounds if bounds is not None else (0, len(self.names))
+        mine = self.names[self.lo:self.hi]
         if self.names:
-            mat = np.stack([np.asarray(db[n]).astype(np.float32).flatten() for n in self.names], 0)
+            self.dim = int(np.asarray(db[self.names[0]]).size)
         else:
-            mat = np.zeros((0, 8), np.float32)
-        self.dim = mat.shape[1]
-        self.rows = _to_dev(mat, device)
-        self.norms = ops.row_norms(self.rows) if len(self.names) else torch.zeros(0, device=device)
+            self.dim = 8
+        if mine:
+            mat = np.stack([np.asarray(db[n]).astype(np.float32).flatten() for n in mine], 0)
+        else:
+            mat = np.zeros((0, self.dim), np.float32)
+        self.rows = _pad8(_to_dev(mat, device))               # [n, pad8(dim)]
+        self.norms = ops.row_norms(self.rows) if len(mine) else torch.zeros(0, device=device)
         self._unit_rows = None
         self._unit_bf16 = None
 
@@ -123,25 +152,27 @@ class FlatIPIndex:
 
     def __init__(self, d: int, device: Optional[str] = None, dtype: torch.dtype = torch.float32):
         self.d = int(d)
+        self.dp = (self.d + 7) // 8 * 8            # stored row length: zero-padded to the kernels' vector width
         self.device = _match_device(device)
         self.dtype = dtype
-        self.rows = torch.zeros((0, self.d), dtype=dtype, device=self.device)
+        self.rows = torch.zeros((0, self.dp), dtype=dtype, device=self.device)
 
     @property
     def ntotal(self) -> int:
         return int(self.rows.shape[0])
 
     def add(self, x: np.ndarray) -> None:
-        x = _to_dev(np.asarray(x).reshape(-1, self.d), self.device)
+        x = _pad8(_to_dev(np.asarray(x).reshape(-1, self.d), self.device))
         if self.dtype == torch.bfloat16:
             x = ops.normalize_rows(x, N.FRB_QNORM_NONE, torch.bfloat16)
         self.rows = torch.cat([self.rows, x], 0).contiguous()
 
     def search_device(self, x: torch.Tensor, k: int, qnorm_mode: int = N.FRB_QNORM_NONE):
-        return ops.cosine_topk(x, self.rows, k, score_mode=N.FRB_SCORE_IP, qnorm_mode=qnorm_mode)
+        return ops.cosine_topk(_pad8(x), self.rows, k, score_mode=N.FRB_SCORE_IP, qnorm_mode=qnorm_mode)
 
-    def search(self, x: np.ndarray, k: int):
-        s, i = self.search_device(_to_dev(np.asarray(x).reshape(-1, self.d), self.device), k)
+    def search(self, x, k: int):
+        """faiss's search(x, k) -> (scores, ids) on the host; x may also be a CUDA tensor [Q, d]."""
+        s, i = self.search_device(_queries_to_dev(x, self.d, self.device), k)
         return s.cpu().numpy(), i.cpu().numpy()
 
     @classmethod
@@ -152,7 +183,7 @@ class FlatIPIndex:
         return idx
 
     def write(self, path: str) -> None:
-        formats.write_faiss_flat_ip(path, self.rows.float().cpu().numpy())
+        formats.write_faiss_flat_ip(path, self.rows[:, :self.d].float().cpu().numpy())
 
 
 def group_plan(labels: np.ndarray, n_groups: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray]:
@@ -215,7 +246,7 @@ def build_faiss_index(embeddings: np.ndarray, output_path: str = None, use_gpu: 
     dev = _match_device(device)
     e = _to_dev(np.asarray(embeddings).astype("float32"), dev)
     index = FlatIPIndex(e.shape[1], str(dev))
-    index.rows = ops.normalize_rows(e, N.FRB_QNORM_EPS)
+    index.rows = ops.normalize_rows(_pad8(e), N.FRB_QNORM_EPS)
     if output_path:
         index.write(output_path)
     return index
@@ -235,7 +266,14 @@ class RecognitionEngine:
         threshold: float = 0.5,
         use_face_detection: bool = True,
         embedder: Optional[Callable[[object], Optional[np.ndarray]]] = None,
+        group=None,
     ):
+        """`group` (new; a torch.distributed process group, or True for the default group): the dict gallery is
+        sharded by identity over the group's ranks — rank r keeps rows shard_bounds(len(db), R, r) on its GPU, every
+        rank passes the same queries, each searches its shard and ONE fused NVLink exchange + merge kernel gives every
+        rank the same answer as a single-GPU engine (ties -> lowest row).  All ranks must make the same calls."""
+        self.group = group
+        self._sharded = None
         self.device = device or "cuda"
         self.match_device = _match_device(device)
         self.threshold = threshold
@@ -291,29 +329,74 @@ class RecognitionEngine:
         self.threshold = threshold
 
     # ---- gallery on the device ---------------------------------------------------------------
+    def _dist_group(self):
+        import torch.distributed as dist
+        if self.group is None or not (dist.is_available() and dist.is_initialized()):
+            return None
+        return None if self.group is True else self.group
+
+    def _world_rank(self) -> Tuple[int, int]:
+        import torch.distributed as dist
+        if self.group is None or not (dist.is_available() and dist.is_initialized()):
+            return 1, 0
+        g = self._dist_group()
+        return dist.get_world_size(g), dist.get_rank(g)
+
     def gallery(self) -> DeviceGallery:
         if self._gallery is None or self._gallery_version != self._db.version:
-            self._gallery = DeviceGallery(self._db, self.match_device)
+            world, rank = self._world_rank()
+            bounds = None
+            if world > 1:
+                from .sharded import shard_bounds
+                bounds = shard_bounds(len(self._db), world, rank)
+            self._gallery = DeviceGallery(self._db, self.match_device, bounds)
             self._gallery_version = self._db.version
+            self._sharded = None
         return self._gallery
 
+    def refresh_gallery(self) -> None:
+        """Force the device copy to be rebuilt from self.db (after in-place edits of stored vectors)."""
+        self._gallery = None
+
     # ---- matching -----------------------------------------------------------------------------
-    def _db_topk(self, emb: np.ndarray, k: int):
-        """(scores [Q, k], rows [Q, k]) on the host for Q query embeddings under the reference's cosine rule."""
+    def _local_topk(self, q: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(scores, global rows) of this device's rows for padded fp32 CUDA queries, the reference's cosine rule."""
         g = self.gallery()
-        q = _to_dev(np.asarray(emb).astype(np.float32).reshape(-1, g.dim), self.match_device)
         qn = ops.row_norms(q)
-        if (q.shape[0] >= ops.REFINE_MIN_QUERIES and len(g.names) >= ops.REFINE_MIN_ROWS and ops.refine_list_length(k)
-                and g.dim % 64 == 0 and g.dim <= 512):
-            # large batches against large galleries: bf16 tensor-core first pass + exact fp32 re-score of 64 candidates
-            # per query, each list proven complete; any query without a provable margin sends the batch to the exact kernel
+        n_local, pdim = g.rows.shape[0], g.rows.shape[1]
+        if (q.shape[0] >= ops.refine_min_queries(k) and n_local >= ops.REFINE_MIN_ROWS and ops.refine_list_length(k)
+                and pdim % 64 == 0 and pdim <= 512):
+            # batches against large galleries: bf16 tensor-core first pass + exact fp32 re-score of the candidates,
+            # each list proven complete; any query without a provable margin sends the batch to the exact kernel
             s, i, fail = ops.cosine_topk_refined(q, g.rows, g.unit_rows_bf16(), k, score_mode=N.FRB_SCORE_REF_COSINE,
-                                                 q_norms=qn, g_norms=g.norms)
-            s, i, fail = s.cpu().numpy(), i.cpu().numpy(), int(fail.cpu().item())
-            if fail == 0:
-                return s, i, g.names
-        s, i = ops.cosine_topk(q, g.rows, k, score_mode=N.FRB_SCORE_REF_COSINE, q_norms=qn, g_norms=g.norms)
-        return s.cpu().numpy(), i.cpu().numpy(), g.names
+                                                 q_norms=qn, g_norms=g.norms, idx_base=g.lo)
+            if int(fail.cpu().item()) == 0:
+                return s, i
+        return ops.cosine_topk(q, g.rows, k, score_mode=N.FRB_SCORE_REF_COSINE, q_norms=qn, g_norms=g.norms, idx_base=g.lo)
+
+    def recognize_embeddings_device(self, embeddings, k: int = 5) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Device-level batched match: embeddings (numpy [Q, D] or a CUDA tensor, e.g. straight from the embedding
+        network) -> (scores fp32 [Q, k], gallery rows int64 [Q, k]) as CUDA tensors, no host synchronisation on the
+        single-kernel paths.  Row r is the r-th key of self.db."""
+        g = self.gallery()
+        q = _queries_to_dev(embeddings, g.dim, self.match_device)
+        world, _ = self._world_rank()
+        if world > 1:
+            if self._sharded is None:
+                self._sharded = self._make_sharded()
+            return self._sharded.search(q, k)
+        return self._local_topk(q, k)
+
+    def _make_sharded(self):
+        """The cross-rank step behind a sharded engine: local top-k with global ids -> fused NVLink exchange + merge."""
+        from .sharded import ShardedSearch
+        return ShardedSearch(self._local_topk, ops.topk_merge, True, self._dist_group(), merge_packed=ops.topk_merge_packed,
+                             peer_exchange=True)
+
+    def _db_topk(self, emb, k: int):
+        """(scores [Q, k], rows [Q, k]) on the host for Q query embeddings under the reference's cosine rule."""
+        s, i = self.recognize_embeddings_device(emb, k)
+        return s.cpu().numpy(), i.cpu().numpy(), self.gallery().names
 
     def _format_db_result(self, scores, rows, names):
         top = [(names[j], float(s)) for s, j in zip(scores, rows) if j >= 0]
@@ -329,8 +412,9 @@ class RecognitionEngine:
         s, i, names = self._db_topk(embedding, 5)
         return self._format_db_result(s[0], i[0], names)
 
-    def recognize_embeddings(self, embeddings: np.ndarray) -> List[Tuple[str, float, List[Tuple[str, float]]]]:
-        """Batched recognize_with_db: Q embeddings [Q, D] -> Q result tuples from ONE kernel launch."""
+    def recognize_embeddings(self, embeddings) -> List[Tuple[str, float, List[Tuple[str, float]]]]:
+        """Batched recognize_with_db: Q embeddings [Q, D] (numpy, or a CUDA tensor) -> Q result tuples from ONE fused
+        similarity + top-k call."""
         if self.db is None:
             return [("No database", 0.0, [])] * len(embeddings)
         s, i, names = self._db_topk(embeddings, 5)
@@ -340,9 +424,16 @@ class RecognitionEngine:
         """inference/recognition_engine.py:291-326: e/(||e||+1e-8), IndexFlatIP.search, strict '<' threshold."""
         if self.faiss_index is None:
             return "No FAISS index", 0.0, []
-        q = _to_dev(np.asarray(embedding).astype(np.float32).reshape(1, -1), self.match_device)
+        return self._faiss_results(np.asarray(embedding).astype(np.float32).reshape(1, -1), k)[0]
+
+    def _faiss_results(self, embeddings, k: int) -> List[Tuple[str, float, List[Tuple[str, float]]]]:
+        """recognize_with_faiss for Q embeddings in one search call."""
+        q = _queries_to_dev(embeddings, self.faiss_index.d, self.match_device)
         scores, indices = self.faiss_index.search_device(q, k, qnorm_mode=N.FRB_QNORM_EPS)
-        scores, indices = scores.cpu().numpy().flatten(), indices.cpu().numpy().flatten()
+        scores, indices = scores.cpu().numpy(), indices.cpu().numpy()
+        return [self._format_faiss_result(indices[r], scores[r]) for r in range(scores.shape[0])]
+
+    def _format_faiss_result(self, indices, scores):
         results = []
         for idx, score in zip(indices, scores):
             if idx == -1:
@@ -390,8 +481,31 @@ class RecognitionEngine:
         return result
 
     def recognize_batch(self, img_inputs: Sequence, use_faiss: bool = None) -> List[Dict]:
-        """inference/recognition_engine.py:383-389."""
-        return [self.recognize(img, use_faiss) for img in img_inputs]
+        """inference/recognition_engine.py:383-389 — same list of result dicts as calling recognize() per image; the
+        embeddings are extracted per image (upstream of this path) and then matched in ONE batched call."""
+        results = []
+        for img in img_inputs:
+            r = {"identity": "Unknown", "confidence": 0.0, "top_k": [], "embedding": None, "status": "success"}
+            r["embedding"] = self.extract_embedding(img)
+            if r["embedding"] is None:
+                r["status"] = "error"
+                r["message"] = "Cannot extract embedding (no face or invalid image)"
+            results.append(r)
+        live = [r for r in results if r["status"] == "success"]
+        if use_faiss is None:
+            use_faiss = self.faiss_index is not None
+        if use_faiss and self.faiss_index is not None:
+            matches = self._faiss_results(np.stack([np.asarray(r["embedding"], np.float32).reshape(-1) for r in live]), 5) if live else []
+        elif self.db is not None:
+            matches = self.recognize_embeddings(np.stack([np.asarray(r["embedding"], np.float32).reshape(-1) for r in live])) if live else []
+        else:
+            for r in live:
+                r["status"] = "error"
+                r["message"] = "No database loaded"
+            return results
+        for r, (identity, confidence, top_k) in zip(live, matches):
+            r["identity"], r["confidence"], r["top_k"] = identity, confidence, top_k
+        return results
 
     def add_to_db(self, name: str, img_inputs: Sequence) -> bool:
         """inference/recognition_engine.py:391-422: mean of the embeddings, / (||mean|| + 1e-8)."""
@@ -439,7 +553,7 @@ def match_facenet(db: Dict[str, np.ndarray], embedding: np.ndarray, threshold: f
     Returns {"identity", "confidence", "distance", "top_k"}."""
     dev = _match_device(device)
     g = gallery or DeviceGallery(db, dev)
-    q = _to_dev(np.asarray(embedding).astype(np.float32).reshape(1, -1), dev)
+    q = _pad8(_to_dev(np.asarray(embedding).astype(np.float32).reshape(1, -1), dev))
     qn = ops.normalize_rows(q, N.FRB_QNORM_EPS)
     s, i = ops.cosine_topk(qn, g.unit_rows(), 5, score_mode=N.FRB_SCORE_IP)
     s, i = s.cpu().numpy()[0], i.cpu().numpy()[0]
@@ -447,7 +561,7 @@ def match_facenet(db: Dict[str, np.ndarray], embedding: np.ndarray, threshold: f
     # the 5 winning rows come back to the host so the displayed L2 distance is the reference's own
     # float32 expression ||e - d|| (web_app.py:552) rather than a cancellation-prone sqrt(2 - 2s)
     e = qn.cpu().numpy()[0]
-    rows = g.unit_rows()[torch.tensor(keep, dtype=torch.int64, device=dev)].cpu().numpy() if keep else np.zeros((0, g.dim))
+    rows = g.unit_rows()[torch.tensor(keep, dtype=torch.int64, device=dev)].cpu().numpy() if keep else np.zeros((0, e.shape[0]))
     top_k = [(g.names[j], float(sc), float(np.linalg.norm(e - rows[r]))) for r, (sc, j) in enumerate(zip(s, keep))]
     best_name, best_score, best_distance = top_k[0]
     if best_score < threshold:

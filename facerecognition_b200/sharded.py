@@ -53,6 +53,11 @@ class ShardedSearch:
         # peer_exchange: use the fused NVLink exchange + merge kernel (frb_exchange_topk_merge) instead of the
         # all-gather; set up lazily, and only if every rank managed to map every peer's buffer (CUDA IPC)
         self.peer_exchange, self._exchange, self._exchange_failed = peer_exchange, None, False
+        # product wiring may add: local search over queries that are already normalised bf16 (cosine), and the
+        # normaliser that produces them (see cosine_sharded)
+        self.local_search_bf16: Optional[Callable[[torch.Tensor, int], Tuple[torch.Tensor, torch.Tensor]]] = None
+        self.normalize_bf16: Optional[Callable[[torch.Tensor, torch.Tensor], None]] = None
+        self._graphs = {}      # (data_ptr, shape, dtype, k) -> (CUDAGraph, scores, idx): the replayed step
 
     def _get_exchange(self, n_query: int, k: int, device: torch.device):
         from . import _native as N
@@ -95,23 +100,98 @@ class ShardedSearch:
     def world(self) -> int:
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
 
-    def search(self, queries: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    def _local(self, queries: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        if queries.dtype == torch.bfloat16:
+            if self.local_search_bf16 is None:
+                raise ValueError("this sharded search has no bf16-query form (cosine over a bf16 shard only)")
+            return self.local_search_bf16(queries, k)
+        return self.local_search(queries, k)
+
+    def search(self, queries: torch.Tensor, k: int, graph: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Merged top-k of the replicated `queries` over all shards, on every rank.  bf16 queries (cosine) are taken as
+        already normalised (see gather_normalized).  graph=True: the step (local search kernels + the exchange kernel)
+        is captured into a CUDA graph on first use for this exact input buffer and replayed afterwards — `queries`
+        must then be the same tensor every call (refill it in place) and the returned tensors are overwritten by the
+        next call with the same buffer."""
         world = self.world()
         n_query = queries.shape[0]
+        if graph and queries.is_cuda and n_query > 0:
+            ex = self._get_exchange(n_query, k, queries.device) if (world > 1 and self.peer_exchange) else None
+            if world == 1 or ex is not None:
+                return self._replay(queries, k, ex)
         if world == 1:
-            return self.local_search(queries, k)               # [Q, k] with global ids
+            return self._local(queries, k)                     # [Q, k] with global ids
         if self.peer_exchange and queries.is_cuda:
             ex = self._get_exchange(n_query, k, queries.device)
             if ex is not None:
-                scores, idx = self.local_search(queries, k)
+                scores, idx = self._local(queries, k)
                 return ex.topk_merge(scores, idx, self.largest)   # ONE kernel: peer stores + flags + merge
+        if queries.dtype == torch.bfloat16:
+            scores, idx = self._local(queries, k)
+            return self._gather_merge(scores, idx)
+        return self._gather_merge(None, None, queries, k)
+
+    def _replay(self, queries: torch.Tensor, k: int, ex) -> Tuple[torch.Tensor, torch.Tensor]:
+        key = (queries.data_ptr(), tuple(queries.shape), queries.dtype, k)
+        hit = self._graphs.get(key)
+        if hit is None:
+            def step():
+                s, i = self._local(queries, k)
+                return ex.topk_merge(s, i, self.largest) if ex is not None else (s, i)
+            step()                                             # eager once: lazy per-device setup must not be captured
+            torch.cuda.synchronize(queries.device)
+            if ex is not None:
+                dist.barrier(group=self.group)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = step()
+            hit = (g, out[0], out[1])
+            if len(self._graphs) >= 8:                         # a serving loop cycles through a few staging buffers
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = hit
+        hit[0].replay()
+        return hit[1], hit[2]
+
+    def gather_normalized(self, my_rows: torch.Tensor, out: torch.Tensor, q0: int) -> torch.Tensor:
+        """This rank's fp32 slice [q1 - q0, D] of the batch -> L2-normalised bf16 rows written into out[q0:q1], then ONE
+        all-gather replicates every rank's slice into `out` (bf16 [Q, D]): half the NVLink bytes of gathering the fp32
+        batch, and each query is normalised once in the job instead of once per rank.  Equal slices on every rank."""
+        if self.normalize_bf16 is None:
+            raise ValueError("this sharded search has no bf16-query form (cosine over a bf16 shard only)")
+        mine = out[q0:q0 + my_rows.shape[0]]
+        self.normalize_bf16(my_rows, mine)
+        if self.world() > 1:
+            dist.all_gather_into_tensor(out, mine, group=self.group)
+        return out
+
+    def resync(self) -> None:
+        """Collective: after any rank skipped or failed a step, restart the exchange epochs (frb_exchange_reset between
+        two barriers) and drop the captured graphs' outputs' validity (graphs themselves stay valid)."""
+        if self._exchange is None:
+            return
+        dev = self._exchange.device
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self.group)
+        self._exchange.reset()
+        dist.barrier(group=self.group)
+
+    def _gather_merge(self, scores, idx, queries: Optional[torch.Tensor] = None, k: int = 0):
+        world = self.world()
+        if scores is not None:
+            n_query, k = scores.shape
+            device = scores.device
+        else:
+            n_query, device = queries.shape[0], queries.device
         idx_bytes, rec, rec_pad = _record_layout(n_query, k)
         rank = dist.get_rank(self.group)
-        gathered = torch.empty((world, rec_pad), dtype=torch.uint8, device=queries.device)
+        gathered = torch.empty((world, rec_pad), dtype=torch.uint8, device=device)
         mine = gathered[rank]                                   # in-place all-gather: my record sits in my slot
         my_idx = mine[:idx_bytes].view(torch.int64).view(n_query, k)
         my_scores = mine[idx_bytes:rec].view(torch.float32).view(n_query, k)
-        if self.local_into is not None:
+        if scores is not None:
+            my_scores.copy_(scores)
+            my_idx.copy_(idx)
+        elif self.local_into is not None:
             self.local_into(queries, k, my_scores, my_idx)
         else:
             scores, idx = self.local_search(queries, k)
@@ -138,8 +218,12 @@ def cosine_sharded(gallery_shard: torch.Tensor, row_offset: int, *, qnorm_mode: 
         ops.cosine_topk(q, gallery_shard, k, score_mode=N.FRB_SCORE_IP, qnorm_mode=qnorm_mode, idx_base=row_offset,
                         out=(scores, idx))
 
-    return ShardedSearch(local, ops.topk_merge, True, group, local_into=local_into, merge_packed=ops.topk_merge_packed,
-                         peer_exchange=peer_exchange)
+    ss = ShardedSearch(local, ops.topk_merge, True, group, local_into=local_into, merge_packed=ops.topk_merge_packed,
+                       peer_exchange=peer_exchange)
+    if gallery_shard.dtype == torch.bfloat16 and qnorm_mode != 0:
+        ss.local_search_bf16 = lambda q16, k: ops.cosine_topk_bf16q(q16, gallery_shard, k, idx_base=row_offset)
+        ss.normalize_bf16 = lambda rows, out: ops.normalize_rows(rows, qnorm_mode, out=out)
+    return ss
 
 
 def chisq_sharded(hist_shard: torch.Tensor, cell_px: int, row_offset: int, *, q_cell_px: Optional[int] = None,
@@ -168,17 +252,28 @@ class HostBatchPipeline:
     the batch; the whole batch on one GPU) and downloads the answers of the same rows.
     """
 
-    def __init__(self, search: Callable[[torch.Tensor, int], Tuple[torch.Tensor, torch.Tensor]], n_query: int, dim: int,
+    def __init__(self, search, n_query: int, dim: int,
                  k: int, device: torch.device, *, rows: Optional[Tuple[int, int]] = None, depth: int = 2,
-                 group: Optional[dist.ProcessGroup] = None):
+                 group: Optional[dist.ProcessGroup] = None, graph: bool = True):
         if device.type != "cuda":
             raise RuntimeError("HostBatchPipeline needs a CUDA device: there is no CPU implementation in this package")
-        self.search, self.k, self.device, self.depth, self.group = search, k, device, depth, group
+        # `search`: a ShardedSearch (preferred: its step is graph-replayed, and with several ranks each rank normalises
+        # its own slice and the all-gather moves bf16 rows) or any callable (stage fp32 [Q, D], k) -> (scores, idx)
+        self.sharded = search if isinstance(search, ShardedSearch) else None
+        self.search = search.search if self.sharded is not None else search
+        self.k, self.device, self.depth, self.group = k, device, depth, group
+        self.graph = graph and self.sharded is not None
         self.q0, self.q1 = rows if rows is not None else (0, n_query)
         self.whole = (self.q0, self.q1) == (0, n_query)
         n_mine = self.q1 - self.q0
+        self.group = group
         self.copy_in, self.copy_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
-        self.stage = [torch.empty((n_query, dim), dtype=torch.float32, device=device) for _ in range(depth)]
+        self.bf16_gather = (self.sharded is not None and self.sharded.normalize_bf16 is not None and not self.whole)
+        if self.bf16_gather:
+            self.stage = [torch.empty((n_mine, dim), dtype=torch.float32, device=device) for _ in range(depth)]
+            self.stage16 = [torch.empty((n_query, dim), dtype=torch.bfloat16, device=device) for _ in range(depth)]
+        else:
+            self.stage = [torch.empty((n_query, dim), dtype=torch.float32, device=device) for _ in range(depth)]
         self.out_s = [torch.empty((n_mine, k), dtype=torch.float32).pin_memory() for _ in range(depth)]
         self.out_i = [torch.empty((n_mine, k), dtype=torch.int64).pin_memory() for _ in range(depth)]
         self.h2d_done = [torch.cuda.Event() for _ in range(depth)]
@@ -197,20 +292,26 @@ class HostBatchPipeline:
         stage = self.stage[slot]
         with torch.cuda.stream(self.copy_in):
             self.copy_in.wait_event(self.searched[slot])        # the search that last read this staging buffer is done
-            stage[self.q0:self.q1].copy_(q_host, non_blocking=True)
+            (stage if self.bf16_gather else stage[self.q0:self.q1]).copy_(q_host, non_blocking=True)
             self.h2d_done[slot].record(self.copy_in)
         main.wait_event(self.h2d_done[slot])
-        if not self.whole:
-            dist.all_gather_into_tensor(stage, stage[self.q0:self.q1], group=self.group)
-        s, i = self.search(stage, self.k)
+        if self.bf16_gather:
+            # normalise my slice -> bf16, ONE all-gather of bf16 rows, tensor-core search on the gathered batch
+            q16 = self.sharded.gather_normalized(stage, self.stage16[slot], self.q0)
+            s, i = self.sharded.search(q16, self.k, graph=self.graph)
+        else:
+            if not self.whole:
+                dist.all_gather_into_tensor(stage, stage[self.q0:self.q1], group=self.group)
+            s, i = self.sharded.search(stage, self.k, graph=self.graph) if self.sharded is not None else self.search(stage, self.k)
         self.searched[slot].record(main)
         with torch.cuda.stream(self.copy_out):
             self.copy_out.wait_event(self.searched[slot])
             self.out_s[slot].copy_(s[self.q0:self.q1], non_blocking=True)
             self.out_i[slot].copy_(i[self.q0:self.q1], non_blocking=True)
             self.d2h_done[slot].record(self.copy_out)
-        s.record_stream(self.copy_out)
-        i.record_stream(self.copy_out)
+        if not self.graph:                                       # graph outputs are static buffers owned by the graph
+            s.record_stream(self.copy_out)
+            i.record_stream(self.copy_out)
         self.busy[slot] = True
         return slot
 

@@ -239,6 +239,20 @@ int frb_lbp_codes_u8(const uint8_t *images_dev, int64_t count, int rows, int col
 int frb_lbp_hist_u8(const uint8_t *images_dev, int64_t count, int rows, int cols, int radius, int neighbors,
                     int grid_x, int grid_y, uint16_t *out_hist_dev, int *out_cell_px, void *stream);
 
+/* The same pass writing u8 counts [count, grid_x*grid_y*256] — the gallery form the chi-square kernels stream
+ * (frb_chisq_topk_g8, frb_chisq_top1_filtered_g8): valid when a cell has <= 255 pixels (100x100 and 112x112 faces under
+ * the 8x8 grid: 144 / 169), else FRB_ERR_UNSUPPORTED.  Half the bytes written per trained face, and no conversion pass
+ * between LBPH train()/update() and the gallery. */
+int frb_lbp_hist_u8_counts8(const uint8_t *images_dev, int64_t count, int rows, int cols, int radius, int neighbors,
+                            int grid_x, int grid_y, uint8_t *out_hist_dev, int *out_cell_px, void *stream);
+
+/* u16 counts -> u8 counts, n elements (every count must be <= 255): adopting a u16 histogram matrix as a u8 gallery. */
+int frb_counts_u16_to_u8(const uint16_t *src_dev, int64_t n, uint8_t *dst_dev, void *stream);
+
+/* idx[i] = idx[i] >= 0 ? table[idx[i]] : idx[i], in place, n entries: local gallery rows -> the caller's global row ids
+ * (LBPH galleries that mix image sizes keep one histogram group per cell size; facerecognition_b200/lbph.py). */
+int frb_index_remap(int64_t *idx_dev, int64_t n, const int64_t *table_dev, int64_t table_len, void *stream);
+
 size_t frb_chisq_topk_workspace_bytes(int64_t n_query, int64_t n_gallery, int hist_len, int k);
 
 /* Chi-square (HISTCMP_CHISQR_ALT) nearest neighbours: for each query histogram find the k

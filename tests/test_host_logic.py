@@ -80,6 +80,103 @@ def test_sharded_search_gloo_world2():
     assert sorted(results) == [(0, True), (1, True)]
 
 
+def _engine_worker(rank, world, port, q_out):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        sys.path.insert(0, ROOT)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        import facerecognition_b200 as F
+        from facerecognition_b200 import recognition_engine as RE
+        from facerecognition_b200.sharded import ShardedSearch, shard_bounds
+        from oracle import cosine as OC
+        from oracle import lbph as OL
+        rng = np.random.default_rng(11)
+        gal = rng.standard_normal((37, 64)).astype(np.float32)
+        gal /= np.linalg.norm(gal, axis=1, keepdims=True)
+        gal[30] = gal[4]                                       # a tie across the two shards: the first identity wins
+        db = {f"id_{i:03d}": g for i, g in enumerate(gal)}
+        qs = np.concatenate([gal[[4, 36, 0]] * 1.7, rng.standard_normal((3, 64)).astype(np.float32)])
+
+        # ---- RecognitionEngine(group=True): only the three device-touching seams are replaced by CPU stand-ins ----
+        RE._queries_to_dev = lambda emb, dim, dev: torch.from_numpy(np.asarray(emb, np.float32).reshape(-1, dim))
+        eng = F.RecognitionEngine(model_path=None, threshold=0.5, use_face_detection=False, group=True)
+        eng.db = db
+        lo, hi = shard_bounds(len(db), world, rank)
+
+        class Gallery:
+            names, dim = list(db.keys()), 64
+        eng.gallery = lambda: Gallery
+
+        def local(q, k):                                      # this rank's rows only, global ids
+            S = np.array([[OC.cosine_similarity(a, b) for b in gal[lo:hi]] for a in q.numpy()], np.float32).reshape(len(q), hi - lo)
+            order = np.argsort(-S, axis=1, kind="stable")[:, :k]
+            return torch.from_numpy(np.take_along_axis(S, order, 1)), torch.from_numpy(order + lo)
+        eng._local_topk = local
+        eng._make_sharded = lambda: ShardedSearch(local, _np_merge, True, None)
+        got = eng.recognize_embeddings(qs)
+        ok = True
+        for e, g in zip(qs, got):
+            name, score, top = OC.recognize_with_db(db, e, 0.5)
+            ok = ok and g[0] == name and abs(g[1] - score) < 1e-6 and [t[0] for t in g[2]] == [t[0] for t in top]
+        ok = ok and [t[0] for t in got[0][2][:2]] == ["id_004", "id_030"]
+
+        # ---- LBPHFaceRecognizer(group=True): train() keeps this rank's slice, predict merges across ranks ----
+        faces = rng.integers(0, 256, (11, 40, 40), dtype=np.uint8)
+        faces[9] = faces[2]                                    # duplicate faces on different ranks: the lower row wins
+        labels = np.arange(100, 111, dtype=np.int32)
+        ref = OL.OracleLBPH()
+        ref.train(list(faces), labels)
+        model = F.LBPHFaceRecognizer_create(group=True)
+        flo, fhi = shard_bounds(len(faces), world, rank)
+        kept = {}
+
+        def fake_add(src, lab, what):                          # host part of _add with the K2 call replaced by the oracle
+            from facerecognition_b200.lbph import _Group
+            fs = list(src)
+            a, b = shard_bounds(len(fs), world, rank)
+            h, px = OL.c_lbp_hist(np.stack(fs[a:b])) if b > a else (np.zeros((0, 16384), np.uint16), 0)
+            kept["hist"], kept["px"], kept["lo"] = h, px, model.size + a
+            model._labels = np.concatenate([model._labels, np.asarray(lab, np.int32)])
+        model._add = fake_add
+        model.train(list(faces), labels)
+
+        def local_lbph(qh, kk):
+            d = np.stack([OL.c_chisq_scan_u16(kept["hist"], kept["px"], q.astype(np.uint16), kept["px"]) for q in qh.numpy()])
+            d = d.astype(np.float32).reshape(len(qh), len(kept["hist"]))
+            order = np.argsort(d, axis=1, kind="stable")[:, :kk]
+            return torch.from_numpy(np.take_along_axis(d, order, 1)), torch.from_numpy(order + kept["lo"])
+        model._make_sharded = lambda: ShardedSearch(None, _np_merge, False, None)
+        model._search_local = lambda qh, qpx, kk: local_lbph(qh, kk)
+        qh, qpx = OL.c_lbp_hist(faces[[2, 9, 5]])
+        d, i = model._search(torch.from_numpy(qh.astype(np.int32)), qpx, 1)
+        want = [ref.predict(f) for f in faces[[2, 9, 5]]]
+        ok = ok and [int(model._labels[j]) for j in i[:, 0]] == [w[0] for w in want] == [102, 102, 105]
+        ok = ok and all(abs(float(a) - w[1]) <= 1e-5 * max(w[1], 1e-30) for a, w in zip(d[:, 0], want))
+        q_out.put((rank, bool(ok)))
+        dist.destroy_process_group()
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q_out.put((rank, traceback.format_exc()))
+
+
+def test_sharded_engine_and_lbph_classes_gloo_world2():
+    """RecognitionEngine(group=...) and LBPHFaceRecognizer(group=...) shard their galleries by shard_bounds and route the
+    batched entry points through ShardedSearch; with the CUDA seams replaced by the oracle, two gloo ranks must give the
+    single-process reference answers (names, scores, tie order, labels, distances)."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_engine_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, True), (1, True)], results
+
+
 def test_faiss_flat_ip_file_roundtrip(tmp_path):
     from facerecognition_b200 import formats
     rows = np.random.default_rng(0).standard_normal((37, 512)).astype(np.float32)
