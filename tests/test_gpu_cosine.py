@@ -397,3 +397,63 @@ def test_engine_batches_on_a_large_gallery_use_the_first_pass_and_agree_with_sin
         name, score, top = eng.recognize_with_db(q[j])
         assert batched[j][0] == name == f"id_{src[j]:06d}" and abs(batched[j][1] - score) <= 2e-6
         assert [t[0] for t in batched[j][2]] == [t[0] for t in top]
+
+
+def test_prenormalised_bf16_queries_entry_equals_the_fp32_query_entry():
+    """frb_cosine_topk_bf16q (what a sharded search calls after gathering the ranks' normalised bf16 query slices) vs
+    frb_cosine_topk with the prologue: identical results, through the tcgen05 kernel and the row-streaming one."""
+    from facerecognition_b200 import ops, _native as NV
+    rng = np.random.default_rng(8)
+    gal = ops.normalize_rows(dev(unit(rng.standard_normal((20_011, 512)))), NV.FRB_QNORM_NONE, torch.bfloat16)
+    for Q in (1, 2, 5, 300):
+        q = dev(rng.standard_normal((Q, 512)).astype(np.float32) * 3)
+        want = ops.cosine_topk(q, gal, 5, qnorm_mode=NV.FRB_QNORM_CLAMP, idx_base=11)
+        q16 = ops.normalize_rows(q, NV.FRB_QNORM_CLAMP, torch.bfloat16)
+        got = ops.cosine_topk_bf16q(q16, gal, 5, idx_base=11)
+        assert torch.equal(got[1], want[1]) and torch.equal(got[0], want[0]), Q
+
+
+def test_any_embedding_dimension_and_batched_recognize_batch(tmp_path):
+    """The reference's matchers take any embedding length (numpy loops); here rows and queries are zero-padded to the
+    kernels' vector width.  recognize_batch matches all images in one call and equals per-image recognize()."""
+    import facerecognition_b200 as F
+    rng = np.random.default_rng(21)
+    for dim in (100, 129, 512):
+        gal = unit(rng.standard_normal((300, dim)))
+        db = {f"p{i:03d}": g for i, g in enumerate(gal)}
+        q = gal[rng.integers(0, 300, 6)] + 0.02 * rng.standard_normal((6, dim)).astype(np.float32)
+        table = {f"img{j}": e for j, e in enumerate(q)}
+        table["bad"] = None
+        eng = F.RecognitionEngine(model_path=None, threshold=0.5, use_face_detection=False, embedder=table.get)
+        eng.db = db
+        for e in q[:3]:
+            name, score, top = eng.recognize_with_db(e)
+            rname, rscore, rtop = OC.recognize_with_db(db, e, 0.5)
+            assert name == rname and abs(score - rscore) <= TOL_F32 and [t[0] for t in top] == [t[0] for t in rtop]
+        imgs = ["img0", "bad", "img3", "img5"]
+        batch = eng.recognize_batch(imgs)
+        single = [eng.recognize(x) for x in imgs]
+        assert [b["status"] for b in batch] == ["success", "error", "success", "success"]
+        for b, s1 in zip(batch, single):
+            assert b["identity"] == s1["identity"] and b["status"] == s1["status"] and abs(b["confidence"] - s1["confidence"]) <= 2e-6
+            assert [t[0] for t in b["top_k"]] == [t[0] for t in s1["top_k"]]
+        # device tensors in, device tensors out
+        s_dev, i_dev = eng.recognize_embeddings_device(torch.from_numpy(q).cuda(), 5)
+        assert s_dev.is_cuda and [eng.gallery().names[int(j)] for j in i_dev[:, 0]] == [r[0] if r[0] != "Unknown" else eng.gallery().names[int(i_dev[n, 0])]
+                                                                                       for n, r in enumerate(eng.recognize_embeddings(q))]
+        # FAISS-style index with the same dimension
+        index = F.build_faiss_index(gal, str(tmp_path / f"i{dim}.faiss"))
+        back = F.FlatIPIndex.from_file(str(tmp_path / f"i{dim}.faiss"))
+        s1, i1 = index.search(q, 3)
+        s2, i2 = back.search(torch.from_numpy(q).cuda(), 3)
+        rs, ri = OC.flat_ip_search(OC.build_flat_ip(gal), q, 3)
+        assert np.array_equal(i1, ri) and np.array_equal(i2, ri) and np.abs(s1 - rs).max() <= TOL_F32 * 10
+        got = F.match_facenet(db, q[0], 0.5)
+        name, score, dist, top = OC.facenet_match(db, q[0], 0.5)
+        assert got["identity"] == name and abs(got["confidence"] - score) <= TOL_F32
+    # in-place dict mutations that used to go unnoticed
+    eng.db |= {"zz_new": unit(rng.standard_normal((1, 512)))[0]}
+    assert "zz_new" in eng.gallery().names
+    eng.db["zz_new"][:] = eng.db["p000"]
+    eng.db.invalidate()
+    assert eng.recognize_with_db(eng.db["p000"])[2][1][0] == "zz_new"

@@ -400,3 +400,49 @@ def test_chisq_u8_gallery_limits():
         ops.chisq_topk(q24, 9, torch.zeros((4, 24), dtype=torch.uint8, device="cuda"), 9, k=1)   # 24 % 16 != 0
     h16 = torch.zeros((2, 24), dtype=torch.int16, device="cuda").view(torch.uint16)
     assert ops.compact_histograms(h16, 9).dtype == torch.uint16 and ops.compact_histograms(h16, 300).dtype == torch.uint16
+
+
+@pytest.mark.parametrize("shape,grid", [((100, 100), 8), ((112, 112), 8), ((61, 75), 4), ((130, 98), 8)])
+def test_k2_u8_count_output_equals_the_u16_output(shape, grid):
+    """frb_lbp_hist_u8_counts8 (the gallery form written straight by K2) == frb_lbp_hist_u8 narrowed; also the
+    u16 -> u8 narrowing kernel and the row-id remap kernel that replaced the eager torch ops on the product path."""
+    from facerecognition_b200 import ops
+    rng = np.random.default_rng(shape[0] * 7 + grid)
+    imgs = torch.from_numpy(rng.integers(0, 256, (37,) + shape, dtype=np.uint8)).cuda()
+    imgs[3] = 200                                                          # flat image: one bin holds the whole cell
+    h16, px = ops.lbp_hist(imgs, grid_x=grid, grid_y=grid)
+    h8, px8 = ops.lbp_hist(imgs, grid_x=grid, grid_y=grid, counts8=True)
+    assert px == px8
+    if px <= 255:
+        assert h8.dtype == torch.uint8 and np.array_equal(h8.cpu().numpy(), h16.cpu().numpy().astype(np.uint8))
+        assert int(h8.cpu().numpy().astype(np.int64).sum()) == 37 * grid * grid * px
+        assert torch.equal(ops.compact_histograms(h16, px), h8)
+    else:
+        assert h8.dtype == torch.uint16 and torch.equal(h8.view(torch.int16), h16.view(torch.int16))
+    idx = torch.tensor([[0, 3, -1], [2, -1, 1]], dtype=torch.int64, device="cuda")
+    table = torch.tensor([100, 200, 300, 400], dtype=torch.int64, device="cuda")
+    assert ops.index_remap(idx, table).tolist() == [[100, 400, -1], [300, -1, 200]]
+
+
+def test_mixed_size_gallery_and_web_ui_mapping(oracle_lbph):
+    """Two image sizes in one model (two histogram groups, row ids remapped on the device) against the oracle, plus the
+    web UI's confidence / Unknown mapping (web_app.py:597,605)."""
+    import facerecognition_b200 as F
+    rng = np.random.default_rng(91)
+    a = [rng.integers(0, 256, (100, 100), dtype=np.uint8) for _ in range(9)]
+    b = [rng.integers(0, 256, (112, 112), dtype=np.uint8) for _ in range(7)]
+    faces = [a[0], b[0], a[1], b[1]] + a[2:] + b[2:]
+    labels = np.arange(len(faces), dtype=np.int32) + 10
+    model = F.train_lbph_model(faces, labels)
+    ref = oracle_lbph.OracleLBPH()
+    ref.train(faces, labels)
+    for f in [faces[1], faces[2], faces[-1], rng.integers(0, 256, (112, 112), dtype=np.uint8)]:
+        lab, dist = model.predict(f)
+        rlab, rdist = ref.predict(f)
+        assert lab == rlab and abs(dist - rdist) <= 1e-5 * max(rdist, 1e-30)
+    assert F.web_confidence(0.0) == 1.0 and F.web_confidence(50.0) == 0.75 and F.web_confidence(200.0) == 0.0 and F.web_confidence(1e9) == 0.0
+    r = F.recognize_face_web(model, faces[2], threshold=80.0, label_map={12: "carol"})
+    assert r == {"identity": "carol", "confidence": 1.0, "distance": 0.0, "label": 12}
+    far = rng.integers(0, 256, (100, 100), dtype=np.uint8)
+    r = F.recognize_face_web(model, far, threshold=1.0)
+    assert r["identity"] == "Unknown" and r["confidence"] == F.web_confidence(r["distance"])
