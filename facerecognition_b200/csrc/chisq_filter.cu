@@ -59,6 +59,12 @@ constexpr uint32_t kCfATileBytes = kCfBlockM * kCfBlockK * 2;      // 16 KB
 constexpr uint32_t kCfAStageBytes = kCfQTiles * kCfATileBytes;     // 32 KB
 constexpr uint32_t kCfBStageBytes = kCfBlockN * kCfBlockK * 2;     // 32 KB
 constexpr int kCfTableRows = 256;
+// The generators' table look-ups hit arbitrary rows, so lanes of a quarter-warp would collide on banks (ncu, first
+// version: 89.6 M bank conflicts, 8.6 instead of 4 wavefronts per 128-bit look-up).  The shared-memory copy of the
+// table is therefore REPLICATED: row a holds COP copies of u(a) side by side and lane l reads copy l % COP, so the
+// eight lanes of a quarter-warp always touch eight different bank groups whatever their rows are.  8 copies fit when
+// cell_px + 1 <= 176 rows (22 KB; 100x100 and 112x112 faces: 145 / 170 rows); larger cells get 4 copies of 256 rows.
+constexpr int kCfRows8 = 176;
 constexpr int64_t kCfMaxQueriesPerPass = 1024;
 constexpr int kCfFallbackChunks = 64;
 
@@ -78,6 +84,7 @@ struct CfParams {
     int64_t n_qtiles, n_qpairs, n_gtiles;
     const uint8_t *gallery;             // [n_gallery, hist_len] u8 counts
     const uint4 *u_table;               // [256] gallery-side features, 8 x fp16 per count
+    int table_rows;                     // rows of the shared-memory copy (counts are clamped to table_rows - 1)
     const float *window;                // [n_query] w(q) in S units
     float *best;                        // [n_query] running max of the score S~ - (row total) / 4, -inf on entry
     int *cnt;                           // [n_query] candidates appended (may exceed cap)
@@ -93,6 +100,7 @@ __device__ __forceinline__ float cf_atomic_max(float *addr, float v)   // return
     return __uint_as_float(atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v)));
 }
 
+template <int COP>
 __global__ void __launch_bounds__(kCfThreads, 1)
 chisq_filter_kernel(const __grid_constant__ CUtensorMap tmap_f, const CfParams p)
 {
@@ -101,13 +109,13 @@ chisq_filter_kernel(const __grid_constant__ CUtensorMap tmap_f, const CfParams p
     unsigned char *smem_a = smem;
     unsigned char *smem_b = smem + (size_t)kCfAStages * kCfAStageBytes;
     uint4 *tbl = reinterpret_cast<uint4 *>(smem_b + (size_t)kCfBStages * kCfBStageBytes);
-    float *rowsum = reinterpret_cast<float *>(tbl + kCfTableRows);      // [2][256]: (sum of the row's counts) / 4, by unit parity
+    float *rowsum = reinterpret_cast<float *>(tbl + p.table_rows * COP);   // [2][256]: (sum of the row's counts) / 4, by unit parity
     CfBarriers *bars = reinterpret_cast<CfBarriers *>(rowsum + 2 * kCfBlockN);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_units = p.n_qpairs * p.n_gtiles;
 
-    for (int i = threadIdx.x; i < kCfTableRows; i += kCfThreads) tbl[i] = p.u_table[i];
+    for (int i = threadIdx.x; i < p.table_rows * COP; i += kCfThreads) tbl[i] = p.u_table[i / COP];
     if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_f) : "memory");
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kCfAStages; s++) {
@@ -188,6 +196,8 @@ chisq_filter_kernel(const __grid_constant__ CUtensorMap tmap_f, const CfParams p
         const int r = (warp - kCfGenWarp0) * 32 + lane;          // gallery row inside the tile
         const uint32_t xr = (uint32_t)(r & 7) << 4;              // 128-byte swizzle: 16-byte chunk c of row r sits at c ^ (r & 7)
         const int n_iter = p.n_kblocks >> 1;                     // 16 bins (one 128-bit load) = two k-blocks per iteration
+        const uint4 *my_tbl = tbl + (lane & (COP - 1));          // this lane's copy of every table row
+        const uint32_t last_row = (uint32_t)p.table_rows - 1;
         int sb = 0;
         uint32_t pb = 0, upar = 0;
         for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, upar ^= 1) {
@@ -215,8 +225,8 @@ chisq_filter_kernel(const __grid_constant__ CUtensorMap tmap_f, const CfParams p
                     unsigned char *dst = smem_b + (size_t)sb * kCfBStageBytes + (size_t)r * 128;
 #pragma unroll
                     for (int c = 0; c < 8; c++) {
-                        const uint32_t cnt = (wds[h * 2 + (c >> 2)] >> (8 * (c & 3))) & 0xFFu;
-                        *reinterpret_cast<uint4 *>(dst + (((uint32_t)c << 4) ^ xr)) = tbl[cnt];
+                        const uint32_t cnt = min((wds[h * 2 + (c >> 2)] >> (8 * (c & 3))) & 0xFFu, last_row);
+                        *reinterpret_cast<uint4 *>(dst + (((uint32_t)c << 4) ^ xr)) = my_tbl[cnt * COP];
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the UMMA reads
                     __syncwarp();
@@ -653,13 +663,18 @@ int frb_chisq_top1_filtered_g8(const uint16_t *q_hist, int64_t n_query, const ui
     float *raw_s = (float *)(w + pl.raw_s), *list_s = (float *)(w + pl.list_s);
     int64_t *cand_idx = (int64_t *)(w + pl.cand_idx);
 
+    const bool cop8 = cell_px + 1 <= kCfRows8;
+    const int table_rows = cop8 ? kCfRows8 : kCfTableRows, copies = cop8 ? 8 : 4;
     const size_t smem = 1024 + (size_t)kCfAStages * kCfAStageBytes + (size_t)kCfBStages * kCfBStageBytes +
-                        kCfTableRows * sizeof(uint4) + 2 * kCfBlockN * sizeof(float) + sizeof(CfBarriers);
+                        (size_t)table_rows * copies * sizeof(uint4) + 2 * kCfBlockN * sizeof(float) + sizeof(CfBarriers);
     {
-        static thread_local int attr_dev = -1;
-        if (attr_dev != dev) {
-            FRB_CUDA_OK(cudaFuncSetAttribute(chisq_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_dev = dev;
+        static thread_local int attr_dev[2] = {-1, -1};
+        if (attr_dev[cop8] != dev) {
+            if (cop8)
+                FRB_CUDA_OK(cudaFuncSetAttribute(chisq_filter_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else
+                FRB_CUDA_OK(cudaFuncSetAttribute(chisq_filter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_dev[cop8] = dev;
         }
     }
     const int sms = sm_count() > 0 ? sm_count() : 148;
@@ -692,6 +707,7 @@ int frb_chisq_top1_filtered_g8(const uint16_t *q_hist, int64_t n_query, const ui
             p.n_gtiles = (n_gallery + kCfBlockN - 1) / kCfBlockN;
             p.gallery = gallery;
             p.u_table = tb.d_u;
+            p.table_rows = table_rows;
             p.window = window;
             p.best = best;
             p.cnt = cnt;
@@ -703,7 +719,10 @@ int frb_chisq_top1_filtered_g8(const uint16_t *q_hist, int64_t n_query, const ui
             const int grid = (int)(n_units < sms ? n_units : sms);
             {
                 ProfileScope prof(FRB_K_CHISQ_FILTER, st);
-                chisq_filter_kernel<<<grid, kCfThreads, smem, st>>>(tf, p);
+                if (cop8)
+                    chisq_filter_kernel<8><<<grid, kCfThreads, smem, st>>>(tf, p);
+                else
+                    chisq_filter_kernel<4><<<grid, kCfThreads, smem, st>>>(tf, p);
                 FRB_LAUNCH_OK("chisq_filter_kernel");
             }
         }

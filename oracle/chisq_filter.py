@@ -1,21 +1,30 @@
-"""oracle/chisq_filter.py — CPU statement of the candidate-filter algorithm planned in front of K3.
-TEST INFRASTRUCTURE ONLY; nothing in the product imports it.  It exists so that a future tensor-core filter kernel has
-an oracle: the feature tables, the rigorous error bound and the survivor rule are all defined (and tested) here.
+"""oracle/chisq_filter.py — CPU statement of the candidate filter in front of the chi-square scan
+(facerecognition_b200/csrc/chisq_filter.cu).  TEST INFRASTRUCTURE ONLY; nothing in the product imports it.
 
-chi-square over integer counts:  d(g, q) = sum_j (g_j - q_j)^2 / (g_j + q_j) = sum g + sum q - 4 sum_j f(g_j, q_j),
-f(a, b) = a b / (a + b) (0 at a + b = 0).  f on [0, cell_px]^2 is a table F; its rank-M truncated SVD gives per-count
-feature vectors u(a), v(b) in R^M with F ~ u v^T, so sum_j f(g_j, q_j) ~ <U(g), V(q)> with U(g) = concat_j u(g_j):
-an inner product of length hist_len * M — what a GEMM computes.  With features rounded to `dtype`:
+chi-square over integer counts of equal cell size:
+    d(g, q) = sum_j (g_j - q_j)^2 / (g_j + q_j) = sum g + sum q - 4 S(g, q),   S = sum_j f(g_j, q_j),   f(a, b) = a b / (a + b)
+(f = 0 at a + b = 0), so the nearest row maximises  score(g) = S(g, q) - (sum g) / 4.
+f on [0, cell_px]^2 is a symmetric table F.  The product factors W F W, w(a) = (1 + a)^-1.5, keeps the 8 eigen-pairs of
+largest |eigenvalue| and unscales:  u_m(a) = sqrt|lam_m| e_m(a) / w(a),  v_m(b) = sign(lam_m) u_m(b), both rounded to
+fp16, so  F~(a, b) = <u(a), v(b)>  and  S~(g, q) = sum_j F~(g_j, q_j)  is an inner product of length 8 * hist_len — what
+the tensor cores compute.  With E = F~ - F (float64, exact for the rounded tables):
 
-    |approx(g, q) - d(g, q)| <= eps(q) = 4 * sum_j max_a |F~ - F|(a, q_j)          for EVERY gallery row g,
+    |S~(g, q) - S(g, q)| <= e(q) = sum_j max_a |E(a, q_j)|          for EVERY gallery row g,
 
-so every row whose approximate distance exceeds (approximate minimum + 2 eps) cannot be the nearest neighbour, and the
-exact scan over the remaining rows returns exactly what the exact scan over all rows returns (ties: lowest row).
-(A kernel accumulating in fp32 must add its accumulation error bound to eps; this module accumulates in float64.)
+so a row can only be the exact scan's answer if  score~(g) >= max_rows score~ - 2 e(q)  (the product adds an allowance for
+the fp32 accumulation inside the tensor core and for the exact scan's own rounding to e).  The exact scan over those
+survivors returns exactly what the exact scan over all rows returns (ties: lowest row).
+
+This module restates the tables independently (numpy eigh) and states the survivor rule; tests/test_oracle_lbph.py
+checks the LIBRARY's tables (frb_chisq_filter_tables, a host function) against it: the library's error bounds must
+dominate the true error of the library's own fp16 tables, and the rule must keep the true nearest neighbour.
 """
 from __future__ import annotations
 
 import numpy as np
+
+RANK = 8
+WEIGHT_POWER = 1.5
 
 
 def f_table(cell_px: int) -> np.ndarray:
@@ -24,44 +33,48 @@ def f_table(cell_px: int) -> np.ndarray:
     return np.where(s > 0, a[:, None] * a[None, :] / np.maximum(s, 1.0), 0.0)
 
 
-def feature_tables(cell_px: int, rank: int = 8, dtype=np.float16):
-    """(u [cell_px+1, rank], v [cell_px+1, rank], err [cell_px+1, cell_px+1]) with u, v rounded to `dtype` (returned as
-    float64) and err = |u v^T - F| for exactly those rounded tables."""
+def feature_tables(cell_px: int, rank: int = RANK, dtype=np.float16):
+    """(u [cell_px+1, rank], v [cell_px+1, rank], E [cell_px+1, cell_px+1]) with u, v rounded to `dtype` (returned as
+    float64) and E = u v^T - F for exactly those rounded tables."""
     F = f_table(cell_px)
-    U, S, Vt = np.linalg.svd(F)
-    u = (U[:, :rank] * np.sqrt(S[:rank])).astype(dtype).astype(np.float64)
-    v = (Vt[:rank].T * np.sqrt(S[:rank])).astype(dtype).astype(np.float64)
-    return u, v, np.abs(u @ v.T - F)
+    w = (1.0 + np.arange(cell_px + 1, dtype=np.float64)) ** -WEIGHT_POWER
+    lam, vec = np.linalg.eigh(w[:, None] * F * w[None, :])
+    order = np.argsort(-np.abs(lam))[:rank]
+    u = np.sqrt(np.abs(lam[order]))[None, :] * vec[:, order] / w[:, None]
+    v = u * np.sign(lam[order])[None, :]
+    u[0] = 0.0
+    v[0] = 0.0
+    u = u.astype(dtype).astype(np.float64)
+    v = v.astype(dtype).astype(np.float64)
+    return u, v, u @ v.T - F
 
 
-def eps_bound(q_hist: np.ndarray, err: np.ndarray) -> float:
-    """Rigorous bound on |approx - exact| for this query against ANY gallery row (count units)."""
-    return float(4.0 * err.max(axis=0)[q_hist.astype(np.int64)].sum())
+def eps_bound(q_hist: np.ndarray, E: np.ndarray) -> float:
+    """Rigorous bound on |S~ - S| for this query against ANY gallery row (S units; the distance moves by 4x as much)."""
+    return float(np.abs(E).max(axis=0)[q_hist.astype(np.int64)].sum())
 
 
-def approx_distances(gallery: np.ndarray, q_hist: np.ndarray, u: np.ndarray, v: np.ndarray) -> np.ndarray:
-    """sum g + sum q - 4 <U(g), V(q)> for every gallery row (float64 accumulation)."""
+def approx_scores(gallery: np.ndarray, q_hist: np.ndarray, u: np.ndarray, v: np.ndarray) -> np.ndarray:
+    """score~ = <U(g), V(q)> - (sum g) / 4 for every gallery row (float64 accumulation)."""
     G = gallery.astype(np.int64)
-    q = q_hist.astype(np.int64)
-    vq = v[q]                                             # [L, M]
-    dots = np.empty(G.shape[0])
-    for lo in range(0, G.shape[0], 256):                  # bounded temporaries
-        dots[lo:lo + 256] = np.einsum("nlm,lm->n", u[G[lo:lo + 256]], vq)
-    return G.sum(1) + q.sum() - 4.0 * dots
+    M = u @ v.T                                           # [a, b]
+    S = M[G, q_hist.astype(np.int64)[None, :]].sum(1)
+    return S - G.sum(1) / 4.0
 
 
 def exact_distances(gallery: np.ndarray, q_hist: np.ndarray) -> np.ndarray:
+    """sum_j (g_j - q_j)^2 / (g_j + q_j) in count units (OpenCV's CHISQR_ALT distance is 2 / cell_px times this)."""
     G = gallery.astype(np.int64)
     q = q_hist.astype(np.int64)
     s = G + q
     return np.where(s > 0, (G - q) ** 2 / np.maximum(s, 1), 0.0).sum(1)
 
 
-def filtered_nearest(gallery: np.ndarray, q_hist: np.ndarray, u, v, err):
+def filtered_nearest(gallery: np.ndarray, q_hist: np.ndarray, u, v, E, extra: float = 0.0):
     """(row, exact distance, survivors): nearest neighbour through the filter; equals the unfiltered answer."""
-    approx = approx_distances(gallery, q_hist, u, v)
-    eps = eps_bound(q_hist, err)
-    keep = np.flatnonzero(approx <= approx.min() + 2.0 * eps)
+    score = approx_scores(gallery, q_hist, u, v)
+    e = eps_bound(q_hist, E) + extra
+    keep = np.flatnonzero(score >= score.max() - 2.0 * e)
     d = exact_distances(gallery[keep], q_hist)
     j = int(np.argmin(d))                                 # first minimum: lowest row wins ties
     return int(keep[j]), float(d[j]), int(keep.size)

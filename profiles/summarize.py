@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT = os.path.join(ROOT, "profiles")
+OUT = os.environ.get("FRB_SUMMARY_OUT", os.path.join(ROOT, "profiles"))   # on the GPU box: gpurun_out/summ (only gpurun_out/ comes back)
 SRC = os.path.join(ROOT, "gpurun_out")
 KEYS = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",

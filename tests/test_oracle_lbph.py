@@ -147,29 +147,58 @@ def test_resize_restatement_is_bit_exact_with_the_installed_cv2():
         assert np.array_equal(OR.resize_linear_u8(full, *dsize), cv2.resize(full, dsize))
 
 
+def _library_filter_tables(px):
+    """frb_chisq_filter_tables: a HOST function of libfrb200 (no GPU needed) -> (u, v fp16 tables as float64, emax, absmax)."""
+    import ctypes
+    from facerecognition_b200 import _native as N
+    u = np.zeros((256, 8), np.uint16)
+    v = np.zeros((256, 8), np.uint16)
+    em = np.zeros(256, np.float32)
+    am = np.zeros(256, np.float32)
+    N.call("frb_chisq_filter_tables", px, *(x.ctypes.data_as(ctypes.c_void_p) for x in (u, v, em, am)))
+    return u.view(np.float16).astype(np.float64), v.view(np.float16).astype(np.float64), em, am
+
+
 def test_chisq_filter_statement_is_complete(oracle_lbph):
-    """oracle/chisq_filter.py (the planned tensor-core candidate filter, stated on the CPU): with fp16 rank-8 features the
-    rigorous bound holds for every (query, row) pair and the filtered nearest neighbour equals the exhaustive one —
-    for planted queries, unplanted ones and exact duplicates (lowest row wins)."""
+    """oracle/chisq_filter.py restates the tensor-core candidate filter of csrc/chisq_filter.cu on the CPU.  Checked here
+    without a GPU: (1) the LIBRARY's feature tables (host code: Jacobi eigen-decomposition) — its error bound emax
+    dominates the true error of its own fp16 tables against f(a, b) = ab/(a+b), computed in float64, for 100x100 and
+    112x112 faces; empty bins are exact; (2) the oracle's independent tables (numpy eigh) fit f as well; (3) with either
+    pair of tables the bound holds for every (query, row) pair and the filtered nearest neighbour equals the exhaustive
+    one — planted queries, unplanted ones, exact duplicates (lowest row wins) and rows of unequal mass."""
     from oracle import chisq_filter as CF
+    for px in (144, 169):
+        F = CF.f_table(px)
+        lu, lv, em, am = _library_filter_tables(px)
+        E_lib = lu[:px + 1] @ lv[:px + 1].T - F
+        assert np.all(em[:px + 1] >= np.abs(E_lib).max(0)), "emax must dominate the table error it is used to bound"
+        assert np.all(am[:px + 1] >= (np.abs(lu[:px + 1])[:, None, :] * np.abs(lv[:px + 1])[None, :, :]).sum(2).max(0) - 1e-6)
+        assert np.abs(E_lib[0]).max() == 0 and np.abs(E_lib[:, 0]).max() == 0 and not lu[px + 1:].any() and not lv[px + 1:].any()
+        u, v, E = CF.feature_tables(px)
+        assert np.abs(E).max() < 0.1 and np.abs(E_lib).max() < 0.1
+        # same construction, two eigen-solvers: the per-count bounds agree to fp16 rounding noise
+        assert abs(np.abs(E).max(0).sum() - np.abs(E_lib).max(0).sum()) <= 0.25 * np.abs(E).max(0).sum()
     rng = np.random.default_rng(12)
     faces = rng.integers(0, 256, (260, 100, 100), dtype=np.uint8)
     faces[:, 20:60] //= 3                                    # some structure: darker band
     hist, px = oracle_lbph.c_lbp_hist(faces)
     gallery, fresh = hist[:200].copy(), hist[200:]
     gallery[150] = gallery[7]                                # duplicate row
-    u, v, err = CF.feature_tables(px, 8, np.float16)
-    assert err.max() < 0.1 and err[0].max() == 0 and err[:, 0].max() == 0      # empty bins are exact
-    queries = [gallery[7], gallery[33]] + list(fresh[:10])
-    survivors = []
-    for q in queries:
-        exact = CF.exact_distances(gallery, q)
-        approx = CF.approx_distances(gallery, q, u, v)
-        assert np.abs(approx - exact).max() <= CF.eps_bound(q, err) + 1e-6
-        row, d, kept = CF.filtered_nearest(gallery, q, u, v, err)
-        assert row == int(np.argmin(exact)) and d == exact.min()
-        survivors.append(kept)
-    assert survivors[0] <= 3 and survivors[1] <= 3           # planted: the duplicate pair / the row itself survive
+    gallery[60, 4096:] = 0                                   # rows of unequal mass (not LBPH histograms any more)
+    gallery[61, :8192] //= 2
+    queries = [gallery[7], gallery[33], gallery[60]] + list(fresh[:10])
+    lu, lv, em, _ = _library_filter_tables(px)
+    for name, (u, v, E) in (("oracle", CF.feature_tables(px)), ("library", (lu[:px + 1], lv[:px + 1], lu[:px + 1] @ lv[:px + 1].T - CF.f_table(px)))):
+        survivors = []
+        for q in queries:
+            exact = CF.exact_distances(gallery, q)
+            score = CF.approx_scores(gallery, q, u, v)
+            exact_score = (q.astype(np.int64).sum() - exact) / 4.0                 # S - (sum g) / 4
+            assert np.abs(score - exact_score).max() <= CF.eps_bound(q, E) + 1e-6, name
+            row, d, kept = CF.filtered_nearest(gallery, q, u, v, E)
+            assert row == int(np.argmin(exact)) and d == exact.min(), name
+            survivors.append(kept)
+        assert survivors[0] <= 3 and survivors[1] <= 3 and survivors[2] <= 3    # planted: the duplicate pair / the row itself survive
     # the count-unit distance is the kernels' distance up to the 2 / cell_px scale
-    ref = oracle_lbph.c_chisq_scan_u16(gallery, px, queries[2], px)
-    np.testing.assert_allclose(CF.exact_distances(gallery, queries[2]) * (2.0 / px), ref, rtol=1e-6)   # the C oracle works on OpenCV's float32 view
+    ref = oracle_lbph.c_chisq_scan_u16(gallery, px, queries[3], px)
+    np.testing.assert_allclose(CF.exact_distances(gallery, queries[3]) * (2.0 / px), ref, rtol=1e-6)   # the C oracle works on OpenCV's float32 view
