@@ -13,7 +13,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libfrb200.so")
 
 FRB_OK, FRB_ERR_INVALID, FRB_ERR_UNSUPPORTED, FRB_ERR_CUDA, FRB_ERR_WORKSPACE = 0, -1, -2, -3, -4
-FRB_F32, FRB_BF16 = 0, 1
+FRB_F32, FRB_BF16, FRB_F16 = 0, 1, 2
 FRB_QNORM_NONE, FRB_QNORM_CLAMP, FRB_QNORM_EPS = 0, 1, 2
 FRB_SCORE_IP, FRB_SCORE_REF_COSINE = 0, 1
 FRB_MAX_K = 64
@@ -46,7 +46,7 @@ SIGNATURES = {
     "frb_cosine_topk_bf16q": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                                       c_size_t, c_void_p]),
     "frb_cosine_rescore_topk": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                                        c_int, c_int, c_float, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                        c_int, c_int, c_float, c_float, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "frb_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "frb_bgr2gray_u8": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "frb_resize_linear_u8": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -104,6 +104,8 @@ template <>
 __device__ __forceinline__ float cast_out<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 cast_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ __half cast_out<__half>(float v) { return __float2half_rn(v); }
 
 template <typename OutT>
 __global__ void __launch_bounds__(256) normalize_rows_kernel(const float *__restrict__ x, int64_t rows, int dim,
@@ -405,7 +407,7 @@ int normalize_rows_impl(const float *x, int64_t rows, int dim, int mode, void *o
 {
     FRB_CHECK_ARG(rows >= 0 && dim > 0, "frb_normalize_rows: rows=%lld dim=%d", (long long)rows, dim);
     FRB_CHECK_ARG(mode >= FRB_QNORM_NONE && mode <= FRB_QNORM_EPS, "frb_normalize_rows: mode=%d", mode);
-    FRB_CHECK_ARG(out_dtype == FRB_F32 || out_dtype == FRB_BF16, "frb_normalize_rows: out_dtype=%d", out_dtype);
+    FRB_CHECK_ARG(out_dtype == FRB_F32 || out_dtype == FRB_BF16 || out_dtype == FRB_F16, "frb_normalize_rows: out_dtype=%d", out_dtype);
     if (rows == 0) return FRB_OK;
     FRB_CHECK_ARG(x && out, "frb_normalize_rows: null pointer");
     int64_t blocks = (rows + 7) / 8;
@@ -413,6 +415,8 @@ int normalize_rows_impl(const float *x, int64_t rows, int dim, int mode, void *o
     if (grid < 1) grid = 1;
     if (out_dtype == FRB_F32)
         normalize_rows_kernel<float><<<grid, 256, 0, st>>>(x, rows, dim, mode, (float *)out, neg_inf_fill, zero_fill);
+    else if (out_dtype == FRB_F16)
+        normalize_rows_kernel<__half><<<grid, 256, 0, st>>>(x, rows, dim, mode, (__half *)out, neg_inf_fill, zero_fill);
     else
         normalize_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, rows, dim, mode, (__nv_bfloat16 *)out, neg_inf_fill, zero_fill);
     FRB_LAUNCH_OK("normalize_rows_kernel");

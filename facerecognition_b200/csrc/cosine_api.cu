@@ -14,7 +14,7 @@ int launch_cosine_simt(const float *queries, int64_t nq, const void *gallery, in
 size_t cosine_tc_workspace_bytes(int64_t n_query, int64_t n_gallery, int dim, int k);
 int launch_cosine_tc(const float *queries, const void *queries_bf16, int64_t nq, const void *gallery_bf16, int64_t ng, int dim,
                      int qnorm_mode, int k, int64_t idx_base, float *out_scores, int64_t *out_idx, void *ws, size_t ws_bytes,
-                     cudaStream_t st);
+                     cudaStream_t st, int op_dtype);
 
 bool gemv_applicable(int64_t n_query, int dim, int gallery_dtype);
 int64_t gemv_ctas(int64_t n_gallery, int64_t *rows_per_cta);
@@ -67,7 +67,7 @@ size_t frb_cosine_topk_workspace_bytes(int64_t n_query, int64_t n_gallery, int d
         GemvPlan p = gemv_plan(n_query, n_gallery, dim, k);
         return p.q_bytes + p.cnt_bytes + p.idx_bytes + p.score_bytes;
     }
-    if (gallery_dtype == FRB_BF16) return cosine_tc_workspace_bytes(n_query, n_gallery, dim, k);
+    if (gallery_dtype == FRB_BF16 || gallery_dtype == FRB_F16) return cosine_tc_workspace_bytes(n_query, n_gallery, dim, k);
     SimtPlan p = simt_plan(n_query, n_gallery, dim, k, true);
     return p.qn_bytes + p.idx_bytes + p.score_bytes;
 }
@@ -81,7 +81,8 @@ int frb_cosine_topk(const float *queries, int64_t n_query, const void *gallery, 
                   (long long)n_gallery);
     FRB_CHECK_ARG(dim > 0 && (dim % 8) == 0, "frb_cosine_topk: dim=%d must be a positive multiple of 8", dim);
     FRB_CHECK_ARG(k >= 1 && k <= FRB_MAX_K, "frb_cosine_topk: k=%d (1..%d)", k, FRB_MAX_K);
-    FRB_CHECK_ARG(gallery_dtype == FRB_F32 || gallery_dtype == FRB_BF16, "frb_cosine_topk: gallery_dtype=%d", gallery_dtype);
+    FRB_CHECK_ARG(gallery_dtype == FRB_F32 || gallery_dtype == FRB_BF16 || gallery_dtype == FRB_F16, "frb_cosine_topk: gallery_dtype=%d",
+                  gallery_dtype);
     FRB_CHECK_ARG(score_mode == FRB_SCORE_IP || score_mode == FRB_SCORE_REF_COSINE, "frb_cosine_topk: score_mode=%d",
                   score_mode);
     FRB_CHECK_ARG(qnorm_mode >= FRB_QNORM_NONE && qnorm_mode <= FRB_QNORM_EPS, "frb_cosine_topk: qnorm_mode=%d", qnorm_mode);
@@ -100,8 +101,8 @@ int frb_cosine_topk(const float *queries, int64_t n_query, const void *gallery, 
         return FRB_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (gallery_dtype == FRB_BF16 && score_mode != FRB_SCORE_IP) {
-        set_error("frb_cosine_topk: bf16 galleries hold pre-normalised rows; only FRB_SCORE_IP is implemented");
+    if (gallery_dtype != FRB_F32 && score_mode != FRB_SCORE_IP) {
+        set_error("frb_cosine_topk: bf16 / fp16 galleries hold pre-normalised rows; only FRB_SCORE_IP is implemented");
         return FRB_ERR_UNSUPPORTED;
     }
 
@@ -128,9 +129,9 @@ int frb_cosine_topk(const float *queries, int64_t n_query, const void *gallery, 
         return topk_merge_compact(cs, ci, cnt, p.ctas * k, n_query, k, /*largest=*/1, out_scores, out_idx, st);
     }
 
-    if (gallery_dtype == FRB_BF16) {
+    if (gallery_dtype == FRB_BF16 || gallery_dtype == FRB_F16) {
         return launch_cosine_tc(queries, nullptr, n_query, gallery, n_gallery, dim, qnorm_mode, k, idx_base, out_scores, out_idx,
-                                workspace, workspace_bytes, st);
+                                workspace, workspace_bytes, st, gallery_dtype);
     }
 
     SimtPlan p = simt_plan(n_query, n_gallery, dim, k, true);
@@ -180,7 +181,7 @@ int frb_cosine_topk_bf16q(const void *queries_bf16, int64_t n_query, const void 
         return topk_merge_compact(cs, ci, cnt, p.ctas * k, n_query, k, /*largest=*/1, out_scores, out_idx, st);
     }
     return launch_cosine_tc(nullptr, queries_bf16, n_query, gallery_bf16, n_gallery, dim, FRB_QNORM_NONE, k, idx_base, out_scores, out_idx,
-                            workspace, workspace_bytes, st);
+                            workspace, workspace_bytes, st, FRB_BF16);
 }
 
 }  // extern "C"

@@ -198,7 +198,7 @@ cosine_gemv_kernel(const GT *__restrict__ queries, const GT *__restrict__ galler
 // FFMA-tiled path, so fp32 batches up to 16 queries run here as passes of 4.
 bool gemv_applicable(int64_t n_query, int dim, int gallery_dtype)
 {
-    if (n_query < 1 || dim % 256 != 0 || dim > 32 * kGvMaxPerLane) return false;
+    if (n_query < 1 || dim % 256 != 0 || dim > 32 * kGvMaxPerLane || gallery_dtype == FRB_F16) return false;
     return n_query <= (gallery_dtype == FRB_BF16 ? 2 : 16);
 }
 

@@ -1,15 +1,16 @@
 // cosine_refine.cu — exact fp32 answers at tensor-core speed: re-score a short candidate list.
 //
-// For fp32 galleries the 1e-5 bar rules out bf16 operands, but not a bf16 FIRST PASS: the tcgen05 kernel ranks the
-// gallery on a unit-norm bf16 copy and returns kp > k candidates per query; this kernel then computes the EXACT fp32
-// score of those kp rows under the reference's rule (cosine_similarity()'s three branches,
+// For fp32 galleries the 1e-5 bar rules out 16-bit operands, but not a 16-bit FIRST PASS: the tcgen05 kernel ranks the
+// gallery on a unit-norm fp16 (or bf16) copy and returns kp > k candidates per query; this kernel then computes the
+// EXACT fp32 score of those kp rows under the reference's rule (cosine_similarity()'s three branches,
 // inference/recognition_engine.py:52-63, or an inner product), keeps the best k (ties -> lowest row) and PROVES
-// completeness: every row outside the list has a first-pass score <= a_min (the list's smallest), hence an exact
-// score <= a_min + eps, where eps bounds |exact - first pass| (bf16 keeps 8 significant bits, so rounding two unit
-// vectors moves their inner product by at most 2 * 2^-8 + 2^-16 by Cauchy-Schwarz; cosine_similarity()'s raw-dot
-// branch adds at most 2e-3).  If a_min + eps < the k-th exact score no outside row can enter or tie; otherwise the
-// query is counted in *fail_count and the caller reruns the exact kernel.  One CTA per query: warps take
-// candidates round-robin, lanes split the dot product.
+// completeness: every row outside the list has a first-pass score <= a_min (the list's smallest), hence a true
+// cosine <= x = a_min + eps_abs (fp16 keeps 11 significant bits: rounding two unit vectors moves their inner product
+// by at most 2 * 2^-11 by Cauchy-Schwarz, + subnormal tails + fp32 accumulation = 1.1e-3; bf16: 8.0e-3), hence a
+// reference score <= x + eps_rel |x| + 1e-6 (cosine_similarity()'s raw-dot branch returns cos * |q| |g| with both norms
+// within 1e-3 of 1: eps_rel = 2.001e-3).  If that is below the k-th exact score no outside row can enter or tie;
+// otherwise the query is counted in *fail_count (and flagged) and the caller reruns the exact kernel for it.  One CTA
+// per query: warps take candidates round-robin, lanes split the dot product.
 #include "frb_common.cuh"
 
 namespace frb {
@@ -26,8 +27,9 @@ __device__ __forceinline__ float rf_ref_cosine(float dot, float na, float nb)
 __global__ void __launch_bounds__(kRfThreads)
 cosine_rescore_kernel(const float *__restrict__ queries, const float *__restrict__ gallery, int dim, const float *__restrict__ q_norms,
                       const float *__restrict__ g_norms, int score_mode, const int64_t *__restrict__ cand_idx,
-                      const float *__restrict__ cand_approx, int kp, int k, float eps, int64_t n_gallery, int64_t idx_base,
-                      float *__restrict__ out_scores, int64_t *__restrict__ out_idx, int *__restrict__ fail_count)
+                      const float *__restrict__ cand_approx, int kp, int k, float eps, float eps_rel, int64_t n_gallery,
+                      int64_t idx_base, float *__restrict__ out_scores, int64_t *__restrict__ out_idx, int *__restrict__ fail_count,
+                      int *__restrict__ fail_flags)
 {
     __shared__ float s_exact[FRB_MAX_K];
     const int64_t q = blockIdx.x;
@@ -85,7 +87,10 @@ cosine_rescore_kernel(const float *__restrict__ queries, const float *__restrict
     // complete when the list holds the whole gallery, or no outside row can reach the k-th exact score
     const bool whole = valid >= n_gallery;
     const float kth = id[k - 1] >= 0 ? s[k - 1] : -INFINITY;
-    if (!whole && !(a_min + eps < kth)) atomicAdd(fail_count, 1);
+    const float x = a_min + eps;
+    const bool fail = !whole && !(x + eps_rel * fabsf(x) + 1e-6f < kth);
+    if (fail) atomicAdd(fail_count, 1);
+    if (fail_flags) fail_flags[q] = fail ? 1 : 0;
 }
 
 }  // namespace frb
@@ -94,13 +99,14 @@ using namespace frb;
 
 extern "C" int frb_cosine_rescore_topk(const float *queries, int64_t n_query, const float *gallery, int64_t n_gallery, int dim,
                                        const float *q_norms, const float *g_norms, int score_mode, const int64_t *cand_idx,
-                                       const float *cand_approx, int kp, int k, float eps, int64_t idx_base, float *out_scores,
-                                       int64_t *out_idx, int *fail_count, void *stream)
+                                       const float *cand_approx, int kp, int k, float eps, float eps_rel, int64_t idx_base,
+                                       float *out_scores, int64_t *out_idx, int *fail_count, int *fail_flags, void *stream)
 {
     FRB_CHECK_ARG(n_query >= 0 && n_gallery >= 0 && dim > 0 && dim % 4 == 0, "frb_cosine_rescore_topk: n_query=%lld n_gallery=%lld dim=%d",
                   (long long)n_query, (long long)n_gallery, dim);
     FRB_CHECK_ARG(k >= 1 && kp >= k && kp <= FRB_MAX_K, "frb_cosine_rescore_topk: k=%d kp=%d (k <= kp <= %d)", k, kp, FRB_MAX_K);
     FRB_CHECK_ARG(score_mode == FRB_SCORE_IP || score_mode == FRB_SCORE_REF_COSINE, "frb_cosine_rescore_topk: score_mode=%d", score_mode);
+    FRB_CHECK_ARG(eps >= 0.f && eps_rel >= 0.f, "frb_cosine_rescore_topk: eps_abs=%g eps_rel=%g", (double)eps, (double)eps_rel);
     if (n_query == 0) return FRB_OK;
     FRB_CHECK_ARG(queries && cand_idx && cand_approx && out_scores && out_idx && fail_count && (gallery || n_gallery == 0),
                   "frb_cosine_rescore_topk: null pointer");
@@ -108,8 +114,8 @@ extern "C" int frb_cosine_rescore_topk(const float *queries, int64_t n_query, co
                   "frb_cosine_rescore_topk: FRB_SCORE_REF_COSINE needs q_norms and g_norms");
     FRB_CHECK_ARG(n_query <= 2147483647LL, "frb_cosine_rescore_topk: n_query too large");
     cosine_rescore_kernel<<<(unsigned)n_query, kRfThreads, 0, (cudaStream_t)stream>>>(queries, gallery, dim, q_norms, g_norms, score_mode,
-                                                                                     cand_idx, cand_approx, kp, k, eps, n_gallery, idx_base,
-                                                                                     out_scores, out_idx, fail_count);
+                                                                                     cand_idx, cand_approx, kp, k, eps, eps_rel, n_gallery,
+                                                                                     idx_base, out_scores, out_idx, fail_count, fail_flags);
     FRB_LAUNCH_OK("cosine_rescore_kernel");
     return FRB_OK;
 }

@@ -55,8 +55,9 @@ struct TcBarriers {
     uint32_t tmem_base;
 };
 
-// kind::f16 instruction descriptor: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), both K-major, N>>3 at 17, M>>4 at 24
-constexpr uint32_t kTcIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcBlockN >> 3) << 17) | ((uint32_t)(kTcBlockM >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32 (1<<4), A and B bf16 (1<<7, 1<<10) or fp16 (format 0), both K-major, N>>3 at 17, M>>4 at 24
+constexpr uint32_t kTcIdescF16 = (1u << 4) | ((uint32_t)(kTcBlockN >> 3) << 17) | ((uint32_t)(kTcBlockM >> 4) << 24);
+constexpr uint32_t kTcIdescBf16 = kTcIdescF16 | (1u << 7) | (1u << 10);
 
 
 // ---- register-resident best-k list, RK = 8 / 16 / 32 / 64 slots (k <= RK; 8 covers the common top-1 / top-5) ---
@@ -171,6 +172,7 @@ __device__ __forceinline__ float ld_relaxed_f32(const float *addr)
 struct TcParams {
     int64_t n_query, n_gallery;
     int k_blocks;          // dim / 64
+    uint32_t idesc;        // UMMA instruction descriptor: bf16 or fp16 operands
     int stages;            // B ring depth
     int64_t n_qtiles, tiles_per_group, n_groups;  // units of THIS launch = n_qtiles * n_groups
     int64_t tile_begin, tile_end;                 // gallery tiles [tile_begin, tile_end) are scanned by this launch
@@ -294,7 +296,7 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
                         for (int k4 = 0; k4 < kTcBlockK / kTcUmmaK; k4++) {
                             // advance 16 elements (32 B) along K inside the 128-byte swizzle row: +2 in 16-byte units
-                            umma_bf16(tmem_d, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), kTcIdesc, (kb | k4) != 0 ? 1u : 0u);
+                            umma_bf16(tmem_d, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), p.idesc, (kb | k4) != 0 ? 1u : 0u);
                         }
                         tcgen05_commit(&bars->empty[stage]);  // stage reusable once these MMAs retire
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -482,7 +484,8 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 // ---- host side ---------------------------------------------------------------------------------
 // row-major bf16 [rows, dim] -> boxes of (64 of K) x box_rows rows, 128-byte swizzled, zero fill out of bounds
 static int make_bf16_map(CUtensorMap *map, const void *base, int64_t rows, int dim, int box_rows, int box_cols = kTcBlockK,
-                         CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B)
+                         CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B,
+                         CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)
 {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) {
@@ -493,7 +496,7 @@ static int make_bf16_map(CUtensorMap *map, const void *base, int64_t rows, int d
     cuuint64_t strides[1] = {(cuuint64_t)dim * 2};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+    CUresult r = enc(map, dtype, 2, const_cast<void *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -640,10 +643,12 @@ __global__ void __launch_bounds__(256) tc_reset_kernel(float *__restrict__ thr, 
 // queries: fp32 rows that the prologue normalises (qnorm_mode) and rounds to bf16 — or, when queries_bf16 is given, rows
 // that are ALREADY normalised bf16 (e.g. all-gathered from the ranks that normalised their own slice of the batch): the
 // TMA reads them in place and no prologue runs.
+// op_dtype: FRB_BF16 or FRB_F16 — the 16-bit format of the gallery and of the (normalised) queries.
 int launch_cosine_tc(const float *queries, const void *queries_bf16, int64_t nq, const void *gallery_bf16, int64_t ng, int dim,
                      int qnorm_mode, int k, int64_t idx_base, float *out_scores, int64_t *out_idx, void *ws, size_t ws_bytes,
-                     cudaStream_t st)
+                     cudaStream_t st, int op_dtype)
 {
+    const CUtensorMapDataType tm_dtype = op_dtype == FRB_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     (void)ws_bytes;
     if (dim % kTcBlockK != 0 || dim / kTcBlockK > kTcMaxKBlocks) {
         set_error("bf16 tensor-core path: dim=%d must be a multiple of 64 and <= 512", dim);
@@ -673,26 +678,27 @@ int launch_cosine_tc(const float *queries, const void *queries_bf16, int64_t nq,
         tc_reset_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(thr, cnt, nq);
         FRB_LAUNCH_OK("tc_reset_kernel");
     } else {
-        rc = normalize_rows_impl(queries, nq, dim, qnorm_mode, qb, FRB_BF16, thr, cnt, st);
+        rc = normalize_rows_impl(queries, nq, dim, qnorm_mode, qb, op_dtype, thr, cnt, st);
         if (rc != FRB_OK) return rc;
     }
     if (pl.share_bytes) FRB_CUDA_OK(cudaMemsetAsync(share, 0xFF, pl.share_bytes, st));   // 0xFFFFFFFF = not published
 
     CUtensorMap tq, tg, tpf;
-    rc = make_bf16_map(&tq, qb, nq, dim, kTcBlockM);
+    rc = make_bf16_map(&tq, qb, nq, dim, kTcBlockM, kTcBlockK, CU_TENSOR_MAP_SWIZZLE_128B, tm_dtype);
     if (rc != FRB_OK) return rc;
-    rc = make_bf16_map(&tg, ng > 0 ? gallery_bf16 : (const void *)qb, ng, dim, kTcBlockN);
+    rc = make_bf16_map(&tg, ng > 0 ? gallery_bf16 : (const void *)qb, ng, dim, kTcBlockN, kTcBlockK, CU_TENSOR_MAP_SWIZZLE_128B, tm_dtype);
     if (rc != FRB_OK) return rc;
 
     // prefetch view of the gallery: unswizzled boxes of (up to) 256 of K x 256 rows, L2 only
     rc = make_bf16_map(&tpf, ng > 0 ? gallery_bf16 : (const void *)qb, ng, dim, kTcBlockN, dim < 256 ? dim : 256,
-                       CU_TENSOR_MAP_SWIZZLE_NONE);
+                       CU_TENSOR_MAP_SWIZZLE_NONE, tm_dtype);
     if (rc != FRB_OK) return rc;
 
     TcParams p;
     p.n_query = nq;
     p.n_gallery = ng;
     p.k_blocks = dim / kTcBlockK;
+    p.idesc = op_dtype == FRB_F16 ? kTcIdescF16 : kTcIdescBf16;
     const size_t a_bytes = (size_t)p.k_blocks * kTcABytesPerKb;
     int stages = (int)((kTcSmemLimit - 1024 - sizeof(TcBarriers) - a_bytes) / kTcBBytesPerStage);
     if (stages > kTcMaxStages) stages = kTcMaxStages;

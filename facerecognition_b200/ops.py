@@ -40,6 +40,9 @@ def _stream(dev: torch.device):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+_FRB_DTYPE = {torch.float32: N.FRB_F32, torch.bfloat16: N.FRB_BF16, torch.float16: N.FRB_F16}
+
+
 def row_norms(x: torch.Tensor) -> torch.Tensor:
     """frb_row_norms_f32: fp32 [R, D] -> fp32 [R] L2 norms."""
     dev = _require_cuda(x)
@@ -57,14 +60,13 @@ def normalize_rows(x: torch.Tensor, mode: int = N.FRB_QNORM_EPS, out_dtype: torc
     dev = _require_cuda(x, out)
     assert x.dtype == torch.float32 and x.dim() == 2
     if out is None:
-        assert out_dtype in (torch.float32, torch.bfloat16)
+        assert out_dtype in _FRB_DTYPE
         out = torch.empty(x.shape, dtype=out_dtype, device=dev)
     else:
-        assert out.shape == x.shape and out.dtype in (torch.float32, torch.bfloat16)
+        assert out.shape == x.shape and out.dtype in _FRB_DTYPE
         out_dtype = out.dtype
     with torch.cuda.device(dev):
-        N.call("frb_normalize_rows", _p(x), _I64(x.shape[0]), x.shape[1], mode, _p(out),
-               N.FRB_F32 if out_dtype == torch.float32 else N.FRB_BF16, _stream(dev))
+        N.call("frb_normalize_rows", _p(x), _I64(x.shape[0]), x.shape[1], mode, _p(out), _FRB_DTYPE[out_dtype], _stream(dev))
     return out
 
 
@@ -72,13 +74,13 @@ def cosine_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, *, score_m
                 qnorm_mode: int = N.FRB_QNORM_NONE, q_norms: Optional[torch.Tensor] = None,
                 g_norms: Optional[torch.Tensor] = None, idx_base: int = 0,
                 out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """frb_cosine_topk: fp32 queries [Q, D] x fp32|bf16 gallery [N, D] -> (scores fp32 [Q, k], idx int64 [Q, k])."""
+    """frb_cosine_topk: fp32 queries [Q, D] x fp32|bf16|fp16 gallery [N, D] -> (scores fp32 [Q, k], idx int64 [Q, k])."""
     dev = _require_cuda(queries, gallery, q_norms, g_norms)
     assert queries.dtype == torch.float32 and queries.dim() == 2 and gallery.dim() == 2
-    assert gallery.dtype in (torch.float32, torch.bfloat16)
+    assert gallery.dtype in _FRB_DTYPE
     assert gallery.shape[0] == 0 or gallery.shape[1] == queries.shape[1]
     q, d, n = queries.shape[0], queries.shape[1], gallery.shape[0]
-    gdt = N.FRB_F32 if gallery.dtype == torch.float32 else N.FRB_BF16
+    gdt = _FRB_DTYPE[gallery.dtype]
     if out is None:
         scores = torch.empty((q, k), dtype=torch.float32, device=dev)
         idx = torch.empty((q, k), dtype=torch.int64, device=dev)
@@ -116,48 +118,83 @@ def cosine_topk_bf16q(queries_bf16: torch.Tensor, gallery_bf16: torch.Tensor, k:
     return scores, idx
 
 
-# >= |exact score - bf16 first-pass score| for ANY pair: bf16 keeps 8 significant bits (unit roundoff 2^-8), so rounding
-# two unit vectors moves their inner product by at most 2 * 2^-8 + 2^-16 = 0.00783 (Cauchy-Schwarz), and
-# cosine_similarity()'s raw-dot branch (both norms within 1e-3 of 1) differs from the true cosine by at most 0.002
-REFINE_EPS = 0.0105
-# measured (profiles/run_refine.py, 1M fp32 rows): 4096 queries 5.5 ms vs 132 ms for the fp32 tiled kernel, 256 queries
-# 4.1 ms vs 7.7 ms (a 64-slot list warms up in every (query tile, gallery group) unit, which small batches have many of)
-REFINE_MIN_QUERIES = 256
-REFINE_MIN_ROWS = 65536
+# Exact fp32 top-k through the tensor cores: a 16-bit first pass proposes kp candidates per query, frb_cosine_rescore_topk
+# re-scores them in fp32 under the reference's rule and proves every list complete (see include/frb200.h).
+#   eps_abs >= |true cosine - first-pass score| for ANY pair of unit vectors rounded to the first-pass format: fp16 keeps
+#   11 significant bits, so 2 * 2^-11 (Cauchy-Schwarz) + subnormal tails (512 * 2 * 2^-25) + fp32 accumulation (6e-5) <
+#   1.1e-3; bf16 (8 bits): 2 * 2^-8 + ... < 8.0e-3.
+#   eps_rel >= |reference score - true cosine| / |cosine|: cosine_similarity()'s raw-dot branch returns cos * |q| |g| with
+#   both norms within 1e-3 of 1 (inference/recognition_engine.py:57-58), i.e. at most 2.001e-3; 0 for inner products.
+REFINE_EPS_F16 = 1.1e-3
+REFINE_EPS_BF16 = 8.0e-3
+REFINE_EPS_REL = 2.001e-3
+# measured on B200 (profiles/r2_refine.txt): from 8 queries x 16k rows up the first pass + re-score beats the fp32 kernels
+REFINE_MIN_QUERIES = 8
+REFINE_MIN_ROWS = 16384
 
 
 def refine_min_queries(k: int) -> int:
-    """Smallest batch that takes the tensor-core first pass + exact re-score instead of the fp32 tiled kernel."""
+    """Smallest batch that takes the tensor-core first pass + exact re-score instead of the fp32 kernels."""
     return REFINE_MIN_QUERIES
 
 
+def refine_applicable(n_query: int, n_rows: int, dim: int, k: int) -> bool:
+    """Shapes where ops.cosine_topk_exact beats the fp32 kernels (profiles/r2_refine.txt): any batch of >= 8 queries over
+    >= 16k rows (2-40x), and batches of >= 512 over galleries as small as 4k rows (4096 x 10k: 0.21 vs 1.64 ms)."""
+    if not refine_list_length(k) or dim % 64 != 0 or dim > 512 or n_query < REFINE_MIN_QUERIES:
+        return False
+    return n_rows >= REFINE_MIN_ROWS or (n_rows >= 4096 and n_query >= 512)
+
+
 def refine_list_length(k: int) -> int:
-    """Candidates fetched by the first pass for a final top-k (0: k too large for a provable margin)."""
-    return N.FRB_MAX_K if k <= 16 else 0   # the longest list the kernels keep: the widest provable margin
+    """Candidates fetched by the first pass for a final top-k (0: k too large for a provable margin).  With fp16's
+    1.1e-3 bound a 16-slot list proves the reference's top-5 for all but a few in a thousand queries (those are re-run
+    exactly); longer results get the longest list the kernels keep."""
+    return 16 if k <= 5 else (N.FRB_MAX_K if k <= 16 else 0)
 
 
-def cosine_topk_refined(queries: torch.Tensor, gallery: torch.Tensor, gallery_bf16_unit: torch.Tensor, k: int, *,
+def cosine_topk_refined(queries: torch.Tensor, gallery: torch.Tensor, gallery_unit16: torch.Tensor, k: int, *,
                         score_mode: int = N.FRB_SCORE_REF_COSINE, q_norms: Optional[torch.Tensor] = None,
                         g_norms: Optional[torch.Tensor] = None, idx_base: int = 0
-                        ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """Exact fp32 top-k through the tensor cores, for the reference's cosine rule (FRB_SCORE_REF_COSINE; or inner
-    products of unit-norm queries against unit-norm gallery rows, which rank like the cosine): bf16 first pass
-    (frb_cosine_topk on `gallery_bf16_unit`, the unit-norm bf16 copy of `gallery`) -> frb_cosine_rescore_topk.
-    Returns (scores, idx, fail_count int32 [1]); when fail_count != 0 some list could not be proven complete and the
-    caller must use `cosine_topk` on the fp32 gallery."""
-    dev = _require_cuda(queries, gallery, gallery_bf16_unit, q_norms, g_norms)
+                        ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """First pass (frb_cosine_topk on `gallery_unit16`, the unit-norm fp16 or bf16 copy of `gallery`) ->
+    frb_cosine_rescore_topk.  For the reference's cosine rule (FRB_SCORE_REF_COSINE), or inner products of unit-norm
+    queries against unit-norm rows (which rank like the cosine).  Returns (scores, idx, fail_count int32 [1],
+    fail_flags int32 [Q]): flagged queries could not be proven complete and must be answered by `cosine_topk` on the
+    fp32 gallery (`cosine_topk_exact` does that)."""
+    dev = _require_cuda(queries, gallery, gallery_unit16, q_norms, g_norms)
     kp = refine_list_length(k)
-    assert kp > 0 and gallery.dtype == torch.float32 and gallery_bf16_unit.dtype == torch.bfloat16
-    assert gallery.shape == gallery_bf16_unit.shape
+    assert kp > 0 and gallery.dtype == torch.float32 and gallery_unit16.dtype in (torch.bfloat16, torch.float16)
+    assert gallery.shape == gallery_unit16.shape
     q, d, n = queries.shape[0], queries.shape[1], gallery.shape[0]
-    approx, cand = cosine_topk(queries, gallery_bf16_unit, kp, qnorm_mode=N.FRB_QNORM_CLAMP)
+    approx, cand = cosine_topk(queries, gallery_unit16, kp, qnorm_mode=N.FRB_QNORM_CLAMP)
     scores = torch.empty((q, k), dtype=torch.float32, device=dev)
     idx = torch.empty((q, k), dtype=torch.int64, device=dev)
     fail = torch.zeros(1, dtype=torch.int32, device=dev)
+    flags = torch.empty(q, dtype=torch.int32, device=dev)
+    eps = REFINE_EPS_F16 if gallery_unit16.dtype == torch.float16 else REFINE_EPS_BF16
+    eps_rel = REFINE_EPS_REL if score_mode == N.FRB_SCORE_REF_COSINE else 0.0
     with torch.cuda.device(dev):
         N.call("frb_cosine_rescore_topk", _p(queries), _I64(q), _p(gallery), _I64(n), d, _p(q_norms), _p(g_norms), score_mode,
-               _p(cand), _p(approx), kp, k, ctypes.c_float(REFINE_EPS), _I64(idx_base), _p(scores), _p(idx), _p(fail), _stream(dev))
-    return scores, idx, fail
+               _p(cand), _p(approx), kp, k, ctypes.c_float(eps), ctypes.c_float(eps_rel), _I64(idx_base), _p(scores), _p(idx),
+               _p(fail), _p(flags), _stream(dev))
+    return scores, idx, fail, flags
+
+
+def cosine_topk_exact(queries: torch.Tensor, gallery: torch.Tensor, gallery_unit16: torch.Tensor, k: int, *,
+                      q_norms: torch.Tensor, g_norms: torch.Tensor, idx_base: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The reference's exact fp32 top-k (cosine_similarity() rule, ties -> lowest row) at tensor-core speed:
+    cosine_topk_refined, then the fp32 kernels for exactly the queries whose candidate list could not be proven
+    complete (one host read of the failure count; the index plumbing of the re-run is torch gather / scatter)."""
+    s, i, fail, flags = cosine_topk_refined(queries, gallery, gallery_unit16, k, score_mode=N.FRB_SCORE_REF_COSINE,
+                                            q_norms=q_norms, g_norms=g_norms, idx_base=idx_base)
+    if int(fail.item()):
+        rows = torch.nonzero(flags).flatten()
+        s2, i2 = cosine_topk(queries.index_select(0, rows).contiguous(), gallery, k, score_mode=N.FRB_SCORE_REF_COSINE,
+                             q_norms=q_norms.index_select(0, rows).contiguous(), g_norms=g_norms, idx_base=idx_base)
+        s.index_copy_(0, rows, s2)
+        i.index_copy_(0, rows, i2)
+    return s, i
 
 
 def topk_merge(cand_scores: torch.Tensor, cand_idx: torch.Tensor, largest: bool) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -131,13 +131,13 @@ class DeviceGallery:
         self.rows = _pad8(_to_dev(mat, device))               # [n, pad8(dim)]
         self.norms = ops.row_norms(self.rows) if len(mine) else torch.zeros(0, device=device)
         self._unit_rows = None
-        self._unit_bf16 = None
+        self._unit_f16 = None
 
-    def unit_rows_bf16(self) -> torch.Tensor:
-        """Unit-norm bf16 copy of the rows: the tensor-core first pass of ops.cosine_topk_refined."""
-        if self._unit_bf16 is None:
-            self._unit_bf16 = ops.normalize_rows(self.rows, N.FRB_QNORM_CLAMP, torch.bfloat16)
-        return self._unit_bf16
+    def unit_rows_f16(self) -> torch.Tensor:
+        """Unit-norm fp16 copy of the rows: the tensor-core first pass of ops.cosine_topk_exact."""
+        if self._unit_f16 is None:
+            self._unit_f16 = ops.normalize_rows(self.rows, N.FRB_QNORM_CLAMP, torch.float16)
+        return self._unit_f16
 
     def unit_rows(self) -> torch.Tensor:
         """rows / (||row|| + 1e-8) — web_app.py:549 normalises every db row this way."""
@@ -364,14 +364,10 @@ class RecognitionEngine:
         g = self.gallery()
         qn = ops.row_norms(q)
         n_local, pdim = g.rows.shape[0], g.rows.shape[1]
-        if (q.shape[0] >= ops.refine_min_queries(k) and n_local >= ops.REFINE_MIN_ROWS and ops.refine_list_length(k)
-                and pdim % 64 == 0 and pdim <= 512):
-            # batches against large galleries: bf16 tensor-core first pass + exact fp32 re-score of the candidates,
-            # each list proven complete; any query without a provable margin sends the batch to the exact kernel
-            s, i, fail = ops.cosine_topk_refined(q, g.rows, g.unit_rows_bf16(), k, score_mode=N.FRB_SCORE_REF_COSINE,
-                                                 q_norms=qn, g_norms=g.norms, idx_base=g.lo)
-            if int(fail.cpu().item()) == 0:
-                return s, i
+        if ops.refine_applicable(q.shape[0], n_local, pdim, k):
+            # batches: fp16 tensor-core first pass + exact fp32 re-score of the candidates, each list proven complete;
+            # the few queries without a provable margin are re-run on the fp32 kernels
+            return ops.cosine_topk_exact(q, g.rows, g.unit_rows_f16(), k, q_norms=qn, g_norms=g.norms, idx_base=g.lo)
         return ops.cosine_topk(q, g.rows, k, score_mode=N.FRB_SCORE_REF_COSINE, q_norms=qn, g_norms=g.norms, idx_base=g.lo)
 
     def recognize_embeddings_device(self, embeddings, k: int = 5) -> Tuple[torch.Tensor, torch.Tensor]:

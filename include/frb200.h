@@ -40,7 +40,7 @@ typedef enum frb_status {
     FRB_ERR_WORKSPACE = -4    /* workspace missing or too small                               */
 } frb_status;
 
-typedef enum frb_dtype { FRB_F32 = 0, FRB_BF16 = 1 } frb_dtype;
+typedef enum frb_dtype { FRB_F32 = 0, FRB_BF16 = 1, FRB_F16 = 2 } frb_dtype;
 
 /* How a query row x is scaled before the dot product. */
 typedef enum frb_qnorm {
@@ -95,7 +95,7 @@ int frb_profile_read(int kernel, float *total_ms, int *launches);
 int frb_row_norms_f32(const float *x_dev, int64_t rows, int dim, float *out_norms_dev, void *stream);
 
 /* Row-wise L2 normalisation with the reference's two conventions, writing fp32 or bf16.
- * mode = FRB_QNORM_CLAMP | FRB_QNORM_EPS (NONE = plain cast).  Replaces
+ * (out_dtype FRB_F32, FRB_BF16 or FRB_F16).  mode = FRB_QNORM_CLAMP | FRB_QNORM_EPS (NONE = plain cast).  Replaces
  * extract_embeddings.py:622-623 (index rows), web_app.py:549 (db rows), :540 (query). */
 int frb_normalize_rows(const float *x_dev, int64_t rows, int dim, int mode, void *out_dev, int out_dtype,
                        void *stream);
@@ -109,6 +109,9 @@ size_t frb_cosine_topk_workspace_bytes(int64_t n_query, int64_t n_gallery, int d
  *   gallery_dtype FRB_F32 : exact fp32 FFMA kernel (<=1e-5 of the reference's numpy scores).
  *   gallery_dtype FRB_BF16: tcgen05 tensor-core kernel (queries normalised in fp32, rounded to
  *                           bf16 in the prologue; fp32 accumulate in TMEM; <=1e-3).
+ *   gallery_dtype FRB_F16 : the same kernel on fp16 operands (11 significant bits: a unit-norm row pair's inner product
+ *                           moves by <= 1.1e-3 worst case, ~1e-5 typically) — the first pass of the exact-fp32 path,
+ *                           see frb_cosine_rescore_topk.
  *   q_norms_dev / g_norms_dev : fp32 row norms, required for FRB_SCORE_REF_COSINE, else NULL.
  *   out_scores_dev [n_query, k] fp32 descending; out_idx_dev [n_query, k] int64 (idx_base + row);
  *   slots beyond n_gallery hold (-inf, -1) like faiss.
@@ -129,19 +132,24 @@ int frb_cosine_topk_bf16q(const void *queries_bf16_dev, int64_t n_query, const v
                           void *workspace_dev, size_t workspace_bytes, void *stream);
 
 /* Exact fp32 top-k from a tensor-core first pass.  cand_idx / cand_approx [n_query, kp] are the (local row, score) lists
- * frb_cosine_topk returned for a unit-norm bf16 copy of the gallery with kp > k.  Each listed row is re-scored in fp32
- * under score_mode (queries as that rule takes them: normalised rows for FRB_SCORE_IP, raw rows + norms for
- * FRB_SCORE_REF_COSINE), the best k are written (ties -> lowest row, ids + idx_base), and *fail_count_dev is
- * incremented for every query whose list could not be PROVEN complete: min first-pass score + eps must be below the
- * k-th exact score, eps >= the worst |exact - first pass| (0.0105 covers two bf16 roundings of unit vectors,
- * 2 * 2^-8, and cosine_similarity()'s raw-dot branch, 0.002).  A caller that reads a non-zero count reruns
- * frb_cosine_topk on the fp32 gallery.  Same result as recognize_with_db / np.dot + argsort
- * (inference/recognition_engine.py:277-289, notebooks/evaluate_arcface_kaggle.ipynb:618,713), reached through tcgen05. */
+ * frb_cosine_topk returned for a unit-norm fp16 (or bf16) copy of the gallery with kp > k.  Each listed row is re-scored
+ * in fp32 under score_mode (queries as that rule takes them: normalised rows for FRB_SCORE_IP, raw rows + norms for
+ * FRB_SCORE_REF_COSINE), the best k are written (ties -> lowest row, ids + idx_base), and the query FAILS if its list
+ * cannot be PROVEN complete.  Proof: a row outside the list has a first-pass score <= a_min (the list's smallest), hence
+ * an exact score <= x + eps_rel * |x| + 1e-6 with x = a_min + eps_abs; that must be below the k-th exact score.
+ *   eps_abs >= the worst |true cosine - first-pass score|: 1.1e-3 for fp16 unit vectors (2 * 2^-11 by Cauchy-Schwarz,
+ *              subnormal tails and the fp32 accumulation included), 8.0e-3 for bf16;
+ *   eps_rel >= the worst relative gap between the reference's score and the true cosine: 2.001e-3 for
+ *              cosine_similarity()'s raw-dot branch (both norms within 1e-3 of 1), 0 for FRB_SCORE_IP on unit rows.
+ * *fail_count_dev is incremented per failing query and, if fail_flags_dev (int32 [n_query], may be NULL) is given, the
+ * query's flag is set to 1 (0 otherwise): the caller reruns frb_cosine_topk on the fp32 gallery for exactly those
+ * queries.  Same result as recognize_with_db / np.dot + argsort (inference/recognition_engine.py:277-289,
+ * notebooks/evaluate_arcface_kaggle.ipynb:618,713), reached through tcgen05. */
 int frb_cosine_rescore_topk(const float *queries_dev, int64_t n_query, const float *gallery_f32_dev, int64_t n_gallery,
                             int dim, const float *q_norms_dev, const float *g_norms_dev, int score_mode,
-                            const int64_t *cand_idx_dev, const float *cand_approx_dev, int kp, int k, float eps,
-                            int64_t idx_base, float *out_scores_dev, int64_t *out_idx_dev, int *fail_count_dev,
-                            void *stream);
+                            const int64_t *cand_idx_dev, const float *cand_approx_dev, int kp, int k, float eps_abs,
+                            float eps_rel, int64_t idx_base, float *out_scores_dev, int64_t *out_idx_dev,
+                            int *fail_count_dev, int *fail_flags_dev, void *stream);
 
 /* Gallery builder (K4): out[g] = mean(emb[order[offsets[g] .. offsets[g+1])]) / (||mean|| + 1e-8), float32 sums in
  * the given order then a division by the count (numpy's mean(axis=0)); groups with no rows come out all-zero.
