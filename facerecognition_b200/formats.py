@@ -78,18 +78,34 @@ def write_faiss_flat_ip(path: str, rows: np.ndarray) -> None:
 # ---- OpenCV LBPH model ------------------------------------------------------------------------------
 
 
-def _infer_cell_px(h: np.ndarray) -> int:
-    """A stored float histogram row is count * float32(1/n) per cell; each cell sums to 1.  Recover n."""
+def _fits_cell_px(h: np.ndarray, n: int) -> bool:
+    """True when every value of the stored row is an integer count over n pixels and each 256-bin cell holds exactly n."""
+    c = h.astype(np.float64) * n
+    r = np.round(c)
+    if np.any(np.abs(c - r) > 1e-6 * np.maximum(r, 1.0)):        # float32(count) * float32(1/n): relative error ~2e-7
+        return False
+    cells = r.reshape(-1, 256).sum(1) if h.shape[0] % 256 == 0 else np.array([r.sum()])
+    return bool(np.all(cells == n)) or h.shape[0] % 256 != 0
+
+
+def _infer_cell_px(h: np.ndarray, hint: int = 0) -> int:
+    """A stored float histogram row is count * float32(1/n) per cell and each cell's counts sum to n: recover n.  The
+    smallest non-zero value is c_min / n for an unknown integer c_min, so n = round(c / v_min) is tried for c = 1, 2, ...
+    against the STRUCTURE (all values integral over n, every cell summing to n) — not against a list of multiples of
+    round(1 / v_min), which misses rows whose smallest count does not divide n (e.g. 5 of 144)."""
+    if hint and _fits_cell_px(h, hint):
+        return hint
     nz = h[h > 0]
     if nz.size == 0:
         raise ValueError("cannot infer the cell size of an all-zero histogram")
-    base = int(round(1.0 / float(nz.min())))
-    for mult in range(1, 65):
-        n = base * mult
-        c = h.astype(np.float64) * n
-        if np.max(np.abs(c - np.round(c))) < 1e-2:
+    vmin = float(nz.min())
+    for c in range(1, 65536):
+        n = int(round(c / vmin))
+        if n > 65535:
+            break
+        if n >= 1 and _fits_cell_px(h, n):
             return n
-    raise ValueError("histogram values are not multiples of 1/cell_px; not an OpenCV LBPH histogram")
+    raise ValueError("histogram values are not integer counts over a common cell size; not an OpenCV LBPH histogram")
 
 
 def write_lbph_model(model, filename: str) -> None:
@@ -156,10 +172,12 @@ def read_lbph_model(model, filename: str) -> None:
         return
     L = model.hist_len
     by_px: Dict[int, list] = {}
+    last_px = 0
     for i, h in enumerate(hists):
         if h.shape[0] != L:
             raise model_error(f"{filename}: histogram {i} has {h.shape[0]} bins, expected {L}")
-        by_px.setdefault(_infer_cell_px(h), []).append(i)
+        last_px = _infer_cell_px(h, last_px)              # rows of one model nearly always share a cell size: try it first
+        by_px.setdefault(last_px, []).append(i)
     from .lbph import _Group
     for px, rows in by_px.items():
         counts = np.round(np.stack([hists[i] for i in rows]).astype(np.float64) * px).astype(np.uint16)

@@ -244,3 +244,23 @@ def test_threshold_sweep_matches_the_real_reference():
         assert a.keys() == b.keys()
         for k in a:
             assert a[k] == pytest.approx(b[k], abs=1e-12), k
+
+
+def test_lbph_cell_size_inference_from_stored_float_rows():
+    """formats._infer_cell_px: a row whose smallest count does not divide the cell size (5 of 144) must still be read
+    (round-1 advisor finding); a reading is valid when it reproduces the stored floats as integer counts per cell."""
+    from facerecognition_b200.formats import _infer_cell_px
+    rng = np.random.default_rng(0)
+    for px in (144, 169, 16, 1, 2401, 7):
+        for trial in range(6):
+            counts = rng.multinomial(px, rng.dirichlet(np.ones(256) * rng.choice([0.05, 1, 10])), size=64).astype(np.float32)
+            if trial == 0 and px >= 7:
+                counts[:] = 0
+                counts[:, 0], counts[:, 1] = 5, px - 5
+            h = (counts * np.float32(1.0 / px)).reshape(-1)
+            got = _infer_cell_px(h)
+            assert got == px, (px, got, trial)
+    with pytest.raises(ValueError):
+        _infer_cell_px(np.full(16384, 0.3, np.float32))
+    with pytest.raises(ValueError):
+        _infer_cell_px(np.zeros(16384, np.float32))

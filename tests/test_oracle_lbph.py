@@ -202,3 +202,22 @@ def test_chisq_filter_statement_is_complete(oracle_lbph):
     # the count-unit distance is the kernels' distance up to the 2 / cell_px scale
     ref = oracle_lbph.c_chisq_scan_u16(gallery, px, queries[3], px)
     np.testing.assert_allclose(CF.exact_distances(gallery, queries[3]) * (2.0 / px), ref, rtol=1e-6)   # the C oracle works on OpenCV's float32 view
+
+
+def test_third_party_pins():
+    """tests/golden/verify_with_contrib.py under pytest: pins the LBP histogram stage on the real cv2.face and the FAISS
+    file layout / search order on the real faiss wherever those modules are installed; skipped (stages stay "parity
+    unpinned") where they are not — as in the authoring image and on the GPU box."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("verify_with_contrib", os.path.join(os.path.dirname(__file__), "golden", "verify_with_contrib.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ran = []
+    if mod.have_cv2_face():
+        ran += mod.check_lbph_against_contrib()
+    if mod.have_faiss():
+        ran += mod.check_faiss_against_real()
+    if not ran:
+        pytest.skip("neither cv2.face (opencv-contrib-python) nor faiss is installed")
+    assert all(ok for _, ok, _ in ran), [r for r in ran if not r[1]]
