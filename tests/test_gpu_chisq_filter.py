@@ -163,3 +163,25 @@ def test_rows_with_unequal_totals_and_arbitrary_counts():
     assert torch.equal(i, want_i) and torch.equal(d.view(torch.int32), want_d.view(torch.int32))
     assert int(stats[3]) == 0 and float(d[:10].abs().max()) == 0.0
     print(f"\n[filter] unequal totals: fallback {int(stats[0])}, survivors/query {int(stats[1]) / nq:.1f}")
+
+
+def test_configs4_share_at_full_shape_is_identical_to_the_exact_scan():
+    """BASELINE configs[4] as one GPU of eight sees it: 1024 frames against 125 000 gallery histograms, the bench's own data
+    recipe (bench.c5_gallery / c5_step).  The filter's answers must equal the exact scan's bit for bit, with no fallback
+    and no audited row outside the bound."""
+    import bench
+    from facerecognition_b200 import ops
+    g8, px = bench.c5_gallery(torch, ops, torch.device("cuda"), 0, 125_000)
+    frames = torch.cat([faces_gpu(256, 112, 41), bench.blocky_faces(torch, 768, 112, torch.device("cuda"), 31337)], 0)
+    chunk0 = bench.blocky_faces(torch, bench.C5_CHUNK, 112, torch.device("cuda"), 500)
+    frames[:128] = chunk0[1000:1128]                                    # exact re-shots: distance 0 at rows 1000..1127
+    qh, qpx = hists(frames)
+    assert qpx == px and g8.dtype == torch.uint8 and g8.shape == (125_000, 16384)
+    stats = torch.zeros(4, dtype=torch.int32, device="cuda")
+    d, i = ops.chisq_top1_filtered(qh, g8, px, stats=stats)
+    want_d, want_i = exact_top1(qh, g8, px)
+    assert torch.equal(i, want_i) and torch.equal(d.view(torch.int32), want_d.view(torch.int32))
+    assert i[:128, 0].tolist() == list(range(1000, 1128)) and float(d[:128].abs().max()) == 0.0
+    st = stats.cpu().tolist()
+    assert st[0] == 0 and st[3] == 0
+    print(f"\n[filter] configs[4] share: survivors/query {st[1] / 1024:.1f}, raw candidates/query {st[2] / 1024:.1f}")
