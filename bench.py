@@ -315,10 +315,10 @@ def lbph_leg(torch, ops, NV, device, peaks, flush):
     ops.FILTER_ENABLED = False
     try:
         for _ in range(2):
-            d, i = ops.chisq_topk(qh, px, gal16, px, 1)
+            d, i = ops.chisq_topk(qh, px, gal8, px, 1)
         NV.profile_read(NV.K_CHISQ)
         for _ in range(3):
-            d, i = ops.chisq_topk(qh, px, gal16, px, 1)
+            d, i = ops.chisq_topk(qh, px, gal8, px, 1)
         ms, n = NV.profile_read(NV.K_CHISQ)
     finally:
         ops.FILTER_ENABLED = saved
@@ -326,12 +326,12 @@ def lbph_leg(torch, ops, NV, device, peaks, flush):
     pairs = n_gal * n_q
     tf = pairs * 65536 / (per * 1e-3) / 1e12
     out["match_exact_batched"] = {"pairs_per_s": pairs / (per * 1e-3), "predicts_per_s_at_100k_gallery": n_q / (per * 1e-3),
-                                  "ms_per_launch": per, "queries": n_q, "gallery_rows": n_gal,
+                                  "ms_per_launch": per, "queries": n_q, "gallery_rows": n_gal, "gallery": "u8 counts (the form LBPHFaceRecognizer keeps)",
                                   "roofline": {"bound": "fp32", "achieved": tf, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
                                                "frac": tf / FP32_PEAK_TFLOPS, **ncu_traffic("chisq_kernel"),
                                                "note": "SURVEY §8d: 65536 flop per (query, row) pair against the measured FP32 peak "
                                                        "(72 TFLOP/s, profiles/micro/fp32_peak.cu); the gallery chunk is shared through L2, "
-                                                       "so DRAM traffic (`traffic`) is a small fraction of pairs x 32 KiB and HBM is not the bound"}}
+                                                       "so DRAM traffic (`traffic`) is a small fraction of pairs x 16 KiB and HBM is not the bound"}}
     # front end: interleaved BGR video crops -> gray (3 B read + 1 B written per pixel)
     n_fr = 32768
     bgr = torch.randint(0, 256, (n_fr, 112, 112, 3), generator=gen, device=device, dtype=torch.uint8)
@@ -421,7 +421,8 @@ def c5_step(torch, ops, NV, device, peaks, rows, lo, search_factory, reps=3):
                        "audit_violations": st[3]} if search is None else None,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"],
                          "frac_of_sustained": tf / peaks["bf16_tflops_sustained"], "kernel": "chisq_filter_kernel",
-                         "ms_in_kernel": kms / max(kn, 1), "traffic": (ncu_traffic("chisq_filter_kernel")["traffic"] if rows == 125_000 else None),
+                         "ms_in_kernel": kms / max(kn, 1), "traffic": None,
+                         "traffic_note": "ncu capture at 256 queries x 37888 rows (profiles/r2_prof_filter_r2.txt): 0.69 GB read for 0.62 GB of gallery + 0.07 GB of query features",
                          "note": "algorithmic flops = 2 x frames x rows x 16384 bins x 8 fp16 features (the rank-8 feature GEMM that "
                                  "decides every pair; exact re-score of the few survivors and K2 are inside ms_per_step); peak = "
                                  "the measured cuBLAS bf16 figure (fp16 runs at the same tensor rate)"}}

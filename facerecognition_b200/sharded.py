@@ -293,12 +293,14 @@ class HostBatchPipeline:
         with torch.cuda.stream(self.copy_in):
             self.copy_in.wait_event(self.searched[slot])        # the search that last read this staging buffer is done
             (stage if self.bf16_gather else stage[self.q0:self.q1]).copy_(q_host, non_blocking=True)
+            if self.bf16_gather:
+                # still on the ingest stream, so it overlaps the search of the previous batch: normalise my slice -> bf16,
+                # ONE all-gather of bf16 rows (every rank issues its collectives in submission order on this stream)
+                q16 = self.sharded.gather_normalized(stage, self.stage16[slot], self.q0)
             self.h2d_done[slot].record(self.copy_in)
         main.wait_event(self.h2d_done[slot])
         if self.bf16_gather:
-            # normalise my slice -> bf16, ONE all-gather of bf16 rows, tensor-core search on the gathered batch
-            q16 = self.sharded.gather_normalized(stage, self.stage16[slot], self.q0)
-            s, i = self.sharded.search(q16, self.k, graph=self.graph)
+            s, i = self.sharded.search(q16, self.k, graph=self.graph)   # tensor-core search on the gathered batch
         else:
             if not self.whole:
                 dist.all_gather_into_tensor(stage, stage[self.q0:self.q1], group=self.group)
