@@ -708,6 +708,7 @@ def main():
             strong = {"value": q_per_gpu * args.steps / (ms_s * 1e-3), "unit": "queries/s", "ms_per_step": ms_s / args.steps,
                       "queries_per_step": q_per_gpu, "note": "same 1M gallery, batch NOT grown: total work fixed"}
 
+    exchange_kind = search._exchange is not None
     okt = torch.tensor([1 if ok else 0], device=device)
     if world > 1:
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
@@ -747,8 +748,9 @@ def main():
     if strong:
         line["strong"] = strong
     if world > 1:
-        line["config"]["exchange"] = ("one fused kernel over NVLink peer memory (frb_exchange_topk_merge: peer stores + flags + merge)"
-                                      if search._exchange is not None else "one NCCL all-gather of packed records + frb_topk_merge_strided")
+        # (kept out of `config`, which must read the same in the reference arm)
+        line["exchange"] = ("one fused kernel over NVLink peer memory (frb_exchange_topk_merge: peer stores + flags + merge)"
+                            if exchange_kind else "one NCCL all-gather of packed records + frb_topk_merge_strided")
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # bounded CPU sample: 256-query chunks of the same batch against the full gallery until ~12 s

@@ -496,12 +496,106 @@ using namespace frb;
 static int check_lbp_args(const char *fn, int64_t count, int rows, int cols, int radius, int neighbors)
 {
     FRB_CHECK_ARG(count >= 0, "%s: count=%lld", fn, (long long)count);
-    if (radius != 1 || neighbors != 8) {
-        set_error("%s: only radius=1, neighbors=8 is implemented (got %d, %d)", fn, radius, neighbors);
+    if (radius < 1 || radius > 32 || neighbors < 1 || neighbors > 8) {
+        set_error("%s: radius 1..32 and neighbors 1..8 are implemented (got %d, %d); more than 8 neighbours would need "
+                  "histograms longer than the 16384 bins the chi-square kernels keep in registers", fn, radius, neighbors);
         return FRB_ERR_UNSUPPORTED;
     }
-    FRB_CHECK_ARG(rows >= 3 && cols >= 3, "%s: image %dx%d is smaller than the 3x3 LBP window", fn, rows, cols);
+    FRB_CHECK_ARG(rows >= 2 * radius + 1 && cols >= 2 * radius + 1, "%s: image %dx%d is smaller than the %dx%d LBP window", fn, rows,
+                  cols, 2 * radius + 1, 2 * radius + 1);
     return FRB_OK;
+}
+
+// ---- any (radius, neighbors): the general elbp_ of lbph_faces.cpp ----------------------------------------------------
+// The reference exposes both as options (models/lbphmodel/train_lbph_script.py:353-363, configs/lbph_config.yaml); only
+// its defaults (1, 8) are on the hot path and have the tuned kernels above.  Everything else takes these plain kernels:
+// same arithmetic as OpenCV — sample point n at (x, y) = (r cos(2 pi n / P), -r sin(2 pi n / P)) in float, bilinear
+// weights w1..w4 in float, t = w1 a + w2 b + w3 c + w4 d with every product and sum rounded to float32 left to right,
+// bit n = (t > centre) || |t - centre| < FLT_EPSILON.
+struct LbpTaps {
+    int fx[8], fy[8], cx[8], cy[8];
+    float w1[8], w2[8], w3[8], w4[8];
+};
+
+static LbpTaps make_taps(int radius, int neighbors)
+{
+    LbpTaps t;
+    for (int n = 0; n < 8; n++) {
+        t.fx[n] = t.fy[n] = t.cx[n] = t.cy[n] = 0;
+        t.w1[n] = t.w2[n] = t.w3[n] = t.w4[n] = 0.f;
+    }
+    for (int n = 0; n < neighbors; n++) {
+        const float x = (float)(radius * cos(2.0 * 3.1415926535897932384626433832795 * n / (float)neighbors));
+        const float y = (float)(-radius * sin(2.0 * 3.1415926535897932384626433832795 * n / (float)neighbors));
+        const int fx = (int)floor(x), fy = (int)floor(y), cx = (int)ceil(x), cy = (int)ceil(y);
+        volatile float ty = y - fy, tx = x - fx;             // volatile: every step rounded to float32, as OpenCV's build does
+        volatile float omx = 1 - tx, omy = 1 - ty;
+        t.fx[n] = fx; t.fy[n] = fy; t.cx[n] = cx; t.cy[n] = cy;
+        volatile float a = omx * omy, b = tx * omy, c = omx * ty, d = tx * ty;
+        t.w1[n] = a; t.w2[n] = b; t.w3[n] = c; t.w4[n] = d;
+    }
+    return t;
+}
+
+__device__ __forceinline__ unsigned lbp_code_generic(const uint8_t *__restrict__ img, int cols, int y, int x, int neighbors,
+                                                     const LbpTaps &tp)
+{
+    const float c = (float)img[y * cols + x];
+    unsigned code = 0;
+    for (int n = 0; n < neighbors; n++) {
+        const float a = (float)img[(y + tp.fy[n]) * cols + (x + tp.fx[n])], b = (float)img[(y + tp.fy[n]) * cols + (x + tp.cx[n])];
+        const float cc = (float)img[(y + tp.cy[n]) * cols + (x + tp.fx[n])], d = (float)img[(y + tp.cy[n]) * cols + (x + tp.cx[n])];
+        float t = __fmul_rn(tp.w1[n], a);
+        t = __fadd_rn(t, __fmul_rn(tp.w2[n], b));
+        t = __fadd_rn(t, __fmul_rn(tp.w3[n], cc));
+        t = __fadd_rn(t, __fmul_rn(tp.w4[n], d));
+        const bool bit = (t > c) || (fabsf(__fsub_rn(t, c)) < 1.1920928955078125e-07f);
+        code |= bit ? (1u << n) : 0u;
+    }
+    return code;
+}
+
+__global__ void __launch_bounds__(256) lbp_codes_generic_kernel(const uint8_t *__restrict__ img, int64_t count, int rows, int cols,
+                                                                int radius, int neighbors, const __grid_constant__ LbpTaps tp,
+                                                                uint8_t *__restrict__ out)
+{
+    const int orows = rows - 2 * radius, ocols = cols - 2 * radius;
+    const int64_t per = (int64_t)orows * ocols, total = count * per;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = t / per;
+        const int r = (int)(t - b * per), y = r / ocols, x = r - y * ocols;
+        out[t] = (uint8_t)lbp_code_generic(img + b * rows * cols, cols, y + radius, x + radius, neighbors, tp);
+    }
+}
+
+// one CTA per image at a time; u32 counters [cells][2^P] in shared memory; OUT8 as above
+template <bool OUT8>
+__global__ void __launch_bounds__(256) lbp_hist_generic_kernel(const uint8_t *__restrict__ img, int64_t count, int rows, int cols,
+                                                               int radius, int neighbors, int grid_x, int grid_y,
+                                                               const __grid_constant__ LbpTaps tp, void *__restrict__ out_v)
+{
+    extern __shared__ unsigned lbp_gen_hist[];
+    const int orows = rows - 2 * radius, ocols = cols - 2 * radius;
+    const int cw = ocols / grid_x, ch = orows / grid_y, bins = 1 << neighbors, n_ctr = grid_x * grid_y * bins;
+    const int used = cw * grid_x * ch * grid_y;
+    for (int64_t b = blockIdx.x; b < count; b += gridDim.x) {
+        for (int i = threadIdx.x; i < n_ctr; i += blockDim.x) lbp_gen_hist[i] = 0;
+        __syncthreads();
+        const uint8_t *im = img + b * rows * cols;
+        for (int i = threadIdx.x; i < used; i += blockDim.x) {
+            const int y = i / (cw * grid_x), x = i - y * (cw * grid_x);
+            const unsigned code = lbp_code_generic(im, cols, y + radius, x + radius, neighbors, tp);
+            atomicAdd(&lbp_gen_hist[((y / ch) * grid_x + x / cw) * bins + code], 1u);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_ctr; i += blockDim.x) {
+            if (OUT8)
+                reinterpret_cast<uint8_t *>(out_v)[b * n_ctr + i] = (uint8_t)lbp_gen_hist[i];
+            else
+                reinterpret_cast<uint16_t *>(out_v)[b * n_ctr + i] = (uint16_t)lbp_gen_hist[i];
+        }
+        __syncthreads();
+    }
 }
 
 // OUT8: u8 counts (cells of <= 255 pixels) instead of u16
@@ -512,7 +606,7 @@ static int lbp_hist_impl(const uint8_t *images, int64_t count, int rows, int col
     int rc = check_lbp_args("frb_lbp_hist_u8", count, rows, cols, radius, neighbors);
     if (rc != FRB_OK) return rc;
     FRB_CHECK_ARG(grid_x >= 1 && grid_y >= 1, "frb_lbp_hist_u8: grid %dx%d", grid_x, grid_y);
-    const int cw = (cols - 2) / grid_x, ch = (rows - 2) / grid_y;
+    const int cw = (cols - 2 * radius) / grid_x, ch = (rows - 2 * radius) / grid_y;
     if (out_cell_px) *out_cell_px = cw * ch;
     if (cw * ch > (OUT8 ? 255 : 65535)) {
         set_error("frb_lbp_hist_u8: %d pixels per cell overflow the %s counters", cw * ch, OUT8 ? "u8" : "u16");
@@ -520,6 +614,22 @@ static int lbp_hist_impl(const uint8_t *images, int64_t count, int rows, int col
     }
     if (count == 0) return FRB_OK;
     FRB_CHECK_ARG(images && out_hist, "frb_lbp_hist_u8: null pointer");
+    if (radius != 1 || neighbors != 8) {
+        const size_t ctr_bytes = (size_t)grid_x * grid_y * ((size_t)1 << neighbors) * sizeof(unsigned);
+        if (ctr_bytes > 200 * 1024) {
+            set_error("frb_lbp_hist_u8: grid %dx%d with %d neighbours needs %zu B of counters (> 200 KB)", grid_x, grid_y, neighbors, ctr_bytes);
+            return FRB_ERR_UNSUPPORTED;
+        }
+        FRB_CUDA_OK(cudaFuncSetAttribute(lbp_hist_generic_kernel<OUT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctr_bytes));
+        const LbpTaps tp = make_taps(radius, neighbors);
+        const int64_t cap = (int64_t)sm_count() * 2;
+        const int grid = (int)(count < cap ? count : cap);
+        ProfileScope prof(FRB_K_LBP_HIST, (cudaStream_t)stream);
+        lbp_hist_generic_kernel<OUT8><<<grid, 256, ctr_bytes, (cudaStream_t)stream>>>(images, count, rows, cols, radius, neighbors, grid_x,
+                                                                                        grid_y, tp, out_hist);
+        FRB_LAUNCH_OK("lbp_hist_generic_kernel");
+        return FRB_OK;
+    }
     // +16: the right-most column pair reads up to 2 bytes past the image (zeroed, never used in a code it emits)
     const int img_smem = (int)align_up((size_t)rows * cols, 16) + 16;
     // counters: one u32 per (cell pair, bin), pairs = ceil(grid_y / 2) * grid_x, plus one scratch pair
@@ -597,10 +707,17 @@ int frb_lbp_codes_u8(const uint8_t *images, int64_t count, int rows, int cols, i
     if (rc != FRB_OK) return rc;
     if (count == 0) return FRB_OK;
     FRB_CHECK_ARG(images && out_codes, "frb_lbp_codes_u8: null pointer");
-    int64_t total = count * (int64_t)(rows - 2) * (cols - 2);
+    int64_t total = count * (int64_t)(rows - 2 * radius) * (cols - 2 * radius);
+    if (total == 0) return FRB_OK;
     int64_t blocks = (total + 255) / 256;
     int64_t cap = (int64_t)sm_count() * 16;
     int grid = (int)(blocks < cap ? blocks : cap);
+    if (radius != 1 || neighbors != 8) {
+        const LbpTaps tp = make_taps(radius, neighbors);
+        lbp_codes_generic_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(images, count, rows, cols, radius, neighbors, tp, out_codes);
+        FRB_LAUNCH_OK("lbp_codes_generic_kernel");
+        return FRB_OK;
+    }
     lbp_codes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(images, count, rows, cols, out_codes);
     FRB_LAUNCH_OK("lbp_codes_kernel");
     return FRB_OK;

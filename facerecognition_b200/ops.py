@@ -343,19 +343,20 @@ def exchange_emulate(ranks: Sequence["Exchange"], scores: torch.Tensor, idx: tor
 
 
 def lbp_codes(images: torch.Tensor, radius: int = 1, neighbors: int = 8) -> torch.Tensor:
-    """frb_lbp_codes_u8: u8 [B, H, W] -> u8 [B, H-2, W-2] LBP codes (OpenCV elbp_ semantics)."""
+    """frb_lbp_codes_u8: u8 [B, H, W] -> u8 [B, H-2r, W-2r] LBP codes (OpenCV elbp_ semantics; radius 1 / 8 neighbours
+    take the tuned kernel, other settings with up to 8 neighbours the general one)."""
     dev = _require_cuda(images)
     assert images.dtype == torch.uint8 and images.dim() == 3
     b, h, w = images.shape
-    out = torch.empty((b, max(h - 2, 0), max(w - 2, 0)), dtype=torch.uint8, device=dev)
+    out = torch.empty((b, max(h - 2 * radius, 0), max(w - 2 * radius, 0)), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         N.call("frb_lbp_codes_u8", _p(images), _I64(b), h, w, radius, neighbors, _p(out), _stream(dev))
     return out
 
 
-def lbp_cell_px(rows: int, cols: int, grid_x: int = 8, grid_y: int = 8) -> int:
-    """Pixels per LBP grid cell (OpenCV spatial_histogram: floor((cols-2)/grid_x) x floor((rows-2)/grid_y))."""
-    return max((cols - 2) // grid_x, 0) * max((rows - 2) // grid_y, 0)
+def lbp_cell_px(rows: int, cols: int, grid_x: int = 8, grid_y: int = 8, radius: int = 1) -> int:
+    """Pixels per LBP grid cell (OpenCV spatial_histogram: floor((cols-2r)/grid_x) x floor((rows-2r)/grid_y))."""
+    return max((cols - 2 * radius) // grid_x, 0) * max((rows - 2 * radius) // grid_y, 0)
 
 
 def lbp_hist(images: torch.Tensor, radius: int = 1, neighbors: int = 8, grid_x: int = 8, grid_y: int = 8,
@@ -366,8 +367,8 @@ def lbp_hist(images: torch.Tensor, radius: int = 1, neighbors: int = 8, grid_x: 
     dev = _require_cuda(images)
     assert images.dtype == torch.uint8 and images.dim() == 3
     b, h, w = images.shape
-    as8 = counts8 and lbp_cell_px(h, w, grid_x, grid_y) <= 255
-    out = torch.empty((b, grid_x * grid_y * 256), dtype=torch.uint8 if as8 else torch.uint16, device=dev)
+    as8 = counts8 and lbp_cell_px(h, w, grid_x, grid_y, radius) <= 255
+    out = torch.empty((b, grid_x * grid_y * (1 << neighbors)), dtype=torch.uint8 if as8 else torch.uint16, device=dev)
     cell_px = ctypes.c_int(0)
     with torch.cuda.device(dev):
         N.call("frb_lbp_hist_u8_counts8" if as8 else "frb_lbp_hist_u8", _p(images), _I64(b), h, w, radius, neighbors, grid_x,

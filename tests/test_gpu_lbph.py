@@ -446,3 +446,37 @@ def test_mixed_size_gallery_and_web_ui_mapping(oracle_lbph):
     far = rng.integers(0, 256, (100, 100), dtype=np.uint8)
     r = F.recognize_face_web(model, far, threshold=1.0)
     assert r["identity"] == "Unknown" and r["confidence"] == F.web_confidence(r["distance"])
+
+
+@pytest.mark.parametrize("radius,neighbors,shape,grid", [(2, 8, (100, 100), 8), (1, 4, (64, 80), 4), (3, 6, (90, 70), 5),
+                                                          (2, 3, (50, 50), 8), (1, 8, (100, 100), 8)])
+def test_other_radius_and_neighbor_settings(oracle_lbph, radius, neighbors, shape, grid):
+    """The reference exposes radius / neighbors as options (models/lbphmodel/train_lbph_script.py:353-363); settings other
+    than its defaults (1, 8) take the general kernels: codes and histograms bit-exact against the oracle's elbp_,
+    predict() == the oracle's (label, distance)."""
+    import facerecognition_b200 as F
+    from facerecognition_b200 import ops
+    rng = np.random.default_rng(radius * 100 + neighbors)
+    faces = rng.integers(0, 256, (14,) + shape, dtype=np.uint8)
+    faces[2] = 77                                                          # flat image
+    faces[3, :, ::2] = 255
+    want, wpx = oracle_lbph.c_lbp_hist(faces, radius, neighbors, grid, grid)
+    dev_faces = torch.from_numpy(faces).cuda()
+    got, px = ops.lbp_hist(dev_faces, radius, neighbors, grid, grid)
+    assert px == wpx and got.shape == want.shape and np.array_equal(got.cpu().numpy(), want)
+    got8, _ = ops.lbp_hist(dev_faces, radius, neighbors, grid, grid, counts8=True)
+    assert np.array_equal(got8.cpu().numpy().astype(np.uint16), want)
+    codes = ops.lbp_codes(dev_faces[:2].contiguous(), radius, neighbors).cpu().numpy()
+    for j in range(2):
+        ref = np.zeros((shape[0] - 2 * radius, shape[1] - 2 * radius), np.int32)
+        oracle_lbph.lib().frb_oracle_elbp(oracle_lbph._p(np.ascontiguousarray(faces[j])), shape[0], shape[1], radius, neighbors, oracle_lbph._p(ref))
+        assert np.array_equal(codes[j], ref)
+    if (grid * grid * (1 << neighbors)) % 16 == 0:
+        labels = np.arange(14, dtype=np.int32) * 3
+        model = F.train_lbph_model(list(faces[:10]), labels[:10], radius=radius, neighbors=neighbors, grid_x=grid, grid_y=grid)
+        ref_model = oracle_lbph.OracleLBPH(radius, neighbors, grid, grid)
+        ref_model.train(list(faces[:10]), labels[:10])
+        for f in faces[8:14]:
+            lab, dist = model.predict(f)
+            rlab, rdist = ref_model.predict(f)
+            assert lab == rlab and abs(dist - rdist) <= 1e-5 * max(rdist, 1e-30), (lab, dist, rlab, rdist)
