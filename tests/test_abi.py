@@ -31,8 +31,12 @@ def test_version_and_argument_errors():
     # invalid arguments are rejected before anything touches the device
     assert N.lib.frb_topk_merge(None, None, 1, 4, 0, 1, None, None, None) == N.FRB_ERR_INVALID
     assert "k=0" in N.last_error()
-    assert N.lib.frb_lbp_hist_u8(None, 1, 100, 100, 2, 8, 8, 8, None, None, None) == N.FRB_ERR_UNSUPPORTED
-    assert "radius=1" in N.last_error()
+    assert N.lib.frb_lbp_hist_u8(None, 1, 100, 100, 2, 9, 8, 8, None, None, None) == N.FRB_ERR_UNSUPPORTED   # > 8 neighbours
+    assert "neighbors 1..8" in N.last_error()
+    assert N.lib.frb_lbp_hist_u8_counts8(None, 1, 600, 600, 1, 8, 8, 8, None, None, None) == N.FRB_ERR_UNSUPPORTED  # cells > 255 px
+    assert N.lib.frb_chisq_top1_filtered_g8(None, 1, None, 1, 100, 144, 0, None, None, None, None, None, 0, None) == N.FRB_ERR_INVALID
+    assert N.lib.frb_chisq_top1_filtered_g8(None, 1, None, 1, 16384, 300, 0, None, None, None, None, None, 0, None) == N.FRB_ERR_INVALID
+    assert N.lib.frb_cosine_rescore_topk(None, 1, None, 1, 512, None, None, 0, None, None, 4, 5, 0.0, 0.0, 0, None, None, None, None, None) == N.FRB_ERR_INVALID
     assert N.lib.frb_lbp_hist_u8(None, 1, 2, 100, 1, 8, 8, 8, None, None, None) == N.FRB_ERR_INVALID
     assert N.lib.frb_chisq_topk(None, 1, 144, None, 1, 100, 144, 1, 0, None, None, None, 0, None) == N.FRB_ERR_INVALID
     assert N.lib.frb_cosine_topk(None, 1, None, 0, 1, 100, None, None, 0, 0, 1, 0, None, None, None, 0, None) == N.FRB_ERR_INVALID
