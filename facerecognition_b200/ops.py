@@ -399,9 +399,10 @@ def index_remap(idx: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
 
 
 # Batches at least this large against galleries at least this long go through the tensor-core candidate filter
-# (frb_chisq_top1_filtered_g8): same answers as the exact scan, ~10x the pairs per second (profiles/r2_*).  Below these
-# sizes a unit of the filter kernel (256 queries x 256 rows x the whole histogram) cannot fill the GPU.
-FILTER_MIN_QUERIES = 64
+# (frb_chisq_top1_filtered_g8): same answers as the exact scan.  Measured (profiles/r2_chisq_filter.txt): 1024 x 125k
+# 20.7 vs 482 ms, 64 x 8192 1.4 vs 2.5 ms, 16 x 100k 3.8 vs 6.2 ms, 16 x 30k 1.4 vs 2.0 ms; at 8 queries the exact scan
+# still wins (a filter unit multiplies a full 128-query tile whatever the batch holds).
+FILTER_MIN_QUERIES = 16
 FILTER_MIN_ROWS = 8192
 FILTER_ENABLED = True
 

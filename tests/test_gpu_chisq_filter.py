@@ -185,3 +185,25 @@ def test_configs4_share_at_full_shape_is_identical_to_the_exact_scan():
     st = stats.cpu().tolist()
     assert st[0] == 0 and st[3] == 0
     print(f"\n[filter] configs[4] share: survivors/query {st[1] / 1024:.1f}, raw candidates/query {st[2] / 1024:.1f}")
+
+
+def test_more_queries_than_one_pass_and_edge_cell_sizes():
+    """1100 queries = two passes of the 1024-query workspace; cell_px = 255 is the largest cell a u8 gallery can hold
+    (4-copy table); counts above the declared cell size (a contract violation) must not crash."""
+    from facerecognition_b200 import ops
+    gal, px = hists(faces_gpu(9000, 112, 51))
+    qh, _ = hists(faces_gpu(1100, 112, 52))
+    g8 = ops.compact_histograms(gal, px)
+    d, i = ops.chisq_top1_filtered(qh, g8, px)
+    want_d, want_i = exact_top1(qh, g8, px)
+    assert torch.equal(i, want_i) and torch.equal(d.view(torch.int32), want_d.view(torch.int32))
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    g255 = (torch.rand((8300, 4096), generator=gen, device="cuda") < 0.05) * torch.randint(1, 256, (8300, 4096), generator=gen, device="cuda")
+    g255 = g255.to(torch.uint8).contiguous()
+    q255 = g255[torch.randint(0, 8300, (20,), generator=gen, device="cuda")].to(torch.int16).contiguous().view(torch.uint16)
+    d, i = ops.chisq_top1_filtered(q255, g255, 255)
+    want_d, want_i = exact_top1(q255, g255, 255)
+    assert torch.equal(i, want_i) and torch.equal(d.view(torch.int32), want_d.view(torch.int32)) and float(d.max()) == 0.0
+    d, i = ops.chisq_top1_filtered(q255, g255, 100)          # counts up to 255 declared as cell_px = 100: defined behaviour, no fault
+    torch.cuda.synchronize()
+    assert i.shape == (20, 1)
