@@ -73,3 +73,38 @@ def test_lbph_step_replays_in_a_graph(oracle_lbph):
         want = [oracle_lbph.c_chisq_scan_u16(gal.cpu().numpy(), px, hq, px).argmin() for hq in
                 ops.lbp_hist(ops.bgr_to_gray(frames))[0].cpu().numpy()[8:]]
         assert i_out[8:, 0].cpu().tolist() == [int(w) for w in want]
+
+
+def test_sharded_search_graph_replay_and_host_pipeline_on_one_gpu():
+    """ShardedSearch.search(graph=True) (the replayed step bench.py and HostBatchPipeline use) on a single rank: replays on
+    refilled input buffers equal plain calls, for fp32 queries and for pre-normalised bf16 queries; the host pipeline returns
+    every batch's own answers with two batches in flight."""
+    from facerecognition_b200 import ops, _native as NV
+    from facerecognition_b200.sharded import HostBatchPipeline, cosine_sharded
+    g = torch.Generator(device="cuda").manual_seed(11)
+    gal = ops.normalize_rows(torch.randn((50_000, 512), generator=g, device="cuda"), NV.FRB_QNORM_CLAMP, torch.bfloat16)
+    search = cosine_sharded(gal, 1000, qnorm_mode=NV.FRB_QNORM_CLAMP)
+    q = torch.empty((300, 512), device="cuda")
+    q16 = torch.empty((300, 512), dtype=torch.bfloat16, device="cuda")
+    for trial in range(3):
+        q.copy_(gal[torch.randint(0, 50_000, (300,), generator=g, device="cuda")].float() + 0.05 * torch.randn((300, 512), generator=g, device="cuda"))
+        s, i = search.search(q, 5, graph=True)
+        ws, wi = ops.cosine_topk(q, gal, 5, qnorm_mode=NV.FRB_QNORM_CLAMP, idx_base=1000)
+        assert torch.equal(i, wi) and torch.equal(s, ws), trial
+        search.gather_normalized(q, q16, 0)                       # world 1: normalise in place of the gather
+        s2, i2 = search.search(q16, 5, graph=True)
+        assert torch.equal(i2, wi) and torch.equal(s2, ws), trial
+    pipe = HostBatchPipeline(search, 300, 512, 5, torch.device("cuda"))
+    batches = [(gal[torch.randint(0, 50_000, (300,), generator=g, device="cuda")].float()).cpu().pin_memory() for _ in range(5)]
+    tickets, got = [], []
+    for b in batches:
+        tickets.append(pipe.submit(b))
+        if len(tickets) == pipe.depth:
+            s, i = pipe.result(tickets.pop(0))
+            got.append((s.clone(), i.clone()))
+    for t in tickets:
+        s, i = pipe.result(t)
+        got.append((s.clone(), i.clone()))
+    for b, (s, i) in zip(batches, got):
+        ws, wi = ops.cosine_topk(b.cuda(), gal, 5, qnorm_mode=NV.FRB_QNORM_CLAMP, idx_base=1000)
+        assert torch.equal(i, wi.cpu()) and torch.equal(s, ws.cpu())
