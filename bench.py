@@ -220,9 +220,8 @@ def run_reference(args):
             "config": cfg,
             "cpu_baseline": {"value": val, "unit": "queries/s", "cores": cores, "kind": "port",
                              "sample": (f"each step = a {sample_q}-query sample of the batch x the full 1M fp32 gallery: numpy sgemm on {cores} threads + "
-                                        "argpartition, which numpy runs on ONE thread -- a floor for the reference's batched "
-                                        "numpy path, not a tuned CPU baseline (the reference's own per-query Python loop is "
-                                        "~20x slower still, BASELINE.md)")},
+                                        f"argpartition spread over {cores} threads by query row (oracle.cosine.batched_topk_fast); the "
+                                        "reference's own per-query Python loop is ~20x slower still (BASELINE.md)")},
             "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))

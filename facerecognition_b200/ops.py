@@ -2,7 +2,9 @@
 
 PyTorch is used here for device memory, streams and nothing else: every function takes CUDA
 tensors, passes raw device pointers + the current stream to the C entry point named in its
-docstring, and returns CUDA tensors.  No arithmetic is done in torch.
+docstring, and returns CUDA tensors.  No arithmetic is done in torch; the one place torch kernels run at all is the
+index plumbing (nonzero / gather / scatter of a few rows) when `cosine_topk_exact` re-runs queries whose candidate list
+could not be proven complete.
 """
 from __future__ import annotations
 
