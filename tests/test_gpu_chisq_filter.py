@@ -207,3 +207,24 @@ def test_more_queries_than_one_pass_and_edge_cell_sizes():
     d, i = ops.chisq_top1_filtered(q255, g255, 100)          # counts up to 255 declared as cell_px = 100: defined behaviour, no fault
     torch.cuda.synchronize()
     assert i.shape == (20, 1)
+
+
+def test_faces_with_flat_and_saturated_regions():
+    """SURVEY §8d's face mix (noise + a 255 stripe, blurred noise, piecewise-flat / saturated patches): cells whose pixels
+    all fall into one or two bins (counts up to the whole cell) stress the large-count end of the feature tables."""
+    import bench
+    from facerecognition_b200 import ops
+    dev = torch.device("cuda")
+    gimg = bench.synthetic_faces(torch, 12_000, 112, 112, dev, seed=7)
+    gal, px = hists(gimg)
+    g8 = ops.compact_histograms(gal, px)
+    qimg = torch.cat([gimg[torch.arange(0, 12_000, 100, device=dev)], bench.synthetic_faces(torch, 180, 112, 112, dev, seed=8)], 0)
+    qimg[5, 40:60, 40:60] = 0                                             # a modified re-shot
+    qh, _ = hists(qimg)
+    stats = torch.zeros(4, dtype=torch.int32, device="cuda")
+    d, i = ops.chisq_top1_filtered(qh, g8, px, stats=stats)
+    want_d, want_i = exact_top1(qh, g8, px)
+    assert torch.equal(i, want_i) and torch.equal(d.view(torch.int32), want_d.view(torch.int32))
+    st = stats.cpu().tolist()
+    assert st[3] == 0
+    print(f"\n[filter] flat / saturated mix: max count {int(gal.cpu().numpy().max())}, fallback {st[0]} of 300, survivors/query {st[1] / 300:.1f}")
