@@ -94,6 +94,19 @@ struct CfParams {
     float *all_scores;                  // debug: [n_query, n_gallery] S~ of every pair (the raw accumulators), or null
 };
 
+// explicit shared-state-space accesses for the generators' hot loop (the compiler emitted generic LD.E / ST.E for the
+// pointer arithmetic on the dynamic shared-memory base: same bytes, but a longer path than LDS / STS)
+__device__ __forceinline__ uint4 cf_lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void cf_sts128(uint32_t addr, uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 __device__ __forceinline__ float cf_atomic_max(float *addr, float v)   // returns the value before the update
 {
     if (v >= 0.f) return __int_as_float(atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v)));
@@ -196,8 +209,9 @@ chisq_filter_kernel(const __grid_constant__ CUtensorMap tmap_f, const CfParams p
         const int r = (warp - kCfGenWarp0) * 32 + lane;          // gallery row inside the tile
         const uint32_t xr = (uint32_t)(r & 7) << 4;              // 128-byte swizzle: 16-byte chunk c of row r sits at c ^ (r & 7)
         const int n_iter = p.n_kblocks >> 1;                     // 16 bins (one 128-bit load) = two k-blocks per iteration
-        const uint4 *my_tbl = tbl + (lane & (COP - 1));          // this lane's copy of every table row
+        const uint32_t my_tbl = smem_u32(tbl + (lane & (COP - 1)));   // this lane's copy of every table row
         const uint32_t last_row = (uint32_t)p.table_rows - 1;
+        const uint32_t b_base = smem_u32(smem_b) + (uint32_t)r * 128u;
         int sb = 0;
         uint32_t pb = 0, upar = 0;
         for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, upar ^= 1) {
@@ -222,11 +236,11 @@ chisq_filter_kernel(const __grid_constant__ CUtensorMap tmap_f, const CfParams p
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     mbar_wait(&bars->b_empty[sb], pb ^ 1);
-                    unsigned char *dst = smem_b + (size_t)sb * kCfBStageBytes + (size_t)r * 128;
+                    const uint32_t dst = b_base + (uint32_t)sb * kCfBStageBytes;
 #pragma unroll
                     for (int c = 0; c < 8; c++) {
                         const uint32_t cnt = min((wds[h * 2 + (c >> 2)] >> (8 * (c & 3))) & 0xFFu, last_row);
-                        *reinterpret_cast<uint4 *>(dst + (((uint32_t)c << 4) ^ xr)) = my_tbl[cnt * COP];
+                        cf_sts128(dst + (((uint32_t)c << 4) ^ xr), cf_lds128(my_tbl + cnt * (COP * 16u)));
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the UMMA reads
                     __syncwarp();
