@@ -481,6 +481,232 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
 }
 
+// ---- CTA-pair variant (cta_group::2), k <= 8 ---------------------------------------------------------------------
+// Two CTAs of a cluster (same TPC) run ONE tcgen05.mma of M = 256: CTA r of the pair owns query tile 2 * qp + r (its
+// 128 TMEM lanes, its own epilogue) and loads only rows [r * 128, r * 128 + 128) of every 256-row gallery tile; the
+// tensor core reads the other half from the peer's shared memory.  Per CTA that halves the B bytes fetched from L2 and
+// held in shared memory: six 16 KB stages fit where the single-CTA kernel has three 32 KB ones, so twice as many
+// k-blocks are in flight under the same TMA latency.  The leader (cluster rank 0) issues the MMAs; its full barriers
+// count the bytes of BOTH CTAs' TMA loads (cp.async.bulk.tensor ... cta_group::2), its commits are multicast to the
+// empty / tmem_full barriers of both CTAs, and the peer's epilogue warps arrive on the leader's tmem_empty barriers.
+// Work unit = (pair of query tiles qp, gallery group); pair c of the grid takes units c, c + n_pairs_in_grid, ...
+constexpr int kTcPairStagesMax = 6;
+constexpr uint32_t kTcPairBBytesPerStage = (kTcBlockN / 2) * kTcBlockK * 2;   // 16 KB: this CTA's half of the gallery tile
+constexpr uint32_t kTcIdescPairF16 = (1u << 4) | ((uint32_t)(kTcBlockN >> 3) << 17) | ((uint32_t)((2 * kTcBlockM) >> 4) << 24);
+constexpr uint32_t kTcIdescPairBf16 = kTcIdescPairF16 | (1u << 7) | (1u << 10);
+
+struct TcPairBarriers {
+    uint64_t full[kTcPairStagesMax];    // leader's copy counts: one arrive.expect_tx (leader) + the bytes of both CTAs
+    uint64_t empty[kTcPairStagesMax];   // each CTA's own copy: multicast commit of the MMAs that read the stage
+    uint64_t a_full, a_empty;
+    uint64_t tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+cosine_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_gh,
+                      const __grid_constant__ CUtensorMap tmap_pf, const TcParams p)
+{
+    constexpr int RS = 8;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *smem_a = smem;
+    unsigned char *smem_b = smem + (size_t)p.k_blocks * kTcABytesPerKb;
+    TcPairBarriers *bars = reinterpret_cast<TcPairBarriers *>(smem_b + (size_t)p.stages * kTcPairBBytesPerStage);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int64_t n_qpairs = (p.n_qtiles + 1) / 2;
+    const int64_t n_units = n_qpairs * p.n_groups;
+    const int64_t pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_gh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_pf) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; s++) {
+            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->empty[s], 1);
+        }
+        mbar_init(&bars->a_full, 1);
+        mbar_init(&bars->a_empty, 1);
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&bars->tmem_full[s], 1);
+            mbar_init(&bars->tmem_empty[s], 8);   // four epilogue warps of each CTA of the pair
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();                       // both CTAs' barriers exist before anyone signals across the pair
+    tcgen05_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, a_phase = 0;
+            for (int64_t u = pair0; u < n_units; u += pair_step) {
+                const int64_t qp = u % n_qpairs, grp = u / n_qpairs;
+                const int64_t qt = 2 * qp + rank;     // may be one past the last tile: TMA zero-fills, the epilogue ignores it
+                const int64_t t0 = p.tile_begin + grp * p.tiles_per_group;
+                const int64_t t1 = (t0 + p.tiles_per_group < p.tile_end) ? t0 + p.tiles_per_group : p.tile_end;
+                mbar_wait(&bars->a_empty, a_phase ^ 1);
+                if (leader) mbar_expect_tx(&bars->a_full, 2u * (uint32_t)p.k_blocks * kTcABytesPerKb);
+                for (int kb = 0; kb < p.k_blocks; kb++)
+                    tma_load_2d_pair(smem_a + (size_t)kb * kTcABytesPerKb, &tmap_q, &bars->a_full, kb * kTcBlockK, (int)(qt * kTcBlockM));
+                a_phase ^= 1;
+                if (leader) {
+                    for (int64_t t = t0 + qp; t < t0 + p.prefetch_dist && t < t1; t += n_qpairs)
+                        for (int c = 0; c < p.k_blocks * kTcBlockK; c += 256) tma_prefetch_l2_2d(&tmap_pf, c, (int)(t * kTcBlockN));
+                }
+                for (int64_t t = t0; t < t1; t++) {
+                    const int64_t tp = t + p.prefetch_dist;
+                    if (leader && tp < t1 && (tp - t0) % n_qpairs == qp)
+                        for (int c = 0; c < p.k_blocks * kTcBlockK; c += 256) tma_prefetch_l2_2d(&tmap_pf, c, (int)(tp * kTcBlockN));
+                    for (int kb = 0; kb < p.k_blocks; kb++) {
+                        mbar_wait(&bars->empty[stage], phase ^ 1);
+                        if (leader) mbar_expect_tx(&bars->full[stage], 2u * kTcPairBBytesPerStage);
+                        tma_load_2d_pair(smem_b + (size_t)stage * kTcPairBBytesPerStage, &tmap_gh, &bars->full[stage], kb * kTcBlockK,
+                                         (int)(t * kTcBlockN + rank * (kTcBlockN / 2)));
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (lane == 0 && leader) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, a_phase = 0, acc_phase = 0;
+            for (int64_t u = pair0; u < n_units; u += pair_step) {
+                const int64_t grp = u / n_qpairs;
+                const int64_t t0 = p.tile_begin + grp * p.tiles_per_group;
+                const int64_t t1 = (t0 + p.tiles_per_group < p.tile_end) ? t0 + p.tiles_per_group : p.tile_end;
+                mbar_wait(&bars->a_full, a_phase);
+                a_phase ^= 1;
+                tcgen05_fence_after();
+                for (int64_t t = t0; t < t1; t++) {
+                    mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+                    tcgen05_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)acc * kTcBlockN;
+                    for (int kb = 0; kb < p.k_blocks; kb++) {
+                        mbar_wait(&bars->full[stage], phase);
+                        tcgen05_fence_after();
+                        const uint64_t da = make_sw128_desc(smem_u32(smem_a + (size_t)kb * kTcABytesPerKb));
+                        const uint64_t db = make_sw128_desc(smem_u32(smem_b + (size_t)stage * kTcPairBBytesPerStage));
+#pragma unroll
+                        for (int k4 = 0; k4 < kTcBlockK / kTcUmmaK; k4++)
+                            umma_f16_pair(tmem_d, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), p.idesc, (kb | k4) != 0 ? 1u : 0u);
+                        tcgen05_commit_pair(&bars->empty[stage]);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                    tcgen05_commit_pair(&bars->tmem_full[acc]);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+                tcgen05_commit_pair(&bars->a_empty);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (both CTAs): own query tile, own TMEM lanes =====================
+        const int ew = warp & 3;
+        const int row = ew * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        float rs[RS];
+        int ri[RS];
+        for (int64_t u = pair0; u < n_units; u += pair_step) {
+            const int64_t qp = u % n_qpairs, grp = u / n_qpairs;
+            const int64_t qt = 2 * qp + rank;
+            const int64_t t0 = p.tile_begin + grp * p.tiles_per_group;
+            const int64_t t1 = (t0 + p.tiles_per_group < p.tile_end) ? t0 + p.tiles_per_group : p.tile_end;
+            const int64_t unit_n0 = t0 * kTcBlockN;
+#pragma unroll
+            for (int j = 0; j < RS; j++) { rs[j] = -INFINITY; ri[j] = -1; }
+            const int64_t q = qt * kTcBlockM + row;
+            const bool q_live = q < p.n_query;
+            float kth = -INFINITY;
+            float gthr = q_live ? ld_relaxed_f32(p.thr + q) : INFINITY;
+            float adm = gthr;
+            float published = gthr;
+            for (int64_t t = t0; t < t1; t++) {
+                mbar_wait(&bars->tmem_full[acc], acc_phase);
+                tcgen05_fence_after();
+                const int64_t n0 = t * kTcBlockN;
+                const int valid = (int)((p.n_gallery - n0) < kTcBlockN ? (p.n_gallery - n0) : kTcBlockN);
+                const int col0 = (int)(n0 - unit_n0);
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * kTcBlockN;
+#pragma unroll 1
+                for (int c0 = 0; c0 < kTcBlockN; c0 += 32) {
+                    float v[32];
+                    tmem_ld_32x32(taddr + (uint32_t)c0, v);
+                    if (c0 + 32 > valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) v[j] = (c0 + j < valid) ? v[j] : -INFINITY;
+                    }
+                    if (max32(v) > adm) {
+                        uint32_t cand = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) cand |= (v[j] > adm) ? (1u << j) : 0u;
+                        while (cand) {
+                            const int j = __ffs(cand) - 1;
+                            cand &= cand - 1;
+                            const float x = select32(v, j);
+                            if (x > adm) {
+                                reg_insert<RS>(rs, ri, x, col0 + c0 + j);
+                                kth = reg_kth<RS>(rs, p.k);
+                                adm = fmaxf(kth, gthr);
+                            }
+                        }
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(&bars->tmem_empty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (q_live) {
+                    const float mine = next_below(kth);
+                    if (mine > published) {
+                        atomic_max_f32(p.thr + q, mine);
+                        published = mine;
+                    }
+                    gthr = fmaxf(gthr, ld_relaxed_f32(p.thr + q));
+                    adm = fmaxf(kth, gthr);
+                }
+            }
+            if (q_live) {
+                int nv = 0;
+#pragma unroll
+                for (int j = 0; j < RS; j++) nv += (j < p.k && ri[j] >= 0) ? 1 : 0;
+                if (nv > 0) {
+                    const int64_t o = q * p.cand_cap + atomicAdd(p.cand_cnt + q, nv);
+#pragma unroll
+                    for (int j = 0; j < RS; j++)
+                        if (j < nv) {
+                            p.cand_scores[o + j] = rs[j];
+                            p.cand_idx[o + j] = p.idx_base + unit_n0 + ri[j];
+                        }
+                }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    cluster_sync_all();                       // neither CTA leaves (or frees TMEM) while its peer may still touch it
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 // row-major bf16 [rows, dim] -> boxes of (64 of K) x box_rows rows, 128-byte swizzled, zero fill out of bounds
 static int make_bf16_map(CUtensorMap *map, const void *base, int64_t rows, int dim, int box_rows, int box_cols = kTcBlockK,
@@ -568,12 +794,26 @@ static int64_t tc_balanced_groups(int64_t tiles, int64_t n_qt, int P, int64_t fa
     return best;
 }
 
+// CTA pairs (cosine_tc_pair_kernel) serve the short-list kernels from two query tiles up; FRB_TC_PAIR=0 keeps one CTA per tile
+static bool tc_use_pair(int64_t nq, int k)
+{
+    const char *e = getenv("FRB_TC_PAIR");
+    if (e && e[0] == '0') return false;
+    return k <= kTcShareMinK && nq > kTcBlockM;
+}
+
 static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
 {
     TcPlan pl;
     int sms = sm_count();
     if (sms <= 0) sms = 148;
+    const bool pair = tc_use_pair(nq, k);
     pl.n_qtiles = (nq + kTcBlockM - 1) / kTcBlockM;
+    const int64_t real_qtiles = pl.n_qtiles;
+    if (pair) {                      // schedule in units of (query-tile pair, gallery group) over sms / 2 CTA pairs
+        pl.n_qtiles = (pl.n_qtiles + 1) / 2;
+        sms /= 2;
+    }
     pl.n_tiles = (ng + kTcBlockN - 1) / kTcBlockN;
     if (pl.n_tiles < 1) pl.n_tiles = 1;
     // warm-up: ~1/64 of the gallery, 4..32 tiles, one wave of CTAs
@@ -614,6 +854,7 @@ static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
     }
     tc_split(warm_tiles, pl.n_tiles, want_groups, pl.warm.n_groups, &pl.main);
     pl.n_groups = pl.warm.n_groups + pl.main.n_groups;
+    pl.n_qtiles = real_qtiles;
     size_t n = (size_t)pl.n_groups * (size_t)nq * (size_t)k;
     pl.qbf16_bytes = align_up((size_t)pl.n_qtiles * kTcBlockM * (size_t)dim * 2, 1024);
     pl.thr_bytes = align_up((size_t)nq * sizeof(float), 256);
@@ -700,8 +941,10 @@ int launch_cosine_tc(const float *queries, const void *queries_bf16, int64_t nq,
     p.k_blocks = dim / kTcBlockK;
     p.idesc = op_dtype == FRB_F16 ? kTcIdescF16 : kTcIdescBf16;
     const size_t a_bytes = (size_t)p.k_blocks * kTcABytesPerKb;
-    int stages = (int)((kTcSmemLimit - 1024 - sizeof(TcBarriers) - a_bytes) / kTcBBytesPerStage);
-    if (stages > kTcMaxStages) stages = kTcMaxStages;
+    const bool pair = tc_use_pair(nq, k);
+    int stages = pair ? (int)((kTcSmemLimit - 1024 - sizeof(TcPairBarriers) - a_bytes) / kTcPairBBytesPerStage)
+                      : (int)((kTcSmemLimit - 1024 - sizeof(TcBarriers) - a_bytes) / kTcBBytesPerStage);
+    if (stages > (pair ? kTcPairStagesMax : kTcMaxStages)) stages = pair ? kTcPairStagesMax : kTcMaxStages;
     if (stages < 2) {
         set_error("bf16 tensor-core path: not enough shared memory for 2 gallery stages");
         return FRB_ERR_UNSUPPORTED;
@@ -716,7 +959,22 @@ int launch_cosine_tc(const float *queries, const void *queries_bf16, int64_t nq,
     p.cand_cap = pl.n_groups * k;
     p.cand_scores = cs;
     p.cand_idx = ci;
-    const size_t smem = 1024 + a_bytes + (size_t)stages * kTcBBytesPerStage + sizeof(TcBarriers);
+    const size_t smem = pair ? 1024 + a_bytes + (size_t)stages * kTcPairBBytesPerStage + sizeof(TcPairBarriers)
+                             : 1024 + a_bytes + (size_t)stages * kTcBBytesPerStage + sizeof(TcBarriers);
+    CUtensorMap tgh;
+    if (pair) {
+        // this CTA's half of a gallery tile: boxes of 128 rows
+        rc = make_bf16_map(&tgh, ng > 0 ? gallery_bf16 : (const void *)qb, ng, dim, kTcBlockN / 2, kTcBlockK, CU_TENSOR_MAP_SWIZZLE_128B, tm_dtype);
+        if (rc != FRB_OK) return rc;
+        p.idesc = op_dtype == FRB_F16 ? kTcIdescPairF16 : kTcIdescPairBf16;
+        static thread_local int pair_dev = -1;
+        static thread_local size_t pair_smem = 0;
+        if (pair_dev != dev || pair_smem < smem) {
+            FRB_CUDA_OK(cudaFuncSetAttribute(cosine_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            pair_dev = dev;
+            pair_smem = smem;
+        }
+    }
     const int variant = k <= 8 ? 0 : (k <= 16 ? 1 : (k <= 32 ? 2 : (k <= kTcMaxRegK ? 3 : 4)));  // register list of 8 / 16 / 32 / 64 slots, else local memory
     typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
     const TcKernel kernels[5] = {cosine_tc_kernel<8>, cosine_tc_kernel<16>, cosine_tc_kernel<32>, cosine_tc_kernel<64>, cosine_tc_kernel<0>};
@@ -743,16 +1001,21 @@ int launch_cosine_tc(const float *queries, const void *queries_bf16, int64_t nq,
         p.share_rank = use_share ? (int)((k + ps.n_groups - 1) / ps.n_groups) : k;
         p.tile_begin = ps.tile_begin;
         p.tile_end = ng > 0 ? ps.tile_end : ps.tile_begin;  // empty gallery: units run with no tiles and emit empty lists
-        const int64_t n_units = pl.n_qtiles * ps.n_groups;
-        const int grid = (int)(n_units < sms ? n_units : sms);
+        const int64_t sched_qtiles = pair ? (pl.n_qtiles + 1) / 2 : pl.n_qtiles;     // query tiles, or pairs of them
+        const int64_t n_units = sched_qtiles * ps.n_groups;
+        const int slots = pair ? sms / 2 : sms;
+        const int grid = (int)(n_units < slots ? n_units : slots);                   // CTAs, or CTA pairs
         {
             const size_t tile_bytes = (size_t)kTcBlockN * (size_t)p.k_blocks * kTcBlockK * 2;
-            const size_t groups_in_flight = (size_t)((grid + pl.n_qtiles - 1) / pl.n_qtiles);
+            const size_t groups_in_flight = (size_t)((grid + sched_qtiles - 1) / sched_qtiles);
             const size_t fit = kTcPrefetchL2Budget / (groups_in_flight * tile_bytes);
             p.prefetch_dist = pf_env ? atoi(pf_env) : (int)(fit < (size_t)kTcPrefetchDist ? fit : (size_t)kTcPrefetchDist);
         }
         ProfileScope prof(FRB_K_COSINE_TC, st);
-        kernel<<<grid, kTcThreads, smem, st>>>(tq, tg, tpf, p);
+        if (pair)
+            cosine_tc_pair_kernel<<<2 * grid, kTcThreads, smem, st>>>(tq, tgh, tpf, p);
+        else
+            kernel<<<grid, kTcThreads, smem, st>>>(tq, tg, tpf, p);
         FRB_LAUNCH_OK("cosine_tc_kernel");
     }
     return topk_merge_compact(cs, ci, cnt, p.cand_cap, nq, k, /*largest=*/1, out_scores, out_idx, st);

@@ -67,6 +67,54 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms: two CTAs of a cluster share one MMA ----------------------------------------------
+// Shared-window addresses of the two CTAs of a pair differ in bit 24; clearing it turns a barrier address into the
+// LEADER's (cluster rank 0) barrier at the same offset, from either CTA.
+constexpr uint32_t kPairLeaderMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA tile load into THIS CTA's shared memory whose bytes are counted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar) & kPairLeaderMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+// arrive on the LEADER's barrier (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPairLeaderMask) : "memory");
+}
+// completion of all prior MMAs of this thread -> the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tcgen05_commit_pair(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((unsigned short)3)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // 32 lanes x 32 consecutive columns of fp32 accumulators -> 32 registers per thread
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float *v)
 {

@@ -30,16 +30,25 @@ def measure(q, gal, reps=6):
 
 
 # A/B in one process, interleaved (the power cap makes back-to-back runs drift by several per cent)
+MODES = (("single CTA, rule of thumb", {"FRB_TC_PAIR": "0", "FRB_TC_BALANCE": "0"}),
+         ("single CTA, balanced groups", {"FRB_TC_PAIR": "0", "FRB_TC_BALANCE": "1"}),
+         ("CTA pair (cta_group::2)", {"FRB_TC_PAIR": "1", "FRB_TC_BALANCE": "1"}))
 for n in (1, 2, 4, 8):
     gal = gal_all[:1_000_000 // n].contiguous()
     q = q_all[:4096 * n].contiguous()
-    acc = {"0": [], "1": []}
+    acc = {name: [] for name, _ in MODES}
+    ref = None
     for rnd in range(5):
-        for mode in ("0", "1"):
-            os.environ["FRB_TC_BALANCE"] = mode
-            acc[mode].append(measure(q, gal))
-    for mode, name in (("0", "rule of thumb"), ("1", "balanced groups")):
-        ks = sorted(k for _, k in acc[mode])
-        st = sorted(s for s, _ in acc[mode])
-        print(f"N={n}: {4096 * n:6d} q x {1_000_000 // n:7d} rows, {name:15s}: cosine_tc median {ks[2]:.3f} ms (min {ks[0]:.3f} max {ks[-1]:.3f}), "
+        for name, env in MODES:
+            os.environ.update(env)
+            acc[name].append(measure(q, gal))
+            if rnd == 0:
+                out = ops.cosine_topk(q, gal, 5, qnorm_mode=NV.FRB_QNORM_CLAMP)
+                if ref is None:
+                    ref = out
+                assert torch.equal(out[1], ref[1]) and torch.equal(out[0], ref[0]), name
+    for name, _ in MODES:
+        ks = sorted(k for _, k in acc[name])
+        st = sorted(s for s, _ in acc[name])
+        print(f"N={n}: {4096 * n:6d} q x {1_000_000 // n:7d} rows, {name:28s}: cosine_tc median {ks[2]:.3f} ms (min {ks[0]:.3f} max {ks[-1]:.3f}), "
               f"step median {st[2]:.3f} ms, {2 * 4096 * 1e6 * 512 / (ks[2] * 1e-3) / 1e12:.0f} TFLOP/s")
