@@ -503,11 +503,11 @@ struct TcPairBarriers {
     uint32_t tmem_base;
 };
 
+template <int RS>   // slots of the register-resident best-k list: 8 (k <= 8) or 16 (k <= 16: the exact-fp32 path's first pass)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 cosine_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_gh,
                       const __grid_constant__ CUtensorMap tmap_pf, const TcParams p)
 {
-    constexpr int RS = 8;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *smem_a = smem;
@@ -794,12 +794,15 @@ static int64_t tc_balanced_groups(int64_t tiles, int64_t n_qt, int P, int64_t fa
     return best;
 }
 
-// CTA pairs (cosine_tc_pair_kernel) serve the short-list kernels from two query tiles up; FRB_TC_PAIR=0 keeps one CTA per tile
+// CTA pairs (cosine_tc_pair_kernel) serve lists of up to 16 from two query tiles up; FRB_TC_PAIR=0 keeps one CTA per tile
+constexpr int kTcPairMaxK = 16;
 static bool tc_use_pair(int64_t nq, int k)
 {
     const char *e = getenv("FRB_TC_PAIR");
     if (e && e[0] == '0') return false;
-    return k <= kTcShareMinK && nq > kTcBlockM;
+    // 16-slot lists are inserted without the single-CTA kernel's per-lane queue: fine while few lists warm up (256 x 1M:
+    // 0.62 -> 0.53 ms, 4096 x 100k: 0.57 -> 0.54 ms), slower than the queued kernel for large batches (4096 x 1M: 3.27 -> 3.49 ms)
+    return nq > kTcBlockM && (k <= kTcShareMinK || (k <= kTcPairMaxK && nq <= 2048));
 }
 
 static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
@@ -839,7 +842,7 @@ static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
     if (units_per_cta < 1) units_per_cta = 1;
     if (units_per_cta > 16) units_per_cta = 16;
     int64_t want_groups = ((int64_t)sms * units_per_cta + pl.n_qtiles - 1) / pl.n_qtiles;
-    if (k > kTcShareMinK) {
+    if (k > kTcShareMinK && !pair) {
         // long lists: every unit warms its own k-slot list (~k ln(rows / k) slow-path insertions per query and unit), so
         // few long units -- at most two per CTA, and never a third round (floor, not ceil)
         if (units_per_cta > 2) units_per_cta = 2;
@@ -849,7 +852,7 @@ static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
     if (want_groups > 1024) want_groups = 1024;
     {
         const char *bal = getenv("FRB_TC_BALANCE");      // experiments: 0 keeps the rule of thumb
-        if (k <= kTcShareMinK && tiles_per_cta >= 48 && !(bal && bal[0] == '0'))
+        if ((k <= kTcShareMinK || pair) && tiles_per_cta >= 48 && !(bal && bal[0] == '0'))
             want_groups = tc_balanced_groups(main_tiles, pl.n_qtiles, sms, want_groups);
     }
     tc_split(warm_tiles, pl.n_tiles, want_groups, pl.warm.n_groups, &pl.main);
@@ -858,7 +861,7 @@ static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
     size_t n = (size_t)pl.n_groups * (size_t)nq * (size_t)k;
     pl.qbf16_bytes = align_up((size_t)pl.n_qtiles * kTcBlockM * (size_t)dim * 2, 1024);
     pl.thr_bytes = align_up((size_t)nq * sizeof(float), 256);
-    pl.share_bytes = k > kTcShareMinK ? align_up((size_t)nq * 2 * kTcShareMaxGroups * sizeof(float), 256) : 0;  // one array per pass
+    pl.share_bytes = (k > kTcShareMinK && !pair) ? align_up((size_t)nq * 2 * kTcShareMaxGroups * sizeof(float), 256) : 0;  // one array per pass
     pl.cnt_bytes = align_up((size_t)nq * sizeof(int), 256);
     pl.idx_bytes = align_up(n * sizeof(int64_t), 256);
     pl.score_bytes = align_up(n * sizeof(float), 256);
@@ -970,7 +973,8 @@ int launch_cosine_tc(const float *queries, const void *queries_bf16, int64_t nq,
         static thread_local int pair_dev = -1;
         static thread_local size_t pair_smem = 0;
         if (pair_dev != dev || pair_smem < smem) {
-            FRB_CUDA_OK(cudaFuncSetAttribute(cosine_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FRB_CUDA_OK(cudaFuncSetAttribute(cosine_tc_pair_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FRB_CUDA_OK(cudaFuncSetAttribute(cosine_tc_pair_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             pair_dev = dev;
             pair_smem = smem;
         }
@@ -1012,8 +1016,10 @@ int launch_cosine_tc(const float *queries, const void *queries_bf16, int64_t nq,
             p.prefetch_dist = pf_env ? atoi(pf_env) : (int)(fit < (size_t)kTcPrefetchDist ? fit : (size_t)kTcPrefetchDist);
         }
         ProfileScope prof(FRB_K_COSINE_TC, st);
-        if (pair)
-            cosine_tc_pair_kernel<<<2 * grid, kTcThreads, smem, st>>>(tq, tgh, tpf, p);
+        if (pair && k <= 8)
+            cosine_tc_pair_kernel<8><<<2 * grid, kTcThreads, smem, st>>>(tq, tgh, tpf, p);
+        else if (pair)
+            cosine_tc_pair_kernel<16><<<2 * grid, kTcThreads, smem, st>>>(tq, tgh, tpf, p);
         else
             kernel<<<grid, kTcThreads, smem, st>>>(tq, tg, tpf, p);
         FRB_LAUNCH_OK("cosine_tc_kernel");
