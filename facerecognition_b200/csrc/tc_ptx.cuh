@@ -94,7 +94,7 @@ __device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorM
 // arrive on the LEADER's barrier (from either CTA of the pair)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar)
 {
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPairLeaderMask) : "memory");
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPairLeaderMask) : "memory");
 }
 // completion of all prior MMAs of this thread -> the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void tcgen05_commit_pair(uint64_t *bar)
