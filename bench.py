@@ -594,7 +594,7 @@ def main():
 
     def timed_steps(queries, steps, graph=None):
         """K steps, CUDA events per step on the launching stream, L2 flushed outside the brackets; MAX over ranks (ms)."""
-        graph = use_graph if graph is None else graph
+        graph = (use_graph and world > 1) if graph is None else graph
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
         for a, b in ev:
@@ -613,25 +613,33 @@ def main():
         t_w = time.perf_counter()
         done = 0
         while done < warmup or time.perf_counter() - t_w < args.min_warm_seconds:      # >= W steps and >= 1 s under load (clock samples)
-            s, i = search.search(q_dev, TOPK, graph=use_graph)
+            s, i = search.search(q_dev, TOPK, graph=use_graph and world > 1)
             done += 1
             if done % 16 == 0:
                 torch.cuda.synchronize()
         barrier()
         # correctness of what is being timed: planted queries must come back as their source row
         ok = bool(torch.equal(i[n_rand:, 0], src[n_rand:]))
-        total_ms, s, i = timed_steps(q_dev, args.steps)
-        value = n_query * args.steps / (total_ms * 1e-3)
-        # the roofline's kernel time: the same K steps once more, launched kernel by kernel so that libfrb200 can bracket
-        # every cosine_tc_kernel launch with an event pair on the launching stream (a graph replay has no host-side
-        # launch to bracket); same inputs, same L2 flush, directly after the timed region
+        # One GPU: the timed steps are launched kernel by kernel, so libfrb200 brackets every cosine_tc_kernel launch of the
+        # timed region itself with an event pair on the launching stream (launch gaps are ~1 % of a 2.6 ms step).
+        # Several GPUs: the timed steps are graph replays (launch gaps and rank skew matter there), which have no host-side
+        # launch to bracket; the kernel time then comes from the same K steps repeated kernel by kernel right after the
+        # timed region (a later pass under the power cap can run a few per cent slower than the timed one).
         for _ in range(3):                       # torch.cuda.graph() empties the caching allocator: re-warm the eager path
             search.search(q_dev, TOPK, graph=False)
         NV.profile_enable(True)
         NV.profile_read(NV.K_COSINE_TC)
-        eager_ms, _, _ = timed_steps(q_dev, args.steps, graph=False)
+        if world == 1:
+            total_ms, s, i = timed_steps(q_dev, args.steps, graph=False)
+            eager_ms = total_ms
+        else:
+            NV.profile_enable(False)
+            total_ms, s, i = timed_steps(q_dev, args.steps)
+            NV.profile_enable(True)
+            eager_ms, _, _ = timed_steps(q_dev, args.steps, graph=False)
         k_ms, k_n = NV.profile_read(NV.K_COSINE_TC)
         NV.profile_enable(False)
+        value = n_query * args.steps / (total_ms * 1e-3)
         # the step launches cosine_tc_kernel twice (threshold warm-up pass over ~1/64 of the shard + main pass);
         # achieved = the step's algorithmic flops / the summed device time of those launches
         kernel_ms_per_step = k_ms / args.steps
@@ -731,13 +739,14 @@ def main():
                         "value: sharded.HostBatchPipeline, two batches in flight (copies of one overlap the search of "
                         "the other); blocking_call_value: one batch at a time, host waits for each"},
         "gpu_launches": launches_per_step * args.steps,
-        "launch_mode": "the step's kernels are replayed from one CUDA graph (ShardedSearch.search(graph=True))" if use_graph else "kernel by kernel",
+        "launch_mode": ("the step's kernels are replayed from one CUDA graph (ShardedSearch.search(graph=True))" if use_graph and world > 1
+                        else "kernel by kernel (one GPU: every launch of the timed region is bracketed for the roofline); the e2e legs replay the step's CUDA graph"),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      **traffic, "kernel": "cosine_tc_kernel", "ms_per_step_in_kernel": kernel_ms_per_step,
                      "launches_timed": k_n, "launches_per_step": tc_per_step, "flops_per_step": flops_per_step,
                      "ms_per_step_kernel_by_kernel": eager_ms / args.steps,
-                     "timed_on": ("the K steps repeated kernel by kernel right after the graph-replayed timed region (event pairs around "
-                                  "each launch inside libfrb200)" if use_graph else "the timed region itself"),
+                     "timed_on": ("the timed region's own launches (event pairs around each launch inside libfrb200)" if world == 1 or not use_graph
+                                  else "the K steps repeated kernel by kernel right after the graph-replayed timed region"),
                      "frac_of_burst": achieved / peaks["bf16_tflops"], "frac_of_sustained": achieved / peaks["bf16_tflops_sustained"],
                      "peak_source": peaks["source"] + (", bf16 SUSTAINED figure: the timed steps ran power-capped (median SM clock < 90 % of max, see clocks) after >= 1 s of load"
                                                        if sustained else ", bf16 BURST figure: the SM clock stayed near its maximum during the run")},
