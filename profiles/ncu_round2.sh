@@ -2,7 +2,7 @@ set -x
 cd $GRAFT_REPO_ROOT
 B="python bench.py --steps 3 --warmup 3 --min-warm-seconds 0 --no-cpu-baseline --no-lbph --no-c4 --no-c5"
 $B > gpurun_out/plain_bench.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r2.csv $B > gpurun_out/ncu_bench.log 2>&1
-for t in "tc cosine_tc_kernel 4 2" "filter chisq_filter_kernel 2 1" "chisq_q1_u16 chisq_kernel 2 1" "chisq_q1_u8 chisq_kernel 2 1" "chisq_b_u8 chisq_kernel 2 1" "lbp lbp_hist_pipe_kernel 2 1" "lbp8 lbp_hist_pipe_kernel 2 1"; do
+for t in "tc cosine_tc 4 2" "filter chisq_filter_kernel 2 1" "chisq_q1_u16 chisq_kernel 2 1" "chisq_q1_u8 chisq_kernel 2 1" "chisq_b_u8 chisq_kernel 2 1" "lbp lbp_hist_pipe_kernel 2 1" "lbp8 lbp_hist_pipe_kernel 2 1"; do
   set -- $t
   python profiles/run_ncu_targets.py $1 > gpurun_out/plain_$1.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c $4 -f -o gpurun_out/prof_${1}_r2 python profiles/run_ncu_targets.py $1 > gpurun_out/ncu_$1.log 2>&1
   tail -2 gpurun_out/plain_$1.log
