@@ -282,9 +282,10 @@ int frb_chisq_dist(const uint16_t *q_hist_dev, int64_t n_query, int q_cell_px, c
 
 /* The same two scans over a gallery stored as u8 counts [n_gallery, hist_len] — valid when g_cell_px <= 255 (a cell of
  * a 100x100 or 112x112 face under the 8x8 grid has 144 / 169 pixels, so every count fits a byte) and hist_len % 16 == 0.
- * Same arithmetic on the same integers (queries stay u16, as frb_lbp_hist_u8 writes them); the scan is HBM-bound for a
- * single query, so half the bytes per row is half the time per predict(), and a 1M-histogram gallery is 16.4 GB
- * instead of 32.8 GB (OpenCV keeps 65.5 GB of float32 for it). */
+ * Same arithmetic on the same integers (queries stay u16, as frb_lbp_hist_u8 writes them).  A 1M-histogram gallery is
+ * 16.4 GB instead of 32.8 GB (OpenCV keeps 65.5 GB of float32 for it), and this is the form the tensor-core filter below
+ * streams.  It does NOT halve the time of a single predict(): the u16 scan runs at the HBM roof (100k rows in 0.51 ms,
+ * 6.4 TB/s) and the u8 scan, with half the bytes, hits the FP32/MUFU limit at about the same time (0.50 ms, 3.25 TB/s). */
 int frb_chisq_topk_g8(const uint16_t *q_hist_dev, int64_t n_query, int q_cell_px, const uint8_t *gallery_dev,
                       int64_t n_gallery, int hist_len, int g_cell_px, int k, int64_t idx_base,
                       float *out_dist_dev, int64_t *out_idx_dev, void *workspace_dev, size_t workspace_bytes,
