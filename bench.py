@@ -409,10 +409,29 @@ def c5_step(torch, ops, NV, device, peaks, rows, lo, search_factory, reps=3):
     kms, kn = NV.profile_read(NV.K_CHISQ_FILTER)
     NV.profile_enable(False)
     d, i = step()
+    # end to end: the frames start in pinned host memory and the (distance, row) answers end there
+    frames_host = frames.cpu().pin_memory()
+    out_d = torch.empty((C5_FRAMES, 1), dtype=torch.float32).pin_memory()
+    out_i = torch.empty((C5_FRAMES, 1), dtype=torch.int64).pin_memory()
+
+    def e2e_once():
+        frames.copy_(frames_host, non_blocking=True)
+        dd, ii = step()
+        out_d.copy_(dd, non_blocking=True)
+        out_i.copy_(ii, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_once()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        e2e_once()
+    e2e_ms = (time.perf_counter() - t0) / reps * 1e3
     flop = 2.0 * C5_FRAMES * rows * gal8.shape[1] * 8
     tf = flop / (kms / max(kn, 1) * 1e-3) / 1e12 if kn else 0.0
     st = stats.cpu().tolist()
     return {"faces_per_s": C5_FRAMES / (ms * 1e-3), "ms_per_step": ms, "frames": C5_FRAMES, "gallery_rows": rows,
+            "e2e": {"faces_per_s": C5_FRAMES / (e2e_ms * 1e-3), "ms_per_step": e2e_ms, "h2d_bytes_per_step": C5_FRAMES * 112 * 112,
+                    "d2h_bytes_per_step": C5_FRAMES * 12, "note": "pinned host frames -> GPU, K2 + match, (distance, row) -> pinned host; wall clock on this rank"},
             "gallery": "u8 LBPH histograms (16 KiB per face) of blocky synthetic 112x112 faces; 1/4 of the frames are noisy re-shots "
                        "of gallery faces, 3/4 have no match",
             "planted_top1": (i[:n_plant, 0], src),
