@@ -713,6 +713,28 @@ static int make_bf16_map(CUtensorMap *map, const void *base, int64_t rows, int d
                          CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B,
                          CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)
 {
+    // descriptors of recently used (base, shape, box) combinations are kept per thread: a serving loop calls with the
+    // same gallery (and the same staging buffers) over and over, and an encode is a driver call
+    struct Key {
+        const void *base;
+        int64_t rows;
+        int dim, box_rows, box_cols, swizzle, dtype;
+    };
+    struct Entry {
+        Key k;
+        CUtensorMap m;
+    };
+    static thread_local Entry cache[8];
+    static thread_local int cache_n = 0, cache_next = 0;
+    const Key key{base, rows, dim, box_rows, box_cols, (int)swizzle, (int)dtype};
+    for (int i = 0; i < cache_n; i++) {
+        const Key &c = cache[i].k;
+        if (c.base == key.base && c.rows == key.rows && c.dim == key.dim && c.box_rows == key.box_rows && c.box_cols == key.box_cols &&
+            c.swizzle == key.swizzle && c.dtype == key.dtype) {
+            *map = cache[i].m;
+            return FRB_OK;
+        }
+    }
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -729,6 +751,10 @@ static int make_bf16_map(CUtensorMap *map, const void *base, int64_t rows, int d
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld dim=%d)", (int)r, (long long)rows, dim);
         return FRB_ERR_CUDA;
     }
+    cache[cache_next].k = key;
+    cache[cache_next].m = *map;
+    cache_next = (cache_next + 1) % 8;
+    if (cache_n < 8) cache_n++;
     return FRB_OK;
 }
 
@@ -821,7 +847,12 @@ static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
     if (pl.n_tiles < 1) pl.n_tiles = 1;
     // warm-up: ~1/64 of the gallery, 4..32 tiles, one wave of CTAs
     int64_t warm_tiles = 0;
-    if (pl.n_tiles >= 64) {
+    // The warm-up pass pays for itself in the single-CTA kernels; with CTA pairs it no longer does (interleaved A/B,
+    // profiles/r2_tc_warm.txt: 4096 x 1M 2.85 -> 2.80 ms, 4096 x 125k 0.359 -> 0.347, 1024 x 125k 0.159 -> 0.142, 256 x 1M
+    // 0.253 -> 0.234, 32768 x 125k 2.89 -> 2.88; only 4096 x 250k lost, 0.669 -> 0.695), so pair plans skip it: one launch less.
+    const char *warm_env = getenv("FRB_TC_WARM");     // experiments: 0 / 1 force it off / on
+    const bool want_warm = warm_env ? warm_env[0] != '0' : !pair;
+    if (pl.n_tiles >= 64 && want_warm) {
         warm_tiles = pl.n_tiles / 64;
         if (warm_tiles < 4) warm_tiles = 4;
         if (warm_tiles > 32) warm_tiles = 32;
