@@ -499,7 +499,7 @@ def c4_leg(torch, dist, ops, NV, device, peaks, world, rank, cosine_sharded, sha
     k_ms, k_n = NV.profile_read(NV.K_COSINE_TC)
     NV.profile_enable(False)
     ok = torch.tensor([1 if bool(torch.equal(i[n_rand:, 0], src[n_rand:])) else 0], device=device)
-    kernel_ms = k_ms / (steps + 2)                       # summed over the launches of one step (warm-up pass + main pass)
+    kernel_ms = k_ms / (steps + 2)                       # summed over the cosine_tc launch(es) of one step
     tf = 2.0 * N_QUERY * (hi - lo) * DIM / (kernel_ms * 1e-3) / 1e12
     fr = torch.tensor([tf], dtype=torch.float64, device=device)
     if world > 1:
