@@ -659,8 +659,8 @@ def main():
         k_ms, k_n = NV.profile_read(NV.K_COSINE_TC)
         NV.profile_enable(False)
         value = n_query * args.steps / (total_ms * 1e-3)
-        # the step launches cosine_tc_kernel twice (threshold warm-up pass over ~1/64 of the shard + main pass);
-        # achieved = the step's algorithmic flops / the summed device time of those launches
+        # the step launches cosine_tc_pair_kernel once (the single-CTA kernels, <= 128 queries, add a threshold warm-up pass);
+        # achieved = the step's algorithmic flops / the summed device time of its cosine_tc launches
         kernel_ms_per_step = k_ms / args.steps
         flops_per_step = 2.0 * n_query * (hi - lo) * DIM
         achieved = flops_per_step / (kernel_ms_per_step * 1e-3) / 1e12
