@@ -34,7 +34,7 @@ def entry(name, algorithmic, what, pick=None):
 doc = {
     "_doc": "dram__bytes_read.sum + dram__bytes_write.sum per bench STEP / launch of each kernel, from the round-2 ncu --set full captures "
             "summarised beside this file (profiles/ncu_round2.sh, profiles/run_ncu_targets.py); regenerate with profiles/make_ncu_traffic.py",
-    "cosine_tc_kernel": entry("r2_prof_tc_r2.txt", 1_000_000 * 1024 + 4096 * 2048 + 4096 * 5 * 12, "4096 q x 1M bf16 rows, k = 5: warm-up pass + main pass"),
+    "cosine_tc_kernel": entry("r2_prof_tc_r2.txt", 1_000_000 * 1024 + 4096 * 2048 + 4096 * 5 * 12, "4096 q x 1M bf16 rows, k = 5: one launch per step"),
     "lbp_hist_kernel": entry("r2_prof_lbp_r2.txt", 65536 * (112 * 112 + 32768), "65536 faces of 112x112, u16 counts out"),
     "lbp_hist_kernel_u8": entry("r2_prof_lbp8_r2.txt", 65536 * (112 * 112 + 16384), "65536 faces of 112x112, u8 counts out"),
     "chisq_kernel": entry("r2_prof_chisq_b_u8_r2.txt", 64 * 100_000 * 16384, "batched exact scan, 64 queries x 100k u8 rows: the chunk is shared through L2"),
