@@ -659,7 +659,7 @@ int frb_chisq_top1_filtered_g8(const uint16_t *q_hist, int64_t n_query, const ui
         set_error("%s: workspace %zu B < %zu B", fn, workspace_bytes, pl.total);
         return FRB_ERR_WORKSPACE;
     }
-    FRB_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "%s: workspace must be 256-byte aligned", fn);   // cudaMalloc / torch allocations are
+    FRB_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "%s: workspace must be 256-byte aligned", fn);  // what cudaMalloc and torch's allocator give
     cudaStream_t st = (cudaStream_t)stream;
     CfTables tb;
     int rc = get_tables(cell_px, &tb);

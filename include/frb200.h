@@ -309,6 +309,7 @@ int frb_chisq_dist_g8(const uint16_t *q_hist_dev, int64_t n_query, int q_cell_px
  *              [2] raw candidates appended by the filter kernel, [3] re-scored rows whose filter score missed the exact
  *              one by more than the bound (audit of every survivor; such a query is re-answered by the exact scan).
  *   approx_scores_dev  fp32 [n_query, n_gallery] or NULL: every approximate sum_j f (tests / calibration only).
+ *   workspace_dev  >= frb_chisq_filter_workspace_bytes(...) bytes, 256-byte aligned; histograms 16-byte aligned.
  * The first call for a (device, cell_px) builds and uploads the tables with blocking copies; later calls are
  * stream-ordered and capturable. */
 size_t frb_chisq_filter_workspace_bytes(int64_t n_query, int64_t n_gallery, int hist_len);
