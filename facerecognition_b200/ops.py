@@ -135,17 +135,16 @@ REFINE_MIN_QUERIES = 8
 REFINE_MIN_ROWS = 16384
 
 
-def refine_min_queries(k: int) -> int:
-    """Smallest batch that takes the tensor-core first pass + exact re-score instead of the fp32 kernels."""
-    return REFINE_MIN_QUERIES
-
-
 def refine_applicable(n_query: int, n_rows: int, dim: int, k: int) -> bool:
     """Shapes where ops.cosine_topk_exact beats the fp32 kernels (profiles/r2_refine.txt): any batch of >= 8 queries over
-    >= 16k rows (2-40x), and batches of >= 512 over galleries as small as 4k rows (4096 x 10k: 0.21 vs 1.64 ms)."""
-    if not refine_list_length(k) or dim % 64 != 0 or dim > 512 or n_query < REFINE_MIN_QUERIES:
+    >= 16k rows (2-40x), batches of >= 512 over galleries as small as 4k rows (4096 x 10k: 0.21 vs 1.64 ms), and the
+    5-7-query batches (the fp32 FFMA-tiled kernel's smallest) from 64k rows up (100k rows: 0.15 vs 0.21 ms, 1M: 0.31 vs
+    0.91 ms); 4 queries from 256k rows (1M: 0.31 vs 0.57 ms).  1-3 queries stay on the row-streaming fp32 kernel."""
+    if not refine_list_length(k) or dim % 64 != 0 or dim > 512:
         return False
-    return n_rows >= REFINE_MIN_ROWS or (n_rows >= 4096 and n_query >= 512)
+    if n_query >= REFINE_MIN_QUERIES:
+        return n_rows >= REFINE_MIN_ROWS or (n_rows >= 4096 and n_query >= 512)
+    return (n_query >= 5 and n_rows >= 65536) or (n_query == 4 and n_rows >= 262144)
 
 
 def refine_list_length(k: int) -> int:

@@ -28,7 +28,7 @@ for n_rows in (10_000, 100_000, 1_000_000):
     gal = ops.normalize_rows(torch.randn((n_rows, 512), generator=gen, device=dev), NV.FRB_QNORM_CLAMP)
     g16 = ops.normalize_rows(gal, NV.FRB_QNORM_CLAMP, torch.float16)
     gn = ops.row_norms(gal)
-    for nq in (8, 64, 256, 4096):
+    for nq in tuple(int(x) for x in os.environ.get("FRB_REFINE_Q", "8,64,256,4096").split(",")):
         src = torch.randint(0, n_rows, (nq,), generator=gen, device=dev)
         q = gal[src] + 0.03 * torch.randn((nq, 512), generator=gen, device=dev)
         q[: nq // 10] = torch.randn((nq // 10, 512), generator=gen, device=dev)          # 10 % without a match

@@ -439,6 +439,13 @@ def test_engine_batches_on_a_large_gallery_use_the_first_pass_and_agree_with_sin
         name, score, top = eng.recognize_with_db(q[j])
         assert batched[j][0] == name == f"id_{src[j]:06d}" and abs(batched[j][1] - score) <= 2e-6
         assert [t[0] for t in batched[j][2]] == [t[0] for t in top]
+    # 5-7 queries (the smallest batches that take the first pass, from 64k rows) against the exact single-query answers
+    assert ops.refine_applicable(5, n, 512, 5) and not ops.refine_applicable(3, n, 512, 5)
+    for nb in (5, 7):
+        small = eng.recognize_embeddings(q[20:20 + nb])
+        for j in range(nb):
+            name, score, top = eng.recognize_with_db(q[20 + j])
+            assert small[j][0] == name and abs(small[j][1] - score) <= 2e-6 and [t[0] for t in small[j][2]] == [t[0] for t in top]
 
 
 def test_prenormalised_bf16_queries_entry_equals_the_fp32_query_entry():
