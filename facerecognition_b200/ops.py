@@ -133,18 +133,23 @@ REFINE_EPS_REL = 2.001e-3
 # measured on B200 (profiles/r2_refine.txt): from 8 queries x 16k rows up the first pass + re-score beats the fp32 kernels
 REFINE_MIN_QUERIES = 8
 REFINE_MIN_ROWS = 16384
+REFINE_MIN_ROWS_SINGLE = 750_000      # 1-3 queries: 1M rows 0.31 vs 0.36-0.38 ms, 4M 0.78 vs 1.25-1.31 ms, 400k 0.21 vs 0.19 ms
 
 
 def refine_applicable(n_query: int, n_rows: int, dim: int, k: int) -> bool:
     """Shapes where ops.cosine_topk_exact beats the fp32 kernels (profiles/r2_refine.txt): any batch of >= 8 queries over
     >= 16k rows (2-40x), batches of >= 512 over galleries as small as 4k rows (4096 x 10k: 0.21 vs 1.64 ms), and the
     5-7-query batches (the fp32 FFMA-tiled kernel's smallest) from 64k rows up (100k rows: 0.15 vs 0.21 ms, 1M: 0.31 vs
-    0.91 ms); 4 queries from 256k rows (1M: 0.31 vs 0.57 ms).  1-3 queries stay on the row-streaming fp32 kernel."""
+    0.91 ms); 4 queries from 256k rows (1M: 0.31 vs 0.57 ms); 1-3 queries from REFINE_MIN_ROWS_SINGLE rows, where
+    streaming the half-size fp16 copy outweighs the extra launches (the first pass stays on the tcgen05 kernel: the
+    row-streaming kernel with a 16-slot list per warp measured 0.49 ms at 1M rows against 0.30)."""
     if not refine_list_length(k) or dim % 64 != 0 or dim > 512:
         return False
     if n_query >= REFINE_MIN_QUERIES:
         return n_rows >= REFINE_MIN_ROWS or (n_rows >= 4096 and n_query >= 512)
-    return (n_query >= 5 and n_rows >= 65536) or (n_query == 4 and n_rows >= 262144)
+    if n_query >= 4:
+        return (n_query >= 5 and n_rows >= 65536) or n_rows >= 262144
+    return n_rows >= REFINE_MIN_ROWS_SINGLE
 
 
 def refine_list_length(k: int) -> int:

@@ -23,7 +23,7 @@ def timed(fn, reps=5):
     return sorted(ts)[len(ts) // 2], out
 
 
-for n_rows in (10_000, 100_000, 1_000_000):
+for n_rows in tuple(int(x) for x in os.environ.get("FRB_REFINE_ROWS", "10000,100000,1000000").split(",")):
     gen = torch.Generator(device=dev).manual_seed(n_rows)
     gal = ops.normalize_rows(torch.randn((n_rows, 512), generator=gen, device=dev), NV.FRB_QNORM_CLAMP)
     g16 = ops.normalize_rows(gal, NV.FRB_QNORM_CLAMP, torch.float16)
