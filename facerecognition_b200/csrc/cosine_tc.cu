@@ -193,6 +193,91 @@ struct TcParams {
     int64_t *cand_idx;
 };
 
+// ---- epilogue pieces shared by the single-CTA and the CTA-pair kernel (register-resident lists) -------------------
+// 32 scores of one query (TMEM columns id0 .. id0 + 31 of the unit) against its list.  QUEUED (lists of 16+ slots): a
+// sorted insert is ~6 RS instructions and, done where the candidate is found, the whole warp pays for ONE lane's insert.
+// Lanes park their admitted scores in a 4-slot queue instead; when any lane's queue is full every lane drains its own,
+// so one pass of the insert code serves up to 32 candidates.  Thresholds move only at a drain: a score admitted against
+// a stale threshold is re-checked against the list's last slot inside drain_queue and dropped there.
+template <int RS, bool QUEUED>
+__device__ __forceinline__ void tc_admit32(const float *v, int id0, int k, float gthr, float &adm, float &kth, float (&rs)[RS],
+                                           int (&ri)[RS], float (&qv)[kTcQueue], int (&qi)[kTcQueue], int &qn)
+{
+    if (QUEUED) {
+        if (__any_sync(0xffffffffu, max32(v) > adm)) {
+            uint32_t cand = 0;
+#pragma unroll
+            for (int j = 0; j < 32; j++) cand |= (v[j] > adm) ? (1u << j) : 0u;
+            while (__any_sync(0xffffffffu, cand != 0)) {
+                if (cand) {
+                    const int j = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    const float x = select32(v, j);
+                    if (x > adm) {
+                        const int id = id0 + j;
+#pragma unroll
+                        for (int r = 0; r < kTcQueue; r++) {
+                            qv[r] = (qn == r) ? x : qv[r];
+                            qi[r] = (qn == r) ? id : qi[r];
+                        }
+                        qn++;
+                    }
+                }
+                if (__any_sync(0xffffffffu, qn == kTcQueue)) {
+                    drain_queue<RS>(rs, ri, qv, qi, qn);
+                    kth = reg_kth<RS>(rs, k);
+                    adm = fmaxf(kth, gthr);
+                }
+            }
+        }
+    } else if (max32(v) > adm) {   // rare once the thresholds have warmed up
+        // candidate mask first (straight-line), then visit this lane's candidates in column order; the warp
+        // iterates max-popcount times instead of walking 32 branchy checks
+        uint32_t cand = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) cand |= (v[j] > adm) ? (1u << j) : 0u;
+        while (cand) {
+            const int j = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const float x = select32(v, j);
+            if (x > adm) {
+                reg_insert<RS>(rs, ri, x, id0 + j);
+                kth = reg_kth<RS>(rs, k);
+                adm = fmaxf(kth, gthr);
+            }
+        }
+    }
+}
+
+// Once per tile: publish this unit's bound for query q if it improved (thr[q], and for long lists its share-of-k
+// bound), pick up the other units'.  kth: the unit's own k-th best.
+template <int RS>
+__device__ __forceinline__ void tc_exchange_bounds(const TcParams &p, int64_t q, int64_t grp, const float (&rs)[RS], float kth,
+                                                   float &published, float &pub_share, float &gthr, float &adm)
+{
+    float mine = next_below(kth);
+    if (RS >= 16 && p.share) {
+        float *slot = p.share + q;   // [group][query]: a warp's 32 queries share sectors
+        const float part = next_below(reg_kth<RS>(rs, p.share_rank));
+        if (part > pub_share) {
+            st_relaxed_f32(slot + grp * p.n_query, part);
+            pub_share = part;
+        }
+        float m = INFINITY;
+        for (int64_t g = 0; g < p.n_groups; g++) {
+            const float v = ld_relaxed_f32(slot + g * p.n_query);
+            m = (__float_as_uint(v) == 0xFFFFFFFFu) ? -INFINITY : fminf(m, v);
+        }
+        mine = fmaxf(mine, m);
+    }
+    if (mine > published) {
+        atomic_max_f32(p.thr + q, mine);
+        published = mine;
+    }
+    gthr = fmaxf(gthr, ld_relaxed_f32(p.thr + q));
+    adm = fmaxf(kth, gthr);
+}
+
 // RK: slots of the register-resident list (8, 16, 32, 64), or 0 for the local-memory list
 template <int RK>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -360,41 +445,9 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 32; j++) v[j] = (c0 + j < valid) ? v[j] : -INFINITY;
                     }
-                    if (QUEUED) {
-                        // Long lists: a sorted insert is ~6 RS instructions and, done where the candidate is found, the
-                        // whole warp pays for ONE lane's insert.  Lanes park their admitted scores in a 4-slot queue
-                        // instead; when any lane's queue is full every lane drains its own, so one pass of the insert
-                        // code serves up to 32 candidates.  Thresholds move only at a drain: a score admitted against a
-                        // stale threshold is re-checked against the list's last slot inside drain_queue and dropped there.
-                        if (__any_sync(0xffffffffu, max32(v) > adm)) {
-                            uint32_t cand = 0;
-#pragma unroll
-                            for (int j = 0; j < 32; j++) cand |= (v[j] > adm) ? (1u << j) : 0u;
-                            while (__any_sync(0xffffffffu, cand != 0)) {
-                                if (cand) {
-                                    const int j = __ffs(cand) - 1;
-                                    cand &= cand - 1;
-                                    const float x = select32(v, j);
-                                    if (x > adm) {
-                                        const int id = col0 + c0 + j;
-#pragma unroll
-                                        for (int r = 0; r < kTcQueue; r++) {
-                                            qv[r] = (qn == r) ? x : qv[r];
-                                            qi[r] = (qn == r) ? id : qi[r];
-                                        }
-                                        qn++;
-                                    }
-                                }
-                                if (__any_sync(0xffffffffu, qn == kTcQueue)) {
-                                    drain_queue<RS>(rs, ri, qv, qi, qn);
-                                    kth = reg_kth<RS>(rs, p.k);
-                                    adm = fmaxf(kth, gthr);
-                                }
-                            }
-                        }
-                    } else if (max32(v) > adm) {   // rare once the thresholds have warmed up
-                        // candidate mask first (straight-line), then visit this lane's candidates in column
-                        // order; the warp iterates max-popcount times instead of walking 32 branchy checks
+                    if (REG_LIST) {
+                        tc_admit32<RS, QUEUED>(v, col0 + c0, p.k, gthr, adm, kth, rs, ri, qv, qi, qn);
+                    } else if (max32(v) > adm) {   // local-memory list (k beyond the register variants)
                         uint32_t cand = 0;
 #pragma unroll
                         for (int j = 0; j < 32; j++) cand |= (v[j] > adm) ? (1u << j) : 0u;
@@ -403,12 +456,7 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             cand &= cand - 1;
                             const float x = select32(v, j);
                             if (x > adm) {
-                                if (REG_LIST) {
-                                    reg_insert<RS>(rs, ri, x, col0 + c0 + j);
-                                    kth = reg_kth<RS>(rs, p.k);
-                                } else {
-                                    kth = list_insert_stream<true>(best_s, best_i, p.k, x, p.idx_base + n0 + c0 + j);
-                                }
+                                kth = list_insert_stream<true>(best_s, best_i, p.k, x, p.idx_base + n0 + c0 + j);
                                 adm = fmaxf(kth, gthr);
                             }
                         }
@@ -419,29 +467,7 @@ cosine_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 // exchange thresholds once per tile: publish ours if it improved, pick up the others'
-                if (q_live) {
-                    float mine = next_below(kth);
-                    if (RS >= 16 && p.share) {
-                        float *slot = p.share + q;   // [group][query]: a warp's 32 queries share sectors
-                        const float part = next_below(reg_kth<RS>(rs, p.share_rank));
-                        if (part > pub_share) {
-                            st_relaxed_f32(slot + grp * p.n_query, part);
-                            pub_share = part;
-                        }
-                        float m = INFINITY;
-                        for (int64_t g = 0; g < p.n_groups; g++) {
-                            const float v = ld_relaxed_f32(slot + g * p.n_query);
-                            m = (__float_as_uint(v) == 0xFFFFFFFFu) ? -INFINITY : fminf(m, v);
-                        }
-                        mine = fmaxf(mine, m);
-                    }
-                    if (mine > published) {
-                        atomic_max_f32(p.thr + q, mine);
-                        published = mine;
-                    }
-                    gthr = fmaxf(gthr, ld_relaxed_f32(p.thr + q));
-                    adm = fmaxf(kth, gthr);
-                }
+                if (q_live) tc_exchange_bounds<RS>(p, q, grp, rs, kth, published, pub_share, gthr, adm);
             }
             if (QUEUED && __any_sync(0xffffffffu, qn > 0)) drain_queue<RS>(rs, ri, qv, qi, qn);
             if (q_live) {
@@ -503,7 +529,7 @@ struct TcPairBarriers {
     uint32_t tmem_base;
 };
 
-template <int RS>   // slots of the register-resident best-k list: 8 (k <= 8) or 16 (k <= 16: the exact-fp32 path's first pass)
+template <int RS>   // slots of the register-resident best-k list: 8, 16 (the exact-fp32 path's first pass), 32 or 64
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 cosine_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_gh,
                       const __grid_constant__ CUtensorMap tmap_pf, const TcParams p)
@@ -621,6 +647,12 @@ cosine_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         const int row = ew * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
+        constexpr bool QUEUED = RS >= 16;   // as in the single-CTA kernel: long lists admit through a per-lane queue
+        float qv[kTcQueue];
+        int qi[kTcQueue];
+        int qn = 0;
+#pragma unroll
+        for (int r = 0; r < kTcQueue; r++) { qv[r] = -INFINITY; qi[r] = -1; }
         float rs[RS];
         int ri[RS];
         for (int64_t u = pair0; u < n_units; u += pair_step) {
@@ -637,6 +669,7 @@ cosine_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             float gthr = q_live ? ld_relaxed_f32(p.thr + q) : INFINITY;
             float adm = gthr;
             float published = gthr;
+            float pub_share = -INFINITY;
             for (int64_t t = t0; t < t1; t++) {
                 mbar_wait(&bars->tmem_full[acc], acc_phase);
                 tcgen05_fence_after();
@@ -652,36 +685,15 @@ cosine_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
                         for (int j = 0; j < 32; j++) v[j] = (c0 + j < valid) ? v[j] : -INFINITY;
                     }
-                    if (max32(v) > adm) {
-                        uint32_t cand = 0;
-#pragma unroll
-                        for (int j = 0; j < 32; j++) cand |= (v[j] > adm) ? (1u << j) : 0u;
-                        while (cand) {
-                            const int j = __ffs(cand) - 1;
-                            cand &= cand - 1;
-                            const float x = select32(v, j);
-                            if (x > adm) {
-                                reg_insert<RS>(rs, ri, x, col0 + c0 + j);
-                                kth = reg_kth<RS>(rs, p.k);
-                                adm = fmaxf(kth, gthr);
-                            }
-                        }
-                    }
+                    tc_admit32<RS, QUEUED>(v, col0 + c0, p.k, gthr, adm, kth, rs, ri, qv, qi, qn);
                 }
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader(&bars->tmem_empty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                if (q_live) {
-                    const float mine = next_below(kth);
-                    if (mine > published) {
-                        atomic_max_f32(p.thr + q, mine);
-                        published = mine;
-                    }
-                    gthr = fmaxf(gthr, ld_relaxed_f32(p.thr + q));
-                    adm = fmaxf(kth, gthr);
-                }
+                if (q_live) tc_exchange_bounds<RS>(p, q, grp, rs, kth, published, pub_share, gthr, adm);
             }
+            if (QUEUED && __any_sync(0xffffffffu, qn > 0)) drain_queue<RS>(rs, ri, qv, qi, qn);
             if (q_live) {
                 int nv = 0;
 #pragma unroll
@@ -821,14 +833,25 @@ static int64_t tc_balanced_groups(int64_t tiles, int64_t n_qt, int P, int64_t fa
 }
 
 // CTA pairs (cosine_tc_pair_kernel) serve lists of up to 16 from two query tiles up; FRB_TC_PAIR=0 keeps one CTA per tile
-constexpr int kTcPairMaxK = 16;
+static int tc_pair_max_k()
+{
+    const char *m = getenv("FRB_TC_PAIR_MAXK");                         // experiments: longest list the pair kernel serves
+    return m ? atoi(m) : kTcMaxRegK;
+}
 static bool tc_use_pair(int64_t nq, int k)
 {
     const char *e = getenv("FRB_TC_PAIR");
     if (e && e[0] == '0') return false;
-    // 16-slot lists are inserted without the single-CTA kernel's per-lane queue: fine while few lists warm up (256 x 1M:
-    // 0.62 -> 0.53 ms, 4096 x 100k: 0.57 -> 0.54 ms), slower than the queued kernel for large batches (4096 x 1M: 3.27 -> 3.49 ms)
-    return nq > kTcBlockM && (k <= kTcShareMinK || (k <= kTcPairMaxK && nq <= 2048));
+    return nq > kTcBlockM && k <= tc_pair_max_k();
+}
+// Long lists (k > 8) warm a k-slot list per unit, so big batches want few long units (as the single-CTA kernel always
+// plans them); small batches keep the regular planner.  Interleaved A/B, k = 16 (profiles/r2_tc_pair_long.txt):
+// 4096 x 1M 3.07 -> 2.91 ms, 8192 x 500k 4.11 -> 2.99, 32768 x 125k 3.57 -> 3.24; but 1024 x 1M 1.02 -> 1.10, 256 x 1M 0.46 -> 0.55.
+// k = 32 / 64: 1024 x 1M 1.42 -> 1.25 / 3.57 -> 2.45 ms with long units, 256 x 1M (k = 64) 2.01 -> 3.41 without.
+static bool tc_pair_long_units(int64_t nq, int k)
+{
+    const char *e = getenv("FRB_TC_PAIR_LONG");                         // experiments: 0 / 1 force it
+    return e ? e[0] == '1' : nq >= (k <= 16 ? 2048 : 1024);
 }
 
 static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
@@ -873,7 +896,8 @@ static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
     if (units_per_cta < 1) units_per_cta = 1;
     if (units_per_cta > 16) units_per_cta = 16;
     int64_t want_groups = ((int64_t)sms * units_per_cta + pl.n_qtiles - 1) / pl.n_qtiles;
-    if (k > kTcShareMinK && !pair) {
+    const bool long_units = k > kTcShareMinK && (!pair || tc_pair_long_units(nq, k));
+    if (long_units) {
         // long lists: every unit warms its own k-slot list (~k ln(rows / k) slow-path insertions per query and unit), so
         // few long units -- at most two per CTA, and never a third round (floor, not ceil)
         if (units_per_cta > 2) units_per_cta = 2;
@@ -883,7 +907,7 @@ static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
     if (want_groups > 1024) want_groups = 1024;
     {
         const char *bal = getenv("FRB_TC_BALANCE");      // experiments: 0 keeps the rule of thumb
-        if ((k <= kTcShareMinK || pair) && tiles_per_cta >= 48 && !(bal && bal[0] == '0'))
+        if (!long_units && tiles_per_cta >= 48 && !(bal && bal[0] == '0'))
             want_groups = tc_balanced_groups(main_tiles, pl.n_qtiles, sms, want_groups);
     }
     tc_split(warm_tiles, pl.n_tiles, want_groups, pl.warm.n_groups, &pl.main);
@@ -892,7 +916,7 @@ static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
     size_t n = (size_t)pl.n_groups * (size_t)nq * (size_t)k;
     pl.qbf16_bytes = align_up((size_t)pl.n_qtiles * kTcBlockM * (size_t)dim * 2, 1024);
     pl.thr_bytes = align_up((size_t)nq * sizeof(float), 256);
-    pl.share_bytes = (k > kTcShareMinK && !pair) ? align_up((size_t)nq * 2 * kTcShareMaxGroups * sizeof(float), 256) : 0;  // one array per pass
+    pl.share_bytes = k > kTcShareMinK ? align_up((size_t)nq * 2 * kTcShareMaxGroups * sizeof(float), 256) : 0;  // one array per pass
     pl.cnt_bytes = align_up((size_t)nq * sizeof(int), 256);
     pl.idx_bytes = align_up(n * sizeof(int64_t), 256);
     pl.score_bytes = align_up(n * sizeof(float), 256);
@@ -1006,6 +1030,8 @@ int launch_cosine_tc(const float *queries, const void *queries_bf16, int64_t nq,
         if (pair_dev != dev || pair_smem < smem) {
             FRB_CUDA_OK(cudaFuncSetAttribute(cosine_tc_pair_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             FRB_CUDA_OK(cudaFuncSetAttribute(cosine_tc_pair_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FRB_CUDA_OK(cudaFuncSetAttribute(cosine_tc_pair_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FRB_CUDA_OK(cudaFuncSetAttribute(cosine_tc_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             pair_dev = dev;
             pair_smem = smem;
         }
@@ -1049,8 +1075,12 @@ int launch_cosine_tc(const float *queries, const void *queries_bf16, int64_t nq,
         ProfileScope prof(FRB_K_COSINE_TC, st);
         if (pair && k <= 8)
             cosine_tc_pair_kernel<8><<<2 * grid, kTcThreads, smem, st>>>(tq, tgh, tpf, p);
-        else if (pair)
+        else if (pair && k <= 16)
             cosine_tc_pair_kernel<16><<<2 * grid, kTcThreads, smem, st>>>(tq, tgh, tpf, p);
+        else if (pair && k <= 32)
+            cosine_tc_pair_kernel<32><<<2 * grid, kTcThreads, smem, st>>>(tq, tgh, tpf, p);
+        else if (pair)
+            cosine_tc_pair_kernel<64><<<2 * grid, kTcThreads, smem, st>>>(tq, tgh, tpf, p);
         else
             kernel<<<grid, kTcThreads, smem, st>>>(tq, tg, tpf, p);
         FRB_LAUNCH_OK("cosine_tc_kernel");
