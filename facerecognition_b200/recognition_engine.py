@@ -394,19 +394,23 @@ class RecognitionEngine:
         s, i = self.recognize_embeddings_device(emb, k)
         return s.cpu().numpy(), i.cpu().numpy(), self.gallery().names
 
-    def _format_db_result(self, scores, rows, names):
-        top = [(names[j], float(s)) for s, j in zip(scores, rows) if j >= 0]
-        best_name, best_score = top[0]  # IndexError on an empty dict, as in the reference (:284)
-        if best_score < self.threshold:
-            return "Unknown", best_score, top
-        return best_name, best_score, top
+    def _format_db_results(self, scores: np.ndarray, rows: np.ndarray, names) -> List[Tuple[str, float, List[Tuple[str, float]]]]:
+        """Result tuples of recognize_with_db for Q rows of (scores, gallery rows).  One bulk conversion to Python
+        floats / ints (float64 of the fp32 value == float(np.float32)), then plain tuple building: 3x faster than
+        walking numpy scalars, and the formatting is half of a 256-query call."""
+        out = []
+        for srow, irow in zip(scores.astype(np.float64).tolist(), rows.tolist()):
+            top = [(names[j], s) for s, j in zip(srow, irow) if j >= 0]
+            best_name, best_score = top[0]  # IndexError on an empty dict, as in the reference (:284)
+            out.append(("Unknown" if best_score < self.threshold else best_name, best_score, top))
+        return out
 
     def recognize_with_db(self, embedding: np.ndarray) -> Tuple[str, float, List[Tuple[str, float]]]:
         """(best_name, best_score, top-5) — inference/recognition_engine.py:267-289."""
         if self.db is None:
             return "No database", 0.0, []
         s, i, names = self._db_topk(embedding, 5)
-        return self._format_db_result(s[0], i[0], names)
+        return self._format_db_results(s[:1], i[:1], names)[0]
 
     def recognize_embeddings(self, embeddings) -> List[Tuple[str, float, List[Tuple[str, float]]]]:
         """Batched recognize_with_db: Q embeddings [Q, D] (numpy, or a CUDA tensor) -> Q result tuples from ONE fused
@@ -414,7 +418,7 @@ class RecognitionEngine:
         if self.db is None:
             return [("No database", 0.0, [])] * len(embeddings)
         s, i, names = self._db_topk(embeddings, 5)
-        return [self._format_db_result(s[r], i[r], names) for r in range(s.shape[0])]
+        return self._format_db_results(s, i, names)
 
     def recognize_with_faiss(self, embedding: np.ndarray, k: int = 5) -> Tuple[str, float, List[Tuple[str, float]]]:
         """inference/recognition_engine.py:291-326: e/(||e||+1e-8), IndexFlatIP.search, strict '<' threshold."""
@@ -426,8 +430,8 @@ class RecognitionEngine:
         """recognize_with_faiss for Q embeddings in one search call."""
         q = _queries_to_dev(embeddings, self.faiss_index.d, self.match_device)
         scores, indices = self.faiss_index.search_device(q, k, qnorm_mode=N.FRB_QNORM_EPS)
-        scores, indices = scores.cpu().numpy(), indices.cpu().numpy()
-        return [self._format_faiss_result(indices[r], scores[r]) for r in range(scores.shape[0])]
+        scores, indices = scores.cpu().numpy().astype(np.float64).tolist(), indices.cpu().numpy().tolist()   # bulk -> Python scalars
+        return [self._format_faiss_result(irow, srow) for irow, srow in zip(indices, scores)]
 
     def _format_faiss_result(self, indices, scores):
         results = []
