@@ -14,6 +14,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
 
 
+def pytest_sessionstart(session):
+    """A fresh clone has no libfrb200.so (built files are git-ignored): build it once with the same recipe as
+    __graft_entry__.build() so the C-ABI symbol test and the host-logic tests can load it (nvcc cross-compiles sm_100a
+    without a GPU).  The package itself never builds or falls back: importing it without the library raises."""
+    lib = os.path.join(ROOT, "facerecognition_b200", "libfrb200.so")
+    if os.path.exists(lib):
+        return
+    import shutil
+    import subprocess
+    if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        return                                         # the tests that need the library will say so
+    print("\n[conftest] libfrb200.so is missing: building it (make -C facerecognition_b200/csrc, about a minute)", flush=True)
+    subprocess.run(["make", "-C", os.path.join(ROOT, "facerecognition_b200", "csrc"), "-j8"], check=True,
+                   stdout=subprocess.DEVNULL)
+
+
 def pytest_collection_modifyitems(config, items):
     """GPU tests fail loudly (not skip) when selected on a box without a GPU only if FRB_REQUIRE_GPU=1;
     otherwise they are skipped so a plain `pytest tests/` works on the CPU box."""
