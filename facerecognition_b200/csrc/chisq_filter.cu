@@ -320,7 +320,7 @@ chisq_filter_kernel(const __grid_constant__ CUtensorMap tmap_f, const CfParams p
 // One CTA per query: feat[q][bin][0..7] = v(count), window[q] = 2 (e_tab + e_acc) + e_scan, and the per-query filter
 // state is reset (best = -inf, cnt = 0, flag = 0).
 __global__ void __launch_bounds__(256)
-chisq_feat_kernel(const uint16_t *__restrict__ qhist, int hist_len, const uint4 *__restrict__ v_table,
+chisq_feat_kernel(const uint16_t *__restrict__ qhist, int hist_len, int cell_px, int *__restrict__ stats, const uint4 *__restrict__ v_table,
                   const float *__restrict__ emax, const float *__restrict__ absmax, float acc_rel, uint4 *__restrict__ feat,
                   float *__restrict__ window, float *__restrict__ qtot, float *__restrict__ best, int *__restrict__ cnt,
                   int *__restrict__ flag)
@@ -330,9 +330,13 @@ chisq_feat_kernel(const uint16_t *__restrict__ qhist, int hist_len, const uint4 
     const uint16_t *h = qhist + q * hist_len;
     uint4 *out = feat + q * hist_len;
     float e = 0.f, a = 0.f, tot = 0.f;
+    int invalid = 0;
     for (int j = threadIdx.x; j < hist_len; j += 256) {
         int c = h[j];
-        c = c < kCfTableRows ? c : kCfTableRows - 1;   // a count above cell_px cannot occur in a valid histogram
+        // a count above cell_px cannot occur in a histogram of cells with cell_px pixels; the tables and their bound do
+        // not cover it, so such a query is answered by the exact scan (flag below)
+        invalid |= c > cell_px;
+        c = c < kCfTableRows ? c : kCfTableRows - 1;
         out[j] = __ldg(v_table + c);
         e += emax[c];
         a += absmax[c];
@@ -349,7 +353,7 @@ chisq_feat_kernel(const uint16_t *__restrict__ qhist, int hist_len, const uint4 
         s_red[1][threadIdx.x >> 5] = a;
         s_red[2][threadIdx.x >> 5] = tot;
     }
-    __syncthreads();
+    invalid = __syncthreads_or(invalid);
     if (threadIdx.x == 0) {
         float es = 0.f, as = 0.f, ts = 0.f;
         for (int w = 0; w < 8; w++) { es += s_red[0][w]; as += s_red[1][w]; ts += s_red[2][w]; }
@@ -359,7 +363,8 @@ chisq_feat_kernel(const uint16_t *__restrict__ qhist, int hist_len, const uint4 
         qtot[q] = ts;                                   // exact: an integer below 2^24
         best[q] = -INFINITY;
         cnt[q] = 0;
-        flag[q] = 0;
+        flag[q] = invalid ? 1 : 0;
+        if (invalid && stats) atomicAdd(stats + 0, 1);
     }
 }
 
@@ -374,6 +379,10 @@ chisq_survivor_kernel(int64_t n_query, int cap, const float *__restrict__ best, 
     const int64_t q = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (q >= n_query) return;
+    if (flag[q]) {                       // already flagged (invalid query histogram): the exact scan answers it
+        if (lane == 0) list_cnt[q] = 0;
+        return;
+    }
     const int n_raw = raw_cnt[q];
     if (n_raw > cap) {
         if (lane == 0) {
@@ -695,7 +704,7 @@ int frb_chisq_top1_filtered_g8(const uint16_t *q_hist, int64_t n_query, const ui
     for (int64_t q0 = 0; q0 < n_query; q0 += pl.pass_q) {
         const int64_t nq = (n_query - q0) < pl.pass_q ? (n_query - q0) : pl.pass_q;
         const uint16_t *qh = q_hist + q0 * hist_len;
-        chisq_feat_kernel<<<(unsigned)nq, 256, 0, st>>>(qh, hist_len, tb.d_v, tb.d_emax, tb.d_absmax, cf_acc_rel(), feat, window, qtot,
+        chisq_feat_kernel<<<(unsigned)nq, 256, 0, st>>>(qh, hist_len, cell_px, stats, tb.d_v, tb.d_emax, tb.d_absmax, cf_acc_rel(), feat, window, qtot,
                                                        best, cnt, flag);
         FRB_LAUNCH_OK("chisq_feat_kernel");
         if (n_gallery > 0) {

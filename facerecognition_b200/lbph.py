@@ -173,6 +173,9 @@ class LBPHFaceRecognizer:
         assert hist_u16.dtype in (torch.uint16, torch.uint8) and hist_u16.dim() == 2 and hist_u16.shape[1] == self.hist_len
         n = hist_u16.shape[0]
         hist = hist_u16.contiguous() if hist_u16.dtype == torch.uint8 else ops.compact_histograms(hist_u16.contiguous(), int(cell_px))
+        if n and hist.dtype == torch.uint8 and int(hist.max()) > int(cell_px):
+            # the tensor-core filter's tables (and its error bound) cover counts 0..cell_px, all a cell can hold
+            raise ValueError(f"histogram counts up to {int(hist.max())} with cell_px = {int(cell_px)}: a cell cannot hold more than cell_px codes")
         rows = torch.arange(row_offset, row_offset + n, dtype=torch.int64, device=hist_u16.device)
         self._groups = [_Group(int(cell_px), hist, rows)] if n else []
         self._labels = np.asarray(labels).astype(np.int32).reshape(-1)

@@ -303,8 +303,10 @@ int frb_chisq_dist_g8(const uint16_t *q_hist_dev, int64_t n_query, int q_cell_px
  *   length 8 * hist_len; the table error bounds |approx - exact| per query for EVERY row, rows outside the resulting
  *   window around the best approximate score cannot win, and the survivors are re-scored with the exact kernel's own
  *   arithmetic.  A query whose survivor list overflows is answered by the plain exact scan inside the same call.
- * Needs equal cell sizes on both sides (cell_px <= 255, u8 gallery), hist_len % 16 == 0, hist_len <= 16384.  Rows need
- * not sum to the same total (LBPH rows always do): the kernel ranks by sum_j f - (row total) / 4.
+ * Needs equal cell sizes on both sides (cell_px <= 255, u8 gallery), hist_len % 16 == 0, hist_len <= 16384, and every
+ * count (gallery and query) <= cell_px — all a cell of cell_px pixels can hold; the feature tables and their error bound
+ * cover exactly 0..cell_px, larger counts give undefined candidates (not checked per call).  Rows need not sum to the
+ * same total (LBPH rows always do): the kernel ranks by sum_j f - (row total) / 4.
  *   stats_dev  int32 [4] or NULL, incremented: [0] queries answered by the exact fallback, [1] survivors re-scored,
  *              [2] raw candidates appended by the filter kernel, [3] re-scored rows whose filter score missed the exact
  *              one by more than the bound (audit of every survivor; such a query is re-answered by the exact scan).

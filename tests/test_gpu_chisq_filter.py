@@ -207,6 +207,17 @@ def test_more_queries_than_one_pass_and_edge_cell_sizes():
     d, i = ops.chisq_top1_filtered(q255, g255, 100)          # counts up to 255 declared as cell_px = 100: defined behaviour, no fault
     torch.cuda.synchronize()
     assert i.shape == (20, 1)
+    # a QUERY count above cell_px is outside the tables and their bound: such queries get the exact scan inside the call
+    gal, px = hists(faces_gpu(9000, 112, 21))
+    g8 = ops.compact_histograms(gal, px)
+    qn = gal[:40].cpu().numpy().copy()
+    qn[::2, 7] = px + 30
+    qh = torch.from_numpy(qn).cuda()
+    stats = torch.zeros(4, dtype=torch.int32, device="cuda")
+    d, i = ops.chisq_top1_filtered(qh, g8, px, stats=stats)
+    want_d, want_i = exact_top1(qh, g8, px)
+    assert torch.equal(i, want_i) and torch.equal(d.view(torch.int32), want_d.view(torch.int32))
+    assert int(stats[0]) == 20 and int(stats[3]) == 0
 
 
 def test_faces_with_flat_and_saturated_regions():
