@@ -1,5 +1,5 @@
 """One small program per ncu capture (round 2): python profiles/run_ncu_targets.py <target>
-targets: tc | chisq_q1_u16 | chisq_q1_u8 | chisq_b_u16 | chisq_b_u8 | filter | lbp | lbp8 | resize
+targets: tc | tc16 | chisq_q1_u16 | chisq_q1_u8 | chisq_b_u16 | chisq_b_u8 | filter | lbp | lbp8 | resize
 Each runs the op 3 times (2 warm-up calls + the one to capture with `-s <2 x launches per call> -c <launches per call>`)."""
 import os
 import sys
@@ -34,7 +34,12 @@ def run(fn, label, work=None):
     return out
 
 
-if target == "tc":
+if target == "tc16":
+    # the first pass of the exact-fp32 path: fp16 operands, 16-slot lists through the CTA-pair kernel's queued admission
+    gal = ops.normalize_rows(torch.randn((1_000_000, 512), generator=g, device="cuda"), NV.FRB_QNORM_CLAMP, torch.float16)
+    q = gal[torch.randint(0, 1_000_000, (4096,), generator=g, device="cuda")].float() + 0.03 * torch.randn((4096, 512), generator=g, device="cuda")
+    run(lambda: ops.cosine_topk(q, gal, 16, qnorm_mode=NV.FRB_QNORM_CLAMP), "cosine_tc fp16 4096 x 1M k=16")
+elif target == "tc":
     gal = ops.normalize_rows(torch.randn((1_000_000, 512), generator=g, device="cuda"), NV.FRB_QNORM_CLAMP, torch.bfloat16)
     q = gal[torch.randint(0, 1_000_000, (4096,), generator=g, device="cuda")].float() + 0.03 * torch.randn((4096, 512), generator=g, device="cuda")
     run(lambda: ops.cosine_topk(q, gal, 5, qnorm_mode=NV.FRB_QNORM_CLAMP), "cosine_tc 4096 x 1M k=5")
