@@ -351,18 +351,26 @@ __global__ void __launch_bounds__(256) resize_linear_kernel(const uint8_t *__res
             continue;
         }
         int r = threadIdx.x;
-        for (; r + nthr < n; r += 2 * nthr) {   // two pixels per trip: r and r + nthr
-            int dx2 = dx + step_x, dy2 = dy + step_y;
-            if (dx2 >= dst_cols) { dx2 -= dst_cols; dy2++; }
-            const ResizeColTap ax = tx[dx], bx = tx[dx2];
-            const ResizeRowTap ay = ty[dy], by = ty[dy2];
-            resize_pixel<C, GRAY>(img, ax, ay, out + (int64_t)r * OC);
-            resize_pixel<C, GRAY>(img, bx, by, out + (int64_t)(r + nthr) * OC);
-            dx = dx2 + step_x;
-            dy = dy2 + step_y;
+        constexpr int P = 4;                          // pixels per trip (r, r + nthr, ...): 48 byte loads in flight (2: 0.458 ms, 4: 0.418, 8: 0.480)
+        for (; r + (P - 1) * nthr < n; r += P * nthr) {
+            int px[P], py[P];
+#pragma unroll
+            for (int u = 0; u < P; u++) {
+                px[u] = dx;
+                py[u] = dy;
+                dx += step_x;
+                dy += step_y;
+                if (dx >= dst_cols) { dx -= dst_cols; dy++; }
+            }
+#pragma unroll
+            for (int u = 0; u < P; u++) resize_pixel<C, GRAY>(img, tx[px[u]], ty[py[u]], out + (int64_t)(r + u * nthr) * OC);
+        }
+        for (; r < n; r += nthr) {
+            resize_pixel<C, GRAY>(img, tx[dx], ty[dy], out + (int64_t)r * OC);
+            dx += step_x;
+            dy += step_y;
             if (dx >= dst_cols) { dx -= dst_cols; dy++; }
         }
-        if (r < n) resize_pixel<C, GRAY>(img, tx[dx], ty[dy], out + (int64_t)r * OC);
     }
 }
 
