@@ -910,6 +910,10 @@ static TcPlan tc_plan(int64_t nq, int64_t ng, int dim, int k)
         if (!long_units && tiles_per_cta >= 48 && !(bal && bal[0] == '0'))
             want_groups = tc_balanced_groups(main_tiles, pl.n_qtiles, sms, want_groups);
     }
+    {
+        const char *ut = getenv("FRB_TC_UNIT_TILES");    // experiments: force the unit length (gallery tiles per group)
+        if (ut && atoll(ut) > 0) want_groups = (main_tiles + atoll(ut) - 1) / atoll(ut);
+    }
     tc_split(warm_tiles, pl.n_tiles, want_groups, pl.warm.n_groups, &pl.main);
     pl.n_groups = pl.warm.n_groups + pl.main.n_groups;
     pl.n_qtiles = real_qtiles;
