@@ -20,6 +20,10 @@
 // Shared memory: A = the unit's 128 x dim query tile (dim/64 k-blocks of 16 KB, resident for the unit),
 // B = ring of 32 KB stages (256 rows x 64 of K), both 128-byte swizzled K-major as written by TMA.
 // TMEM: 2 accumulator stages x 256 columns, so the epilogue of tile t overlaps the MMAs of tile t+1.
+//
+// Two kernels share the epilogue code: cosine_tc_kernel (one CTA per unit, described above; batches of up to 128
+// queries) and cosine_tc_pair_kernel (tcgen05.mma.cta_group::2: two CTAs of a cluster share every MMA and each loads
+// half of the gallery tile; every larger batch, all list lengths).  Operands are bf16 or fp16 (launch parameter).
 #include "frb_common.cuh"
 
 #include <stdlib.h>
@@ -832,7 +836,7 @@ static int64_t tc_balanced_groups(int64_t tiles, int64_t n_qt, int P, int64_t fa
     return best;
 }
 
-// CTA pairs (cosine_tc_pair_kernel) serve lists of up to 16 from two query tiles up; FRB_TC_PAIR=0 keeps one CTA per tile
+// CTA pairs (cosine_tc_pair_kernel) serve every list length from two query tiles up; FRB_TC_PAIR=0 keeps one CTA per tile
 static int tc_pair_max_k()
 {
     const char *m = getenv("FRB_TC_PAIR_MAXK");                         // experiments: longest list the pair kernel serves
