@@ -646,18 +646,37 @@ def main():
         # timed region (a later pass under the power cap can run a few per cent slower than the timed one).
         for _ in range(3):                       # torch.cuda.graph() empties the caching allocator: re-warm the eager path
             search.search(q_dev, TOPK, graph=False)
-        NV.profile_enable(True)
-        NV.profile_read(NV.K_COSINE_TC)
-        if world == 1:
-            total_ms, s, i = timed_steps(q_dev, args.steps, graph=False)
-            eager_ms = total_ms
-        else:
-            NV.profile_enable(False)
-            total_ms, s, i = timed_steps(q_dev, args.steps)
+        def measure():
             NV.profile_enable(True)
-            eager_ms, _, _ = timed_steps(q_dev, args.steps, graph=False)
-        k_ms, k_n = NV.profile_read(NV.K_COSINE_TC)
-        NV.profile_enable(False)
+            NV.profile_read(NV.K_COSINE_TC)
+            if world == 1:
+                total, s_, i_ = timed_steps(q_dev, args.steps, graph=False)
+                eager = total
+            else:
+                NV.profile_enable(False)
+                total, s_, i_ = timed_steps(q_dev, args.steps)
+                NV.profile_enable(True)
+                eager, _, _ = timed_steps(q_dev, args.steps, graph=False)
+            km, kn = NV.profile_read(NV.K_COSINE_TC)
+            NV.profile_enable(False)
+            return total, eager, km, kn, s_, i_
+
+        total_ms, eager_ms, k_ms, k_n, s, i = measure()
+        # a timed region that saw a hardware / thermal slowdown on any rank is measured again, once
+        remeasured = None
+        seen = set(clocks.summary()["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if os.environ.get("FRB_BENCH_FORCE_REMEASURE") == "1":          # exercises this path on a healthy box
+            seen = seen | {"forced"}
+        again = torch.tensor([1 if seen else 0], device=device)
+        if world > 1:
+            dist.all_reduce(again, op=dist.ReduceOp.MAX)
+        if int(again.item()):
+            remeasured = {"first_reasons": sorted(seen), "first_value": n_query * args.steps / (total_ms * 1e-3)}
+            time.sleep(5.0)
+            clocks.rows.clear()
+            for _ in range(warmup):
+                search.search(q_dev, TOPK, graph=use_graph and world > 1)
+            total_ms, eager_ms, k_ms, k_n, s, i = measure()
         value = n_query * args.steps / (total_ms * 1e-3)
         # the step launches cosine_tc_pair_kernel once (the single-CTA kernels, <= 128 queries, add a threshold warm-up pass);
         # achieved = the step's algorithmic flops / the summed device time of its cosine_tc launches
@@ -769,7 +788,7 @@ def main():
                      "frac_of_burst": achieved / peaks["bf16_tflops"], "frac_of_sustained": achieved / peaks["bf16_tflops_sustained"],
                      "peak_source": peaks["source"] + (", bf16 SUSTAINED figure: the timed steps ran power-capped (median SM clock < 90 % of max, see clocks) after >= 1 s of load"
                                                        if sustained else ", bf16 BURST figure: the SM clock stayed near its maximum during the run")},
-        "clocks": clock_summary,
+        "clocks": {**clock_summary, **({"remeasured": remeasured} if remeasured else {})},
         "planted_top1_correct": bool(okt.item()),
     }
     if strong:
