@@ -330,7 +330,11 @@ def lbph_leg(torch, ops, NV, device, peaks, flush):
                                                "frac": tf / FP32_PEAK_TFLOPS, **ncu_traffic("chisq_kernel"),
                                                "note": "SURVEY §8d: 65536 flop per (query, row) pair against the measured FP32 peak "
                                                        "(72 TFLOP/s, profiles/micro/fp32_peak.cu); the gallery chunk is shared through L2, "
-                                                       "so DRAM traffic (`traffic`) is a small fraction of pairs x 16 KiB and HBM is not the bound"}}
+                                                       "so DRAM traffic (`traffic`) is a small fraction of pairs x 16 KiB and HBM is not the bound. "
+                                                       "The peak counts an FMA as 2 flop while the exact formula issues ~5 FP32 instructions + half a "
+                                                       "reciprocal per bin, few of them FMAs: ncu has the FP32 pipe 61 % and the MUFU pipe 48 % busy "
+                                                       "(profiles/r2_prof_chisq_b_u8_r2.txt). Batches of 16+ predicts do not run this kernel: they go "
+                                                       "through the tensor-core filter (extract_match_c5_share, c5)"}}
     # front end: interleaved BGR video crops -> gray (3 B read + 1 B written per pixel)
     n_fr = 32768
     bgr = torch.randint(0, 256, (n_fr, 112, 112, 3), generator=gen, device=device, dtype=torch.uint8)
