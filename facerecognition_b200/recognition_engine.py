@@ -118,6 +118,7 @@ class DeviceGallery:
         """bounds = (lo, hi): keep only rows [lo, hi) on this device (one shard of an identity-sharded gallery); `names`
         always lists every identity and the searches report GLOBAL row ids (idx_base = lo)."""
         self.names: List[str] = list(db.keys())
+        self._names_obj: Optional[np.ndarray] = None      # object array of the names, built on the first batched result
         self.lo, self.hi = bounds if bounds is not None else (0, len(self.names))
         mine = self.names[self.lo:self.hi]
         if self.names:
@@ -399,6 +400,14 @@ class RecognitionEngine:
         floats / ints (float64 of the fp32 value == float(np.float32)), then plain tuple building: 3x faster than
         walking numpy scalars, and the formatting is half of a 256-query call."""
         out = []
+        g = self._gallery
+        if rows.shape[0] > 4 and rows.size and int(rows.min()) >= 0 and g is not None and names is g.names:
+            # whole lists (a gallery of at least 5 rows): the names of all rows in one object-array gather
+            if g._names_obj is None:
+                g._names_obj = np.array(names, dtype=object)
+            for nrow, srow in zip(g._names_obj[rows].tolist(), scores.astype(np.float64).tolist()):
+                out.append(("Unknown" if srow[0] < self.threshold else nrow[0], srow[0], list(zip(nrow, srow))))
+            return out
         for srow, irow in zip(scores.astype(np.float64).tolist(), rows.tolist()):
             top = [(names[j], s) for s, j in zip(srow, irow) if j >= 0]
             best_name, best_score = top[0]  # IndexError on an empty dict, as in the reference (:284)
