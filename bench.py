@@ -577,6 +577,7 @@ def main():
     ap.add_argument("--no-c4", action="store_true", help="skip configs[3] (100M-row sharded gallery)")
     ap.add_argument("--no-c5", action="store_true", help="skip configs[4] (LBPH 1024 frames vs 1M sharded histograms)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying its CUDA graph")
+    ap.add_argument("--no-balance", action="store_true", help="equal gallery shards instead of shards proportional to each GPU's measured speed")
     ap.add_argument("--min-warm-seconds", type=float, default=1.0,
                     help="keep warming until this much time has passed under load (clock samples); 0 for ncu launch lists")
     args = ap.parse_args()
@@ -603,7 +604,30 @@ def main():
     warmup = max(args.warmup, 3)
     n_gallery, q_per_gpu = args.gallery, args.queries
     n_query = q_per_gpu * world                      # weak scaling: the batch grows with the job
-    lo, hi = shard_bounds(n_gallery, world, rank)
+    # Several GPUs: a sharded step waits for its slowest rank, and under the power cap the GPUs of one box differ by
+    # 10-30 % (profiles/r2_rank_skew.txt).  A 2 s probe run on all ranks at once measures each GPU's rate and the gallery
+    # rows are split in proportion (sharded.balanced_bounds); the answer does not depend on the split.
+    balance = None
+
+    def bounds_of(n_rows):
+        return shard_bounds(n_rows, world, rank)
+
+    if world > 1 and not args.no_balance:
+        from facerecognition_b200.sharded import balanced_bounds, measure_rank_weights
+        gen_p = torch.Generator(device=device).manual_seed(7)
+        probe_g = ops.normalize_rows(torch.randn((131072, DIM), generator=gen_p, device=device), NV.FRB_QNORM_CLAMP, torch.bfloat16)
+        probe_q = torch.randn((N_QUERY, DIM), generator=gen_p, device=device)
+        weights = measure_rank_weights(lambda: ops.cosine_topk(probe_q, probe_g, TOPK, qnorm_mode=NV.FRB_QNORM_CLAMP),
+                                       torch.cuda.synchronize, 2.0)
+        del probe_g, probe_q
+
+        def bounds_of(n_rows):                                              # noqa: F811
+            return balanced_bounds(n_rows, weights, rank)
+
+        balance = {"weights": [round(w, 4) for w in weights],
+                   "note": "gallery rows per rank proportional to the rank's measured rate on a 2 s probe (4096 x 131072 bf16 top-5 on "
+                           "all ranks at once); applies to the headline, c4 and c5 shards; --no-balance gives equal shards"}
+    lo, hi = bounds_of(n_gallery)
     shard, q_dev, src, n_rand = make_gallery_and_queries(torch, ops, NV, device, lo, hi, n_gallery, n_query)
     search = cosine_sharded(shard, lo, qnorm_mode=NV.FRB_QNORM_CLAMP)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
@@ -797,6 +821,9 @@ def main():
     }
     if strong:
         line["strong"] = strong
+    if balance:
+        balance["rows_this_rank"] = hi - lo
+        line["shard_balance"] = balance
     if world > 1:
         # (kept out of `config`, which must read the same in the reference arm)
         line["exchange"] = ("one fused kernel over NVLink peer memory (frb_exchange_topk_merge: peer stores + flags + merge)"
@@ -829,7 +856,7 @@ def main():
             line["engine_e2e"] = {"error": repr(e)}
     if not args.no_c5:
         try:
-            lo5, hi5 = shard_bounds(C5_ROWS, world, rank)
+            lo5, hi5 = bounds_of(C5_ROWS)
             c5 = c5_step(torch, ops, NV, device, peaks, hi5 - lo5, lo5,
                          (lambda g8, px: chisq_sharded(g8, px, lo5)) if world > 1 else None)
             got, want = c5.pop("planted_top1")
@@ -850,7 +877,7 @@ def main():
         torch.cuda.empty_cache()
     if not args.no_c4:
         try:
-            line["c4"] = c4_leg(torch, dist, ops, NV, device, peaks, world, rank, cosine_sharded, shard_bounds)
+            line["c4"] = c4_leg(torch, dist, ops, NV, device, peaks, world, rank, cosine_sharded, lambda n, w, r: bounds_of(n))
         except Exception as e:
             line["c4"] = {"error": repr(e)}
     if world > 1:

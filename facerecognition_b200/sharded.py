@@ -27,6 +27,53 @@ def shard_bounds(n_rows: int, world_size: int, rank: int) -> Tuple[int, int]:
     return lo, min(lo + per, n_rows)
 
 
+def balanced_bounds(n_rows: int, weights, rank: int, align: int = 256) -> Tuple[int, int]:
+    """Rows [lo, hi) of `rank` when rank r's share of the gallery is proportional to weights[r] — for boxes whose GPUs
+    do not run at the same speed (under the power cap the GPUs of one chassis differ by 10-30 %, and a sharded step
+    waits for its slowest rank: profiles/r2_rank_skew.txt).  Inner boundaries are rounded to `align` rows (a gallery
+    tile); every row belongs to exactly one rank; answers do not depend on the split (global row ids, ties -> lowest)."""
+    w = [max(float(x), 0.0) for x in weights]
+    total = sum(w)
+    if total <= 0.0:
+        return shard_bounds(n_rows, len(w), rank)
+    edges, cum = [0], 0.0
+    for r in range(len(w) - 1):
+        cum += w[r]
+        e = int(round(n_rows * cum / total / align)) * align
+        edges.append(min(max(e, edges[-1]), n_rows))
+    edges.append(n_rows)
+    return edges[rank], edges[rank + 1]
+
+
+def measure_rank_weights(step: Callable[[], None], sync: Callable[[], None], seconds: float = 1.0,
+                         group: Optional[dist.ProcessGroup] = None, clamp: float = 0.3):
+    """Collective calibration for balanced_bounds: every rank runs `step` (the same probe workload on each GPU) back to
+    back for `seconds` at the same time — so each GPU is measured in the state a balanced job keeps it in, busy all the
+    time — and the ranks' steps-per-second are all-gathered.  Returns one weight per rank, mean 1, limited to
+    1 +- clamp so that a noisy probe cannot starve a rank."""
+    import time
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if world == 1:
+        return [1.0]
+    for _ in range(3):
+        step()
+    sync()
+    dist.barrier(group=group)
+    t0, n = time.perf_counter(), 0
+    while True:
+        for _ in range(8):
+            step()
+        n += 8
+        sync()
+        if time.perf_counter() - t0 >= seconds:
+            break
+    rate = n / (time.perf_counter() - t0)
+    rates = [None] * world
+    dist.all_gather_object(rates, float(rate), group=group)
+    mean = sum(rates) / world
+    return [min(max(r / mean, 1.0 - clamp), 1.0 + clamp) for r in rates]
+
+
 def _record_layout(n_query: int, k: int) -> Tuple[int, int, int]:
     """Byte layout of one rank's candidate record: ids i64 [Q, k] first, then scores f32 [Q, k], padded to 16."""
     idx_bytes = n_query * k * 8
