@@ -605,7 +605,7 @@ def main():
     n_gallery, q_per_gpu = args.gallery, args.queries
     n_query = q_per_gpu * world                      # weak scaling: the batch grows with the job
     # Several GPUs: a sharded step waits for its slowest rank, and under the power cap the GPUs of one box differ by
-    # 10-30 % (profiles/r2_rank_skew.txt).  A 2 s probe run on all ranks at once measures each GPU's rate and the gallery
+    # 10-30 % (profiles/r2_rank_skew.txt).  A 3 s probe run on all ranks at once measures each GPU's rate and the gallery
     # rows are split in proportion (sharded.balanced_bounds); the answer does not depend on the split.
     balance = None
 
@@ -615,17 +615,17 @@ def main():
     if world > 1 and not args.no_balance:
         from facerecognition_b200.sharded import balanced_bounds, measure_rank_weights
         gen_p = torch.Generator(device=device).manual_seed(7)
-        probe_g = ops.normalize_rows(torch.randn((131072, DIM), generator=gen_p, device=device), NV.FRB_QNORM_CLAMP, torch.bfloat16)
+        probe_g = ops.normalize_rows(torch.randn((N_GALLERY, DIM), generator=gen_p, device=device), NV.FRB_QNORM_CLAMP, torch.bfloat16)
         probe_q = torch.randn((N_QUERY, DIM), generator=gen_p, device=device)
         weights = measure_rank_weights(lambda: ops.cosine_topk(probe_q, probe_g, TOPK, qnorm_mode=NV.FRB_QNORM_CLAMP),
-                                       torch.cuda.synchronize, 2.0)
+                                       torch.cuda.synchronize, 3.0)
         del probe_g, probe_q
 
         def bounds_of(n_rows):                                              # noqa: F811
             return balanced_bounds(n_rows, weights, rank)
 
         balance = {"weights": [round(w, 4) for w in weights],
-                   "note": "gallery rows per rank proportional to the rank's measured rate on a 2 s probe (4096 x 131072 bf16 top-5 on "
+                   "note": "gallery rows per rank proportional to the rank's measured rate on a 3 s probe (4096 x 1M bf16 top-5, back to back, on "
                            "all ranks at once); applies to the headline, c4 and c5 shards; --no-balance gives equal shards"}
     lo, hi = bounds_of(n_gallery)
     shard, q_dev, src, n_rand = make_gallery_and_queries(torch, ops, NV, device, lo, hi, n_gallery, n_query)
