@@ -577,7 +577,8 @@ def main():
     ap.add_argument("--no-c4", action="store_true", help="skip configs[3] (100M-row sharded gallery)")
     ap.add_argument("--no-c5", action="store_true", help="skip configs[4] (LBPH 1024 frames vs 1M sharded histograms)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying its CUDA graph")
-    ap.add_argument("--no-balance", action="store_true", help="equal gallery shards instead of shards proportional to each GPU's measured speed")
+    ap.add_argument("--balance", action="store_true",
+                    help="gallery shards proportional to each GPU's measured rate (3 s calibration probe) instead of equal shards")
     ap.add_argument("--min-warm-seconds", type=float, default=1.0,
                     help="keep warming until this much time has passed under load (clock samples); 0 for ncu launch lists")
     args = ap.parse_args()
@@ -604,15 +605,16 @@ def main():
     warmup = max(args.warmup, 3)
     n_gallery, q_per_gpu = args.gallery, args.queries
     n_query = q_per_gpu * world                      # weak scaling: the batch grows with the job
-    # Several GPUs: a sharded step waits for its slowest rank, and under the power cap the GPUs of one box differ by
-    # 10-30 % (profiles/r2_rank_skew.txt).  A 3 s probe run on all ranks at once measures each GPU's rate and the gallery
-    # rows are split in proportion (sharded.balanced_bounds); the answer does not depend on the split.
+    # Several GPUs: a sharded step waits for its slowest rank, and under the power cap the GPUs of one box can differ by
+    # 10-30 % (profiles/r2_rank_skew.txt).  With --balance a 3 s probe run on all ranks at once measures each GPU's rate
+    # and the gallery rows are split in proportion (sharded.balanced_bounds); the answer does not depend on the split.
+    # Opt-in: validated at 2 and 4 GPUs (no gain on boxes without skew); the default stays the equal split of SURVEY 8(e).
     balance = None
 
     def bounds_of(n_rows):
         return shard_bounds(n_rows, world, rank)
 
-    if world > 1 and not args.no_balance:
+    if world > 1 and args.balance:
         from facerecognition_b200.sharded import balanced_bounds, measure_rank_weights
         gen_p = torch.Generator(device=device).manual_seed(7)
         probe_g = ops.normalize_rows(torch.randn((N_GALLERY, DIM), generator=gen_p, device=device), NV.FRB_QNORM_CLAMP, torch.bfloat16)
@@ -626,7 +628,7 @@ def main():
 
         balance = {"weights": [round(w, 4) for w in weights],
                    "note": "gallery rows per rank proportional to the rank's measured rate on a 3 s probe (4096 x 1M bf16 top-5, back to back, on "
-                           "all ranks at once); applies to the headline, c4 and c5 shards; --no-balance gives equal shards"}
+                           "all ranks at once); applies to the headline, c4 and c5 shards (opt-in: --balance; the default is equal shards)"}
     lo, hi = bounds_of(n_gallery)
     shard, q_dev, src, n_rand = make_gallery_and_queries(torch, ops, NV, device, lo, hi, n_gallery, n_query)
     search = cosine_sharded(shard, lo, qnorm_mode=NV.FRB_QNORM_CLAMP)

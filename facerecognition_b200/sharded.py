@@ -31,7 +31,8 @@ def balanced_bounds(n_rows: int, weights, rank: int, align: int = 256) -> Tuple[
     """Rows [lo, hi) of `rank` when rank r's share of the gallery is proportional to weights[r] — for boxes whose GPUs
     do not run at the same speed (under the power cap the GPUs of one chassis differ by 10-30 %, and a sharded step
     waits for its slowest rank: profiles/r2_rank_skew.txt).  Inner boundaries are rounded to `align` rows (a gallery
-    tile); every row belongs to exactly one rank; answers do not depend on the split (global row ids, ties -> lowest)."""
+    tile); every row belongs to exactly one rank; answers do not depend on the split (global row ids, ties -> lowest).
+    Used by `bench.py --balance` (opt-in; exercised at 2 and 4 GPUs); the engine classes shard equally (shard_bounds)."""
     w = [max(float(x), 0.0) for x in weights]
     total = sum(w)
     if total <= 0.0:
