@@ -148,6 +148,25 @@ class ClockSampler:
                 "reasons": [n for n, bit in self.REASONS if why & bit], "samples": len(sm)}
 
 
+def warm_in_lockstep(step, sync, min_steps, min_seconds, any_rank_wants_more):
+    """Warm-up in rounds of 16 steps until >= min_steps steps have run and >= min_seconds have passed, WITH THE DECISION
+    TO STOP AGREED BETWEEN THE RANKS: a sharded step ends in the exchange, which waits for every rank, so all ranks must
+    run the same number of steps.  (Each rank deciding on its own clock — as this loop did before — stops the ranks in
+    different rounds whenever a round boundary falls between their start times; the rank that runs one round more then
+    spins in the exchange until its ~10 s time-outs, and the epochs stay out of step for the rest of the run.)
+    any_rank_wants_more(flag) -> bool is the all-reduce (max) of the ranks' flags; identity on one GPU.  Returns the
+    number of steps run (the same on every rank)."""
+    t0, done = time.perf_counter(), 0
+    while True:
+        for _ in range(16):
+            step()
+        done += 16
+        sync()
+        more = done < min_steps or time.perf_counter() - t0 < min_seconds
+        if not any_rank_wants_more(bool(more)):
+            return done
+
+
 def make_gallery_and_queries(torch, ops, NV, device, lo, hi, n_gallery, n_query):
     """This rank's bf16 shard [lo, hi) of the logical gallery + the full replicated fp32 query batch."""
     gen_q = torch.Generator(device=device).manual_seed(4321)
@@ -659,14 +678,29 @@ def main():
 
     with ClockSampler(local_rank) as clocks:
         # ---- device-resident leg: inputs already in HBM ---------------------------------------------
-        t_w = time.perf_counter()
-        done = 0
-        while done < warmup or time.perf_counter() - t_w < args.min_warm_seconds:      # >= W steps and >= 1 s under load (clock samples)
-            s, i = search.search(q_dev, TOPK, graph=use_graph and world > 1)
-            done += 1
-            if done % 16 == 0:
-                torch.cuda.synchronize()
+        def any_rank_wants_more(flag):
+            if world == 1:
+                return flag
+            t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return bool(int(t.item()))
+
+        warm_out = {}
+
+        def warm_step():
+            warm_out["s"], warm_out["i"] = search.search(q_dev, TOPK, graph=use_graph and world > 1)
+
+        # >= W steps and >= 1 s under load (clock samples); every rank runs the same number of steps
+        warm_in_lockstep(warm_step, torch.cuda.synchronize, warmup, args.min_warm_seconds, any_rank_wants_more)
+        s, i = warm_out["s"], warm_out["i"]
         barrier()
+        if world > 1 and search._exchange is not None:
+            # belt and braces: a rank that missed a step would leave the exchange epochs out of step (10 s per step from
+            # then on); the status word says so, and resync() (collective) restarts the epochs
+            missed = torch.tensor([search._exchange.status()[0]], dtype=torch.int32, device=device)
+            dist.all_reduce(missed, op=dist.ReduceOp.MAX)
+            if int(missed.item()):
+                search.resync()
         # correctness of what is being timed: planted queries must come back as their source row
         ok = bool(torch.equal(i[n_rand:, 0], src[n_rand:]))
         # One GPU: the timed steps are launched kernel by kernel, so libfrb200 brackets every cosine_tc_kernel launch of the

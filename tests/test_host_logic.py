@@ -98,6 +98,21 @@ def _worker_body(rank, world, port, q_out):
     from facerecognition_b200.sharded import measure_rank_weights
     w = measure_rank_weights(lambda: time.sleep(0.003 if rank == 1 else 0.001), lambda: None, seconds=0.3)
     ok = ok and len(w) == world and w[0] > w[1] and all(0.7 - 1e-9 <= x <= 1.3 + 1e-9 for x in w)
+    # bench.py's warm-up: ranks that start at different times (and whose steps do not take equally long here, unlike a
+    # sharded step) must still run the SAME number of steps, or one of them would wait in the exchange for a step its
+    # peer never launches
+    import bench
+
+    def any_rank_wants_more(flag):
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return bool(int(t.item()))
+
+    time.sleep(0.04 * rank)
+    n = bench.warm_in_lockstep(lambda: time.sleep(0.0004 * (1 + rank)), lambda: None, 3, 0.12, any_rank_wants_more)
+    counts = [None] * world
+    dist.all_gather_object(counts, n)
+    ok = ok and len(set(counts)) == 1 and n >= 16 and n % 16 == 0
     q_out.put((rank, ok))
     dist.destroy_process_group()
 
