@@ -316,3 +316,32 @@ def test_lbph_cell_size_inference_from_stored_float_rows():
         _infer_cell_px(np.full(16384, 0.3, np.float32))
     with pytest.raises(ValueError):
         _infer_cell_px(np.zeros(16384, np.float32))
+
+
+def test_batched_result_formatting_fast_path_equals_the_row_by_row_form():
+    """RecognitionEngine._format_db_results: the bulk form (one object-array gather of the names) must build exactly the
+    tuples of the reference's per-row form (recognition_engine.py:282-289), incl. 'Unknown' below the threshold and lists
+    cut short by -1 padding (galleries with fewer than 5 rows)."""
+    from facerecognition_b200.recognition_engine import RecognitionEngine
+
+    class _G:
+        pass
+
+    eng = RecognitionEngine.__new__(RecognitionEngine)
+    eng.threshold = 0.5
+    g = _G()
+    g.names, g._names_obj = [f"id_{i:03d}" for i in range(50)], None
+    rng = np.random.default_rng(0)
+    s = np.sort(rng.random((9, 5)).astype(np.float32))[:, ::-1].copy()
+    r = rng.integers(0, 50, (9, 5))
+    eng._gallery = g
+    fast = eng._format_db_results(s, r, g.names)
+    eng._gallery = None
+    slow = eng._format_db_results(s, r, g.names)
+    assert fast == slow and g._names_obj is not None
+    assert {x[0] == "Unknown" for x in fast} == {True, False}
+    assert all(isinstance(x[1], float) and len(x[2]) == 5 for x in fast)
+    r[3, 4] = -1
+    eng._gallery = g
+    padded = eng._format_db_results(s, r, g.names)
+    assert len(padded[3][2]) == 4 and padded[2] == slow[2]
