@@ -328,7 +328,7 @@ def test_batched_result_formatting_fast_path_equals_the_row_by_row_form():
         pass
 
     eng = RecognitionEngine.__new__(RecognitionEngine)
-    eng.threshold = 0.5
+    eng.threshold = 0.85
     g = _G()
     g.names, g._names_obj = [f"id_{i:03d}" for i in range(50)], None
     rng = np.random.default_rng(0)
